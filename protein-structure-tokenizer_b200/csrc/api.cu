@@ -1,0 +1,308 @@
+// C-ABI entry points (include/pst_abi.h): model handle, workspace carving, call sequencing.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "pst_internal.h"
+
+int pst_prepare_tc_weights(pst_model* m);  // edge_mlp_tc.cu
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+bool config_ok(const pst_config* c) {
+  if (!c || c->abi_version != PST_ABI_VERSION) return false;
+  if (c->seq_max_size < 1 || c->seq_max_size > 8192) return false;
+  if (c->max_len < 1 || c->max_len > c->seq_max_size) return false;
+  if (c->num_neighbor < 1 || c->num_neighbor > 64) return false;
+  if (c->downsampling_ratio < 1 || c->downsampling_ratio > 8) return false;
+  if (c->max_out_len < 1 || c->max_out_len < c->max_len / c->downsampling_ratio) return false;
+  if (c->num_levels < 1 || c->num_levels > PST_MAX_LEVELS) return false;
+  if (c->gnn_layers < 1 || c->gnn_layers > PST_MAX_LAYERS) return false;
+  if (c->num_blocks < 1 || c->num_blocks > PST_MAX_BLOCKS) return false;
+  if (c->precision < PST_PREC_FP32 || c->precision > PST_PREC_BF16) return false;
+  long long codes = 1;
+  for (int i = 0; i < c->num_levels; ++i) {
+    if (c->levels[i] < 2 || c->levels[i] > 64) return false;
+    codes *= c->levels[i];
+    if (codes > 0x7fffffffLL) return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+// Walks the blob in the order documented in pst/weights.py; returns the float count.
+size_t pst_fill_weight_pointers(const pst_config& cfg, const float* base, PstWeights* w) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    const float* p = base ? base + off : nullptr;
+    off += n;
+    return p;
+  };
+  const size_t D = PST_D;
+  PstWeights tmp;
+  PstWeights& W = w ? *w : tmp;
+  W.node_table = take((size_t)cfg.seq_max_size * D);
+  W.edge_pe_table = take((size_t)(2 * cfg.seq_max_size - 1) * D);
+  W.edge_feat_w = take(PST_FEAT_PAD * D);
+  for (int l = 0; l < cfg.gnn_layers; ++l) {
+    PstLayerW& L = W.layer[l];
+    L.msg_w1 = take(3 * D * D); L.msg_b1 = take(D);
+    L.msg_w2 = take(D * D);     L.msg_b2 = take(D);
+    L.msg_w3 = take(D * D);     L.msg_b3 = take(D);
+    L.ln0_s = take(D);          L.ln0_o = take(D);
+    L.ffn_w1 = take(D * PST_FFN); L.ffn_b1 = take(PST_FFN);
+    L.ffn_w2 = take(PST_FFN * D); L.ffn_b2 = take(D);
+    L.ln1_s = take(D);          L.ln1_o = take(D);
+    L.edge_w1 = take(3 * D * D); L.edge_b1 = take(D);
+    L.edge_w2 = take(D * D);    L.edge_b2 = take(D);
+    L.edge_w3 = take(D * D);    L.edge_b3 = take(D);
+    L.ln2_s = take(D);          L.ln2_o = take(D);
+  }
+  W.token_table = take((size_t)cfg.max_out_len * D);
+  for (int b = 0; b < cfg.num_blocks; ++b) {
+    PstBlockW& B = W.block[b];
+    B.qn_s = take(D); B.qn_o = take(D); B.dn_s = take(D); B.dn_o = take(D);
+    B.wq = take(D * D); B.wk = take(D * D); B.wv = take(D * D); B.wg = take(D * D);
+    B.bg = take(D);     B.wo = take(D * D); B.bo = take(D);
+    B.rt_ln_s = take(D); B.rt_ln_o = take(D);
+    B.rt_w1 = take(D * PST_TRANS); B.rt_b1 = take(PST_TRANS);
+    B.rt_w2 = take(PST_TRANS * D); B.rt_b2 = take(D);
+    B.ot_ln_s = take(D); B.ot_ln_o = take(D);
+    B.ot_w1 = take(D * PST_TRANS); B.ot_b1 = take(PST_TRANS);
+    B.ot_w2 = take(PST_TRANS * D); B.ot_b2 = take(D);
+  }
+  W.down_w = take(D * PST_C8);
+  W.down_b = take(PST_C8);
+  return off;
+}
+
+PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T) {
+  PstWorkspace ws{};
+  const size_t K = m->cfg.num_neighbor;
+  const size_t E = (size_t)R * K;
+  const size_t D = PST_D;
+  const bool fp32 = m->cfg.precision == PST_PREC_FP32;
+  size_t off = 0;
+  char* b = static_cast<char*>(base);
+  auto take = [&](size_t bytes) {
+    void* p = b ? b + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const size_t RT = (size_t)(R > T ? R : T);
+  ws.status = (int32_t*)take(4 * sizeof(int32_t));
+  ws.row_base = (int32_t*)take((size_t)R * sizeof(int32_t));
+  ws.prep = (double*)take((size_t)R * PST_PREP_STRIDE * sizeof(double));
+  ws.senders = (int32_t*)take(E * sizeof(int32_t));
+  ws.edge_feat = (float*)take(E * PST_EDGE_FEATURES * sizeof(float));
+  ws.e = (float*)take(E * D * sizeof(float));
+  ws.t1 = (float*)take(fp32 ? E * D * sizeof(float) : 0);
+  ws.t2 = (float*)take(fp32 ? E * D * sizeof(float) : 0);
+  ws.h = (float*)take((size_t)R * D * sizeof(float));
+  ws.agg = (float*)take((size_t)R * D * sizeof(float));
+  ws.ps = (float*)take((size_t)R * D * sizeof(float));
+  ws.pr = (float*)take((size_t)R * D * sizeof(float));
+  ws.tmp = (float*)take((size_t)R * D * sizeof(float));
+  ws.u = (float*)take(RT * PST_FFN * sizeof(float));
+  ws.orig = (float*)take((size_t)R * D * sizeof(float));
+  ws.dn = (float*)take((size_t)R * D * sizeof(float));
+  ws.kx = (float*)take((size_t)R * D * sizeof(float));
+  ws.vx = (float*)take((size_t)R * D * sizeof(float));
+  ws.res = (float*)take((size_t)T * D * sizeof(float));
+  ws.qn = (float*)take((size_t)T * D * sizeof(float));
+  ws.q = (float*)take((size_t)T * D * sizeof(float));
+  ws.g = (float*)take((size_t)T * D * sizeof(float));
+  ws.wa = (float*)take((size_t)T * D * sizeof(float));
+  ws.z = (float*)take((size_t)T * PST_C8 * sizeof(float));
+  ws.bytes = off;
+  return ws;
+}
+
+extern "C" {
+
+int pst_abi_version(void) { return PST_ABI_VERSION; }
+
+const char* pst_status_string(int status) {
+  switch (status) {
+    case PST_OK: return "ok";
+    case PST_ERR_BAD_ARGUMENT: return "bad argument";
+    case PST_ERR_UNSUPPORTED_CONFIG: return "unsupported config";
+    case PST_ERR_LENGTH_OUT_OF_RANGE: return "structure length outside [num_neighbor, max_len]";
+    case PST_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case PST_ERR_CUDA: return "CUDA error";
+    case PST_ERR_NO_DEVICE: return "no CUDA device";
+    case PST_ERR_BAD_WEIGHTS: return "weight blob has the wrong size";
+    default: return "unknown status";
+  }
+}
+
+size_t pst_weight_blob_floats(const pst_config* cfg) {
+  if (!config_ok(cfg)) return 0;
+  return pst_fill_weight_pointers(*cfg, nullptr, nullptr);
+}
+
+int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_floats, int device,
+                     pst_model** out) {
+  if (!out) return PST_ERR_BAD_ARGUMENT;
+  *out = nullptr;
+  if (!config_ok(cfg)) return PST_ERR_UNSUPPORTED_CONFIG;
+  if (!blob_host) return PST_ERR_BAD_ARGUMENT;
+  if (blob_floats != pst_fill_weight_pointers(*cfg, nullptr, nullptr)) return PST_ERR_BAD_WEIGHTS;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PST_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return PST_ERR_BAD_ARGUMENT;
+  PST_CUDA_OK(cudaSetDevice(device));
+  pst_model* m = new (std::nothrow) pst_model();
+  if (!m) return PST_ERR_BAD_ARGUMENT;
+  m->cfg = *cfg;
+  m->device = device;
+  m->launch_count = 0;
+  m->tc_dev = nullptr;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete m; return PST_ERR_CUDA; }
+  m->num_sms = prop.multiProcessorCount;
+  if (cudaMalloc(&m->blob_dev, blob_floats * sizeof(float)) != cudaSuccess) { delete m; return PST_ERR_CUDA; }
+  m->blob_floats = blob_floats;
+  if (cudaMemcpy(m->blob_dev, blob_host, blob_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(m->blob_dev); delete m; return PST_ERR_CUDA;
+  }
+  pst_fill_weight_pointers(m->cfg, m->blob_dev, &m->w);
+  // FSQ constants in fp32, operation order of model/quantize.py:177-180
+  int basis = 1;
+  for (int c = 0; c < PST_C8; ++c) {
+    m->half_l[c] = 0.f; m->fsq_offset[c] = 0.f; m->fsq_shift[c] = 0.f; m->basis[c] = 0; m->half_width[c] = 0;
+    if (c < cfg->num_levels) {
+      int L = cfg->levels[c];
+      float half_l = ((float)(L - 1) * (float)(1.0 - 1e-3)) / 2.0f;
+      float offset = (L % 2 == 0) ? 0.5f : 0.0f;
+      m->half_l[c] = half_l;
+      m->fsq_offset[c] = offset;
+      m->fsq_shift[c] = tanf(offset / half_l);
+      m->basis[c] = basis;
+      m->half_width[c] = L / 2;
+      basis *= L;
+    }
+  }
+  if (cfg->precision != PST_PREC_FP32) {
+    int rc = pst_prepare_tc_weights(m);
+    if (rc != PST_OK) { pst_model_destroy(m); return rc; }
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) { pst_model_destroy(m); return PST_ERR_CUDA; }
+  *out = m;
+  return PST_OK;
+}
+
+void pst_model_destroy(pst_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->blob_dev) cudaFree(m->blob_dev);
+  if (m->tc_dev) cudaFree(m->tc_dev);
+  delete m;
+}
+
+size_t pst_workspace_bytes(const pst_model* m, int total_residues, int num_structures) {
+  if (!m || total_residues < 0 || num_structures < 0) return 0;
+  (void)num_structures;
+  return pst_carve_workspace(m, nullptr, total_residues, total_residues).bytes;
+}
+
+int pst_last_launch_count(const pst_model* m) { return m ? m->launch_count : 0; }
+
+int pst_read_status(const pst_model* m, void* stream, void* workspace) {
+  if (!m || !workspace) return PST_ERR_BAD_ARGUMENT;
+  int32_t v = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PST_CUDA_OK(cudaMemcpyAsync(&v, workspace, sizeof(v), cudaMemcpyDeviceToHost, st));
+  PST_CUDA_OK(cudaStreamSynchronize(st));
+  return v;
+}
+
+static int check_batch(const pst_model* m, const void* offsets, int B, int R, void* ws, size_t ws_bytes, int T) {
+  if (!m || !offsets || B < 0 || R < 0 || T < 0 || T > R) return PST_ERR_BAD_ARGUMENT;
+  if (!ws) return PST_ERR_BAD_ARGUMENT;
+  if (ws_bytes < pst_carve_workspace(m, nullptr, R, R).bytes) return PST_ERR_WORKSPACE_TOO_SMALL;
+  return PST_OK;
+}
+
+int pst_featurize_knn(const pst_model* m, void* stream, const float* atoms, const uint8_t* atom_mask,
+                      int atoms_per_residue, const int32_t* offsets, int num_structures, int total_residues,
+                      int32_t* senders_out, float* edge_features_out, void* workspace, size_t workspace_bytes) {
+  int rc = check_batch(m, offsets, num_structures, total_residues, workspace, workspace_bytes, 0);
+  if (rc != PST_OK) return rc;
+  if (!atoms || !senders_out || atoms_per_residue < 4) return PST_ERR_BAD_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PST_CUDA_OK(cudaSetDevice(m->device));
+  PstWorkspace ws = pst_carve_workspace(m, workspace, total_residues, total_residues);
+  PST_CUDA_OK(cudaMemsetAsync(ws.status, 0, 4 * sizeof(int32_t), st));
+  m->launch_count = pst_launch_featurize(m, st, atoms, atom_mask, atoms_per_residue, offsets, num_structures,
+                                         total_residues, senders_out, edge_features_out, ws.prep, ws.status);
+  return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+}
+
+int pst_encode_graph(const pst_model* m, void* stream, const float* edge_features, const int32_t* senders,
+                     const int32_t* offsets, const int32_t* token_offsets, int num_structures, int total_residues,
+                     int total_tokens, float* latents_out, void* workspace, size_t workspace_bytes) {
+  int rc = check_batch(m, offsets, num_structures, total_residues, workspace, workspace_bytes, total_tokens);
+  if (rc != PST_OK) return rc;
+  if (!edge_features || !senders || !token_offsets || !latents_out) return PST_ERR_BAD_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PST_CUDA_OK(cudaSetDevice(m->device));
+  PstWorkspace ws = pst_carve_workspace(m, workspace, total_residues, total_residues);
+  PST_CUDA_OK(cudaMemsetAsync(ws.status, 0, 4 * sizeof(int32_t), st));
+  int n = pst_launch_encode_fp32(m, st, edge_features, senders, offsets, token_offsets, num_structures,
+                                 total_residues, total_tokens, latents_out, ws);
+  if (n < 0) return n;
+  m->launch_count = n;
+  return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+}
+
+int pst_quantize(const pst_model* m, void* stream, const float* latents, int n_tokens, int32_t* tokens_out,
+                 float* bounded_out) {
+  if (!m || !latents || !tokens_out || n_tokens < 0) return PST_ERR_BAD_ARGUMENT;
+  PST_CUDA_OK(cudaSetDevice(m->device));
+  m->launch_count = pst_launch_quantize(m, static_cast<cudaStream_t>(stream), latents, n_tokens, tokens_out, bounded_out);
+  return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+}
+
+int pst_fsq_pack(const pst_model* m, void* stream, const float* bounded, int n_tokens, int32_t* tokens_out) {
+  if (!m || !bounded || !tokens_out || n_tokens < 0) return PST_ERR_BAD_ARGUMENT;
+  PST_CUDA_OK(cudaSetDevice(m->device));
+  m->launch_count = pst_launch_fsq_pack(m, static_cast<cudaStream_t>(stream), bounded, n_tokens, tokens_out);
+  return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+}
+
+int pst_indexes_to_codes(const pst_model* m, void* stream, const int32_t* tokens, int n_tokens, float* codes_out) {
+  if (!m || !tokens || !codes_out || n_tokens < 0) return PST_ERR_BAD_ARGUMENT;
+  PST_CUDA_OK(cudaSetDevice(m->device));
+  m->launch_count = pst_launch_indexes_to_codes(m, static_cast<cudaStream_t>(stream), tokens, n_tokens, codes_out);
+  return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+}
+
+int pst_tokenize(const pst_model* m, void* stream, const float* atoms, const uint8_t* atom_mask,
+                 int atoms_per_residue, const int32_t* offsets, const int32_t* token_offsets, int num_structures,
+                 int total_residues, int total_tokens, int32_t* tokens_out, void* workspace,
+                 size_t workspace_bytes) {
+  int rc = check_batch(m, offsets, num_structures, total_residues, workspace, workspace_bytes, total_tokens);
+  if (rc != PST_OK) return rc;
+  if (!atoms || !token_offsets || !tokens_out || atoms_per_residue < 4) return PST_ERR_BAD_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PST_CUDA_OK(cudaSetDevice(m->device));
+  PstWorkspace ws = pst_carve_workspace(m, workspace, total_residues, total_residues);
+  PST_CUDA_OK(cudaMemsetAsync(ws.status, 0, 4 * sizeof(int32_t), st));
+  int count = pst_launch_featurize(m, st, atoms, atom_mask, atoms_per_residue, offsets, num_structures,
+                                   total_residues, ws.senders, ws.edge_feat, ws.prep, ws.status);
+  int n = pst_launch_encode_fp32(m, st, ws.edge_feat, ws.senders, offsets, token_offsets, num_structures,
+                                 total_residues, total_tokens, ws.z, ws);
+  if (n < 0) return n;
+  count += n;
+  count += pst_launch_quantize(m, st, ws.z, total_tokens, tokens_out, nullptr);
+  m->launch_count = count;
+  return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// Internal declarations shared by the translation units of libpst_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "pst_abi.h"
+
+#define PST_D 128
+#define PST_FFN 512
+#define PST_TRANS 256
+#define PST_HEADS 4
+#define PST_HEAD_DIM 32
+#define PST_C8 PST_MAX_LEVELS
+#define PST_FEAT_PAD 32   // 27 edge features padded to 32 GEMM rows
+#define PST_PREP_STRIDE 16 // doubles per residue in the prep record
+
+// ---- prepared weight blob (fp32), see pst/weights.py for the packer ----------
+struct PstLayerW {
+  const float *msg_w1, *msg_b1, *msg_w2, *msg_b2, *msg_w3, *msg_b3;
+  const float *ln0_s, *ln0_o;
+  const float *ffn_w1, *ffn_b1, *ffn_w2, *ffn_b2;
+  const float *ln1_s, *ln1_o;
+  const float *edge_w1, *edge_b1, *edge_w2, *edge_b2, *edge_w3, *edge_b3;
+  const float *ln2_s, *ln2_o;
+};
+struct PstBlockW {
+  const float *qn_s, *qn_o, *dn_s, *dn_o;
+  const float *wq, *wk, *wv, *wg, *bg, *wo, *bo;
+  const float *rt_ln_s, *rt_ln_o, *rt_w1, *rt_b1, *rt_w2, *rt_b2;
+  const float *ot_ln_s, *ot_ln_o, *ot_w1, *ot_b1, *ot_w2, *ot_b2;
+};
+#define PST_MAX_LAYERS 4
+#define PST_MAX_BLOCKS 4
+struct PstWeights {
+  const float* node_table;    // [seq_max_size,128]   PE_node.W + b
+  const float* edge_pe_table; // [2*seq_max_size-1,128] PE_edge.W[0:128] + b
+  const float* edge_feat_w;   // [32,128]  W[128:155], rows 27..31 zero
+  PstLayerW layer[PST_MAX_LAYERS];
+  const float* token_table;   // [max_out_len,128]
+  PstBlockW block[PST_MAX_BLOCKS];
+  const float* down_w;        // [128,8]
+  const float* down_b;        // [8]
+};
+
+// operand-precision copies of the edge-level MLP weights for the tensor-core path:
+// per MLP three 128x128 matrices, 16-bit, stored [n][k] (K-major "B" operand),
+// W1 restricted to its edge rows (256..383).
+struct PstTcWeights {
+  const uint16_t* w;  // [layers][2 (msg,edge)][3][128*128]
+};
+
+struct pst_model {
+  pst_config cfg;
+  int device;
+  int num_sms;
+  float* blob_dev;
+  size_t blob_floats;
+  PstWeights w;
+  uint16_t* tc_dev;
+  PstTcWeights tc;
+  // FSQ constants (model/quantize.py:175-181), fp32
+  float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
+  int32_t basis[PST_C8], half_width[PST_C8];
+  mutable int launch_count;
+};
+
+size_t pst_fill_weight_pointers(const pst_config& cfg, const float* base, PstWeights* w);
+
+// ---- workspace carving -------------------------------------------------------
+struct PstWorkspace {
+  int32_t* status;       // [4]
+  int32_t* row_base;     // [R]
+  double* prep;          // [R,16]
+  int32_t* senders;      // [E]
+  float* edge_feat;      // [E,27]
+  float* e;              // [E,128]
+  float* t1;             // [E,128]   (fp32 mode only)
+  float* t2;             // [E,128]   (fp32 mode only)
+  float* h;              // [R,128]
+  float* agg;            // [R,128]
+  float* ps;             // [R,128]
+  float* pr;             // [R,128]
+  float* tmp;            // [R,128]
+  float* u;              // [max(R,T),512]
+  float* orig;           // [R,128]
+  float* dn;             // [R,128]
+  float* kx;             // [R,128]
+  float* vx;             // [R,128]
+  float* res;            // [T,128]
+  float* qn;             // [T,128]
+  float* q;              // [T,128]
+  float* g;              // [T,128]
+  float* wa;             // [T,128]
+  float* z;              // [T,8]
+  size_t bytes;
+};
+PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T_upper);
+
+// ---- kernel launchers (each returns the number of kernels enqueued) --------------
+int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms,
+                         const uint8_t* mask, int apr, const int32_t* offsets, int B, int R,
+                         int32_t* senders, float* edge_feat, double* prep, int32_t* status);
+
+int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edge_feat,
+                           const int32_t* senders, const int32_t* offsets,
+                           const int32_t* token_offsets, int B, int R, int T, float* z_out,
+                           PstWorkspace& ws);
+
+int pst_launch_quantize(const pst_model* m, cudaStream_t st, const float* z, int n,
+                        int32_t* tokens, float* bounded);
+int pst_launch_fsq_pack(const pst_model* m, cudaStream_t st, const float* bounded, int n,
+                        int32_t* tokens);
+int pst_launch_indexes_to_codes(const pst_model* m, cudaStream_t st, const int32_t* tokens, int n,
+                                float* codes);
+
+// tensor-core edge MLP (edge_mlp_tc.cu).  mode 0: message MLP -> agg[R,128] = mean_K;
+// mode 1: edge update -> e = LN(e + MLP).  Returns kernels launched, <0 on error.
+int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, float* e,
+                           const float* ps, const float* pr, const int32_t* senders,
+                           const int32_t* offsets, int B, int R, float* agg_out);
+
+#define PST_CUDA_OK(expr)                                  \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return PST_ERR_CUDA;            \
+  } while (0)

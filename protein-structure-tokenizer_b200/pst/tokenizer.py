@@ -1,0 +1,205 @@
+"""Host-side driver of the CUDA hot path: owns the `pst_model` handle and a grow-only
+workspace, and exposes the two drop-in boundaries of SURVEY section 8b on top of the C ABI:
+
+  B1  `encode_graph`  ProteinGraph arrays (edge_features, senders)  -> latents / tokens
+      (the callable the reference builds in InferenceRunner.prepare_tokenize_fn,
+       scripts/inference_runner.py:179-191)
+  B2  `tokenize`      atoms (backbone or atom37) -> token ids
+      (make_graph_from_pdb's featurisation + that callable, scripts/inference_runner.py:288-305)
+
+torch is used for device memory and streams only.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .config import PRECISIONS, TokenizerConfig
+from .weights import pack_weights
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class StructureTokenizer:
+    def __init__(self, cfg: TokenizerConfig, params, device: int = 0, max_rows_per_call: int = 131072):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("StructureTokenizer needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.lib = _lib.load()
+        self.max_rows_per_call = int(max_rows_per_call)
+        c = _lib.PstConfig()
+        c.abi_version = _lib.PST_ABI_VERSION
+        c.seq_max_size, c.max_out_len = cfg.seq_max_size, cfg.max_out_len
+        c.num_neighbor, c.downsampling_ratio = cfg.num_neighbor, cfg.downsampling_ratio
+        c.num_levels = len(cfg.levels)
+        for i, l in enumerate(cfg.levels):
+            c.levels[i] = int(l)
+        c.gnn_layers, c.num_blocks = cfg.gnn_layers, cfg.num_blocks
+        c.precision = PRECISIONS[cfg.precision]
+        c.max_len = cfg.max_len
+        self._c = c
+        blob = np.ascontiguousarray(pack_weights(params, cfg), np.float32)
+        want = self.lib.pst_weight_blob_floats(C.byref(c))
+        if want == 0:
+            raise _lib.PstError(-2, "pst_weight_blob_floats")
+        if want != blob.size:
+            raise ValueError(f"weight blob has {blob.size} floats, library expects {want}")
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pst_model_create(C.byref(c), blob.ctypes.data, blob.size, device, C.byref(handle)),
+                       "pst_model_create")
+        self._h = handle
+        self._ws = None
+        self.launches = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.pst_model_destroy(self._h)
+            self._h = C.c_void_p()
+        self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self) -> int:
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _workspace(self, R: int, B: int):
+        need = self.lib.pst_workspace_bytes(self._h, int(R), int(B))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = self.torch.empty(int(need), dtype=self.torch.uint8, device=self.device)
+        return self._ws
+
+    def token_offsets(self, offsets: np.ndarray) -> np.ndarray:
+        lens = np.diff(np.asarray(offsets, np.int64))
+        out = np.zeros(len(lens) + 1, np.int32)
+        out[1:] = np.cumsum(lens // self.cfg.downsampling_ratio)
+        return out
+
+    def check_lengths(self, offsets: np.ndarray) -> None:
+        """Same rejection rule as scripts/inference_runner.py:52-62 (NotImplementedError)."""
+        lens = np.diff(np.asarray(offsets, np.int64))
+        if (lens > self.cfg.max_len).any():
+            raise NotImplementedError(
+                f"We currently don't support protein with more than {self.cfg.max_len} residues given: {int(lens.max())}")
+        if (lens < self.cfg.num_neighbor).any():
+            raise NotImplementedError(
+                f"We currently don't support protein with less than {self.cfg.num_neighbor} residues given: {int(lens.min())}")
+
+    # ------------------------------------------------------------------ device-level API
+    def featurize_device(self, atoms, atom_mask, offsets_dev, B: int, R: int, want_features: bool = True):
+        """atoms f32 [R, A, 3] (A = 4 or 37), atom_mask u8 [R, A] or None, offsets i32 [B+1], all on device."""
+        t = self.torch
+        K = self.cfg.num_neighbor
+        senders = t.empty((R * K,), dtype=t.int32, device=self.device)
+        feats = t.empty((R * K, 27), dtype=t.float32, device=self.device) if want_features else None
+        ws = self._workspace(R, B)
+        _lib.check(self.lib.pst_featurize_knn(self._h, self._stream(), atoms.data_ptr(), _ptr(atom_mask), int(atoms.shape[1]),
+                                              offsets_dev.data_ptr(), B, R, senders.data_ptr(), _ptr(feats),
+                                              ws.data_ptr(), ws.numel()), "pst_featurize_knn")
+        self.launches = self.lib.pst_last_launch_count(self._h)
+        return senders, feats
+
+    def encode_graph_device(self, edge_features, senders, offsets_dev, token_offsets_dev, B: int, R: int, T: int):
+        t = self.torch
+        z = t.empty((T, 8), dtype=t.float32, device=self.device)
+        ws = self._workspace(R, B)
+        _lib.check(self.lib.pst_encode_graph(self._h, self._stream(), edge_features.data_ptr(), senders.data_ptr(),
+                                             offsets_dev.data_ptr(), token_offsets_dev.data_ptr(), B, R, T,
+                                             z.data_ptr(), ws.data_ptr(), ws.numel()), "pst_encode_graph")
+        self.launches = self.lib.pst_last_launch_count(self._h)
+        return z
+
+    def quantize_device(self, z, want_bounded: bool = False):
+        t = self.torch
+        n = int(z.shape[0])
+        tokens = t.empty((n,), dtype=t.int32, device=self.device)
+        bounded = t.empty((n, 8), dtype=t.float32, device=self.device) if want_bounded else None
+        _lib.check(self.lib.pst_quantize(self._h, self._stream(), z.data_ptr(), n, tokens.data_ptr(), _ptr(bounded)), "pst_quantize")
+        return (tokens, bounded) if want_bounded else tokens
+
+    def fsq_pack_device(self, bounded):
+        t = self.torch
+        n = int(bounded.shape[0])
+        tokens = t.empty((n,), dtype=t.int32, device=self.device)
+        _lib.check(self.lib.pst_fsq_pack(self._h, self._stream(), bounded.data_ptr(), n, tokens.data_ptr()), "pst_fsq_pack")
+        return tokens
+
+    def indexes_to_codes_device(self, tokens):
+        t = self.torch
+        n = int(tokens.shape[0])
+        codes = t.empty((n, 8), dtype=t.float32, device=self.device)
+        _lib.check(self.lib.pst_indexes_to_codes(self._h, self._stream(), tokens.data_ptr(), n, codes.data_ptr()), "pst_indexes_to_codes")
+        return codes
+
+    def tokenize_device(self, atoms, atom_mask, offsets_dev, token_offsets_dev, B: int, R: int, T: int, out=None):
+        """Fused B2 call: atoms -> int32 tokens [T], everything resident on the device."""
+        t = self.torch
+        tokens = out if out is not None else t.empty((T,), dtype=t.int32, device=self.device)
+        ws = self._workspace(R, B)
+        _lib.check(self.lib.pst_tokenize(self._h, self._stream(), atoms.data_ptr(), _ptr(atom_mask), int(atoms.shape[1]),
+                                         offsets_dev.data_ptr(), token_offsets_dev.data_ptr(), B, R, T,
+                                         tokens.data_ptr(), ws.data_ptr(), ws.numel()), "pst_tokenize")
+        self.launches = self.lib.pst_last_launch_count(self._h)
+        return tokens
+
+    def read_status(self) -> int:
+        return self.lib.pst_read_status(self._h, self._stream(), self._ws.data_ptr()) if self._ws is not None else 0
+
+    # ------------------------------------------------------------------ host-level API
+    def _chunks(self, lengths: Sequence[int]) -> List[Tuple[int, int]]:
+        out, start, rows = [], 0, 0
+        for i, L in enumerate(lengths):
+            if rows + L > self.max_rows_per_call and i > start:
+                out.append((start, i))
+                start, rows = i, 0
+            rows += L
+        if start < len(lengths):
+            out.append((start, len(lengths)))
+        return out
+
+    def tokenize(self, structures: Sequence[np.ndarray], masks: Optional[Sequence[Optional[np.ndarray]]] = None) -> List[np.ndarray]:
+        """structures: one fp32 array [L, A, 3] per protein (A = 4: N,CA,C,O; A = 37: atom37),
+        only valid residues; masks: optional u8/bool [L, A].  Returns one uint32 token
+        array [floor(L/df)] per protein (the dtype the reference saves,
+        scripts/inference_runner.py:315-321)."""
+        t = self.torch
+        lengths = [int(s.shape[0]) for s in structures]
+        offs_all = np.zeros(len(lengths) + 1, np.int64)
+        offs_all[1:] = np.cumsum(lengths)
+        self.check_lengths(offs_all)
+        results: List[np.ndarray] = []
+        for a, b in self._chunks(lengths):
+            atoms = np.ascontiguousarray(np.concatenate([np.asarray(s, np.float32) for s in structures[a:b]], axis=0))
+            offsets = (offs_all[a : b + 1] - offs_all[a]).astype(np.int32)
+            tok_off = self.token_offsets(offsets)
+            mask_dev = None
+            if masks is not None and any(m is not None for m in masks[a:b]):
+                mk = np.concatenate([np.ones(s.shape[:2], np.uint8) if m is None else np.asarray(m, np.uint8)
+                                     for s, m in zip(structures[a:b], masks[a:b])], axis=0)
+                mask_dev = t.from_numpy(np.ascontiguousarray(mk)).to(self.device, non_blocking=True)
+            atoms_dev = t.from_numpy(atoms).to(self.device, non_blocking=True)
+            offsets_dev = t.from_numpy(offsets).to(self.device, non_blocking=True)
+            tok_off_dev = t.from_numpy(tok_off).to(self.device, non_blocking=True)
+            R, T = int(offsets[-1]), int(tok_off[-1])
+            tokens = self.tokenize_device(atoms_dev, mask_dev, offsets_dev, tok_off_dev, b - a, R, T).cpu().numpy()
+            st = self.read_status()
+            if st != 0:
+                raise _lib.PstError(st, "pst_tokenize (device status)")
+            for i in range(b - a):
+                results.append(tokens[tok_off[i] : tok_off[i + 1]].astype(np.uint32))
+        return results

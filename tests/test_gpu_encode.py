@@ -1,0 +1,118 @@
+"""CUDA encoder + quantiser against the oracle (fp32 CPU restatement of the reference forward)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [(4096, 1), (64000, 1), (64000, 4), (432, 1), (4096, 2)]
+
+
+def _oracle_cfg(cfg):
+    from oracle import model as om
+
+    return om.OracleConfig(seq_max_size=cfg.seq_max_size, graph_max_neighbor=cfg.num_neighbor,
+                           downsampling_ratio=cfg.downsampling_ratio, max_out_len=cfg.max_out_len, levels=list(cfg.levels))
+
+
+def _setup(codebook, df, precision, lengths, seed=11):
+    import torch
+    from oracle import featurize as fz
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(codebook, df, precision=precision)
+    params = init_params(cfg, 1, "rich")
+    tok = StructureTokenizer(cfg, params)
+    bbs = syn.make_backbones(seed, lengths)
+    graphs = []
+    for bb in bbs:
+        pos, gt, ex = syn.backbone_to_atom37(bb)
+        graphs.append(fz.featurize(pos, gt, ex, cfg.num_neighbor))
+    return cfg, params, tok, bbs, graphs
+
+
+@pytest.mark.parametrize("codebook,df", CONFIGS)
+def test_fp32_latents_and_tokens_match_oracle(built_lib, codebook, df):
+    import torch
+    from oracle import model as om
+
+    lengths = [64, 101, 256, 50, 190]
+    cfg, params, tok, bbs, graphs = _setup(codebook, df, "fp32", lengths)
+    ocfg = _oracle_cfg(cfg)
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)
+    toff = tok.token_offsets(offs)
+    feats = np.concatenate([g["edge_features"].astype(np.float32) for g in graphs])
+    send = np.concatenate([g["senders"].astype(np.int32) for g in graphs])
+    z = tok.encode_graph_device(torch.from_numpy(feats).cuda(), torch.from_numpy(send).cuda(), torch.from_numpy(offs).cuda(),
+                                torch.from_numpy(toff).cuda(), len(lengths), int(offs[-1]), int(toff[-1]))
+    tokens, bounded = tok.quantize_device(z, want_bounded=True)
+    torch.cuda.synchronize()
+    z, tokens, bounded = z.cpu().numpy(), tokens.cpu().numpy(), bounded.cpu().numpy()
+    C = len(cfg.levels)
+    agree = total = 0
+    for i, g in enumerate(graphs):
+        zr = om.encode(params, ocfg, g["edge_features"], g["senders"], g["n_node"])
+        sl = slice(toff[i], toff[i + 1])
+        assert zr.shape[0] == toff[i + 1] - toff[i]
+        # fp32 on both sides, different summation order: stated tolerance 2e-4 absolute on z (|z| ~ 1)
+        assert np.abs(z[sl, :C] - zr).max() < 2e-4, (i, float(np.abs(z[sl, :C] - zr).max()))
+        tr = om.fsq_tokens(zr, cfg.levels)
+        amb = om.fsq_ambiguous(zr, cfg.levels, tol=5e-4)
+        assert np.array_equal(tokens[sl][~amb].astype(np.uint32), tr[~amb]), i
+        agree += int((tokens[sl].astype(np.uint32) == tr).sum())
+        total += len(tr)
+        # quantiser is bit-exact given identical bounded values
+        assert np.array_equal(om.fsq_pack(bounded[sl, :C], cfg.levels), tokens[sl].astype(np.uint32))
+    assert agree / total > 0.995
+
+
+def test_fsq_pack_and_inverse_bit_exact(built_lib):
+    import torch
+    from oracle import model as om
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    rng = np.random.default_rng(0)
+    for codebook in (432, 1728, 4096, 64000):
+        cfg = TokenizerConfig.named(codebook, 1, precision="fp32")
+        tok = StructureTokenizer(cfg, init_params(cfg, 0, "ref"))
+        C = len(cfg.levels)
+        z = np.zeros((20000, 8), np.float32)
+        z[:, :C] = rng.normal(0, 1.5, (20000, C))
+        b = np.zeros_like(z)
+        b[:, :C] = om.fsq_bound(z[:, :C], cfg.levels)
+        b[:64, :C] = np.round(b[:64, :C]) + 0.5  # exact ties: round half to even
+        b[:64, :C] = np.clip(b[:64, :C], -(np.array(cfg.levels) // 2) + 0.5, (np.array(cfg.levels) - 1) // 2 - 0.5)
+        t_pack = tok.fsq_pack_device(torch.from_numpy(b).cuda()).cpu().numpy()
+        assert np.array_equal(t_pack.astype(np.uint32), om.fsq_pack(b[:, :C], cfg.levels))
+        t_q = tok.quantize_device(torch.from_numpy(z).cuda()).cpu().numpy().astype(np.uint32)
+        ref = om.fsq_tokens(z[:, :C], cfg.levels)
+        amb = om.fsq_ambiguous(z[:, :C], cfg.levels, tol=1e-5)
+        assert np.array_equal(t_q[~amb], ref[~amb])
+        assert t_q.max() < cfg.num_codes
+        codes = tok.indexes_to_codes_device(torch.from_numpy(t_pack).cuda()).cpu().numpy()
+        assert np.array_equal(codes[:, :C], om.indexes_to_codes(t_pack, cfg.levels).astype(np.float32))
+        assert np.array_equal(codes[:, :C], np.rint(b[:, :C]))
+        tok.close()
+
+
+@pytest.mark.parametrize("codebook,df", [(4096, 1), (64000, 4)])
+def test_tokenize_end_to_end_matches_oracle(built_lib, codebook, df):
+    from oracle import model as om
+
+    lengths = [75, 128, 300, 60]
+    cfg, params, tok, bbs, graphs = _setup(codebook, df, "fp32", lengths, seed=23)
+    ocfg = _oracle_cfg(cfg)
+    out = tok.tokenize(bbs)
+    agree = total = 0
+    for i, g in enumerate(graphs):
+        zr = om.encode(params, ocfg, g["edge_features"], g["senders"], g["n_node"])
+        tr = om.fsq_tokens(zr, cfg.levels)
+        assert out[i].dtype == np.uint32 and out[i].shape == tr.shape
+        agree += int((out[i] == tr).sum())
+        total += len(tr)
+    assert agree / total > 0.995
+    assert tok.launches > 0

@@ -1,0 +1,105 @@
+"""CUDA featuriser / k-NN (pst_featurize_knn) against the reference's golden vectors and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import valid_atoms
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tok(built_lib):
+    import torch
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(4096, 1, precision="fp32")
+    return StructureTokenizer(cfg, init_params(cfg, 0, "rich"))
+
+
+def _run(tok, structs, masks=None):
+    import torch
+
+    lens = [s.shape[0] for s in structs]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    atoms = torch.from_numpy(np.concatenate(structs)).cuda()
+    mask = None if masks is None else torch.from_numpy(np.concatenate(masks)).cuda()
+    s, f = tok.featurize_device(atoms, mask, torch.from_numpy(offs).cuda(), len(structs), int(offs[-1]))
+    torch.cuda.synchronize()
+    return s.cpu().numpy(), f.cpu().numpy(), offs
+
+
+def ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
+    bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
+    return np.abs(ai - bi)
+
+
+def test_casp14_senders_bit_exact_and_features(tok, casp14):
+    names = list(casp14)
+    structs, masks = zip(*[valid_atoms(casp14[n]) for n in names])
+    s, f, offs = _run(tok, structs, masks)
+    assert tok.read_status() == 0
+    n_feat = 0
+    for i, n in enumerate(names):
+        e = casp14[n]
+        sl = slice(offs[i] * 50, offs[i + 1] * 50)
+        assert np.array_equal(s[sl].astype(np.int64), e["senders"]), n
+        assert abs(float(f[sl].astype(np.float64).sum()) - e["feat_sum"]) < 1e-2, n
+        if e["edge_features"] is not None:
+            u = ulp_diff(f[sl], e["edge_features"])
+            # fp64 arithmetic rounded once: <= 1 fp32 ulp from the reference (CUDA vs NumPy exp / sum order)
+            tiny = np.abs(e["edge_features"]) < 1e-30
+            assert (u[~tiny] <= 1).all(), (n, int(u[~tiny].max()))
+            assert (u == 0).mean() > 0.999
+            n_feat += 1
+    assert n_feat >= 3
+
+
+def test_synthetic_backbone4_matches_oracle(tok):
+    from oracle import featurize as fz
+    from pst import synthetic as syn
+
+    bbs = syn.make_backbones(20240517, [64, 127, 200, 512, 50, 333])
+    s, f, offs = _run(tok, bbs)
+    assert tok.read_status() == 0
+    for i, bb in enumerate(bbs):
+        pos, gt, ex = syn.backbone_to_atom37(bb)
+        g = fz.featurize(pos, gt, ex, 50)
+        sl = slice(offs[i] * 50, offs[i + 1] * 50)
+        assert np.array_equal(s[sl].astype(np.int64), g["senders"]), i
+        ref = g["edge_features"].astype(np.float32)
+        u = ulp_diff(f[sl], ref)
+        tiny = np.abs(ref) < 1e-30
+        assert (u[~tiny] <= 1).all(), (i, int(u[~tiny].max()))
+
+
+def test_length_equal_k_includes_self(tok):
+    from pst import synthetic as syn
+
+    bb = syn.make_backbones(3, [50])[0]
+    s, _, _ = _run(tok, [bb])
+    assert (s.reshape(50, 50)[:, 0] == np.arange(50)).all()
+
+
+def test_too_short_structure_raises_status(tok):
+    from pst import synthetic as syn
+
+    bb = syn.make_backbones(4, [60])[0][:40]
+    _run(tok, [bb])
+    assert tok.read_status() == -3
+    with pytest.raises(NotImplementedError):
+        tok.tokenize([bb])
+
+
+def test_atom37_and_backbone4_layouts_agree(tok):
+    from pst import synthetic as syn
+
+    bb = syn.make_backbones(5, [128])[0]
+    pos, gt, _ = syn.backbone_to_atom37(bb)
+    s4, f4, _ = _run(tok, [bb])
+    s37, f37, _ = _run(tok, [pos], [gt.astype(np.uint8)])
+    assert np.array_equal(s4, s37) and np.array_equal(f4, f37)
