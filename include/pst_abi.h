@@ -151,6 +151,13 @@ int pst_read_status(const pst_model* model, void* stream, void* workspace);
 /* How many kernels of this library the last hot call enqueued (for bench.py's gpu_launches). */
 int pst_last_launch_count(const pst_model* model);
 
+/* Optional per-kernel-group timing for bench.py's roofline: when enabled, the hot calls record
+ * CUDA event pairs on their stream around (kind 0) featurise + k-NN, (1) message-MLP launches,
+ * (2) edge-update-MLP launches.  pst_profile_collect synchronises those events, adds the elapsed
+ * milliseconds and launch-group counts per kind into ms_out[4] / count_out[4], and resets. */
+int pst_profile_enable(const pst_model* model, int enable);
+int pst_profile_collect(const pst_model* model, float* ms_out_host, int* count_out_host);
+
 const char* pst_status_string(int status);
 int pst_abi_version(void);
 

@@ -163,6 +163,9 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   m->device = device;
   m->launch_count = 0;
   m->tc_dev = nullptr;
+  m->prof_on = false;
+  m->prof_n = 0;
+  for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i) m->prof_ev[i] = nullptr;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete m; return PST_ERR_CUDA; }
   m->num_sms = prop.multiProcessorCount;
@@ -202,6 +205,8 @@ void pst_model_destroy(pst_model* m) {
   cudaSetDevice(m->device);
   if (m->blob_dev) cudaFree(m->blob_dev);
   if (m->tc_dev) cudaFree(m->tc_dev);
+  for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i)
+    if (m->prof_ev[i]) cudaEventDestroy(m->prof_ev[i]);
   delete m;
 }
 
@@ -212,6 +217,29 @@ size_t pst_workspace_bytes(const pst_model* m, int total_residues, int num_struc
 }
 
 int pst_last_launch_count(const pst_model* m) { return m ? m->launch_count : 0; }
+
+int pst_profile_enable(const pst_model* m, int enable) {
+  if (!m) return PST_ERR_BAD_ARGUMENT;
+  PST_CUDA_OK(cudaSetDevice(m->device));
+  if (enable && !m->prof_ev[0])
+    for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i) PST_CUDA_OK(cudaEventCreate(&m->prof_ev[i]));
+  m->prof_on = enable != 0;
+  m->prof_n = 0;
+  return PST_OK;
+}
+
+int pst_profile_collect(const pst_model* m, float* ms_out, int* count_out) {
+  if (!m || !ms_out || !count_out) return PST_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < m->prof_n; ++i) {
+    float ms = 0.f;
+    PST_CUDA_OK(cudaEventSynchronize(m->prof_ev[2 * i + 1]));
+    PST_CUDA_OK(cudaEventElapsedTime(&ms, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]));
+    int k = m->prof_kind[i];
+    if (k >= 0 && k < PST_PROF_KINDS) { ms_out[k] += ms; count_out[k] += 1; }
+  }
+  m->prof_n = 0;
+  return PST_OK;
+}
 
 int pst_read_status(const pst_model* m, void* stream, void* workspace) {
   if (!m || !workspace) return PST_ERR_BAD_ARGUMENT;
@@ -294,8 +322,12 @@ int pst_tokenize(const pst_model* m, void* stream, const float* atoms, const uin
   PST_CUDA_OK(cudaSetDevice(m->device));
   PstWorkspace ws = pst_carve_workspace(m, workspace, total_residues, total_residues);
   PST_CUDA_OK(cudaMemsetAsync(ws.status, 0, 4 * sizeof(int32_t), st));
-  int count = pst_launch_featurize(m, st, atoms, atom_mask, atoms_per_residue, offsets, num_structures,
-                                   total_residues, ws.senders, ws.edge_feat, ws.prep, ws.status);
+  int count;
+  {
+    PstSpan span(m, st, 0);
+    count = pst_launch_featurize(m, st, atoms, atom_mask, atoms_per_residue, offsets, num_structures,
+                                 total_residues, ws.senders, ws.edge_feat, ws.prep, ws.status);
+  }
   int n = pst_launch_encode_fp32(m, st, ws.edge_feat, ws.senders, offsets, token_offsets, num_structures,
                                  total_residues, total_tokens, ws.z, ws);
   if (n < 0) return n;

@@ -340,6 +340,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     // message MLP, first linear factorised: [h_s|h_r|e].W1 = (h.W1[0:128])[s] + (h.W1[128:256])[r] + e.W1[256:384]
     L.gemm(ws.h, w.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr));
     L.gemm(ws.h, w.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.msg_b1));
+    PstSpan* span = new PstSpan(m, st, 1);
     if (tc) {
       int n = pst_launch_edge_mlp_tc(m, st, l, 0, ws.e, ws.ps, ws.pr, senders, offsets, B, R, ws.agg);
       if (n < 0) return n;
@@ -353,6 +354,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       segment_mean_kernel<<<(R + 7) / 8, 256, 0, st>>>(ws.t1, K, ws.agg, R);
       ++L.count;
     }
+    delete span;
     L.add_ln(ws.h, ws.agg, w.ln0_s, w.ln0_o, ws.h, R);
     // feed-forward 128 -> 512 -> 128
     L.gemm(ws.h, w.ffn_w1, ws.u, R, PST_FFN, D, Launcher::epi(w.ffn_b1, 1));
@@ -361,6 +363,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     if (l == cfg.gnn_layers - 1) break;  // the last layer's edge update is never read (model.py:385)
     L.gemm(ws.h, w.edge_w1, ws.ps, R, D, D, Launcher::epi(nullptr));
     L.gemm(ws.h, w.edge_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.edge_b1));
+    span = new PstSpan(m, st, 2);
     if (tc) {
       int n = pst_launch_edge_mlp_tc(m, st, l, 1, ws.e, ws.ps, ws.pr, senders, offsets, B, R, nullptr);
       if (n < 0) return n;
@@ -373,6 +376,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       L.gemm(ws.t2, w.edge_w3, ws.t1, E, D, D, Launcher::epi(w.edge_b3));
       L.add_ln(ws.e, ws.t1, w.ln2_s, w.ln2_o, ws.e, E);
     }
+    delete span;
   }
 
   // ---- resampler (CrossAttentionScaler, 3 blocks) -------------------------------------------

@@ -14,6 +14,8 @@
 #define PST_C8 PST_MAX_LEVELS
 #define PST_FEAT_PAD 32   // 27 edge features padded to 32 GEMM rows
 #define PST_PREP_STRIDE 16 // doubles per residue in the prep record
+#define PST_PROF_MAX_SPANS 64
+#define PST_PROF_KINDS 4   // 0 featurise+knn, 1 message MLP, 2 edge-update MLP, 3 rest of the encoder
 
 // ---- prepared weight blob (fp32), see pst/weights.py for the packer ----------
 struct PstLayerW {
@@ -63,6 +65,24 @@ struct pst_model {
   float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
   int32_t basis[PST_C8], half_width[PST_C8];
   mutable int launch_count;
+  // optional per-kernel-group timing (pst_profile_*): CUDA events recorded on the call's stream
+  mutable bool prof_on;
+  mutable int prof_n;
+  mutable cudaEvent_t prof_ev[2 * PST_PROF_MAX_SPANS];
+  mutable int prof_kind[PST_PROF_MAX_SPANS];
+};
+
+// RAII span: records an event pair around a group of launches when profiling is enabled
+struct PstSpan {
+  const pst_model* m; cudaStream_t st; int idx;
+  PstSpan(const pst_model* m_, cudaStream_t st_, int kind) : m(m_), st(st_), idx(-1) {
+    if (m->prof_on && m->prof_n < PST_PROF_MAX_SPANS) {
+      idx = m->prof_n++;
+      m->prof_kind[idx] = kind;
+      cudaEventRecord(m->prof_ev[2 * idx], st);
+    }
+  }
+  ~PstSpan() { if (idx >= 0) cudaEventRecord(m->prof_ev[2 * idx + 1], st); }
 };
 
 size_t pst_fill_weight_pointers(const pst_config& cfg, const float* base, PstWeights* w);

@@ -47,6 +47,8 @@ SIGNATURES = {
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "pst_read_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pst_last_launch_count": (C.c_int, [C.c_void_p]),
+    "pst_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "pst_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
 
 _lib = None

@@ -157,6 +157,17 @@ class StructureTokenizer:
         self.launches = self.lib.pst_last_launch_count(self._h)
         return tokens
 
+    def profile_enable(self, on: bool = True) -> None:
+        _lib.check(self.lib.pst_profile_enable(self._h, int(on)), "pst_profile_enable")
+
+    def profile_collect(self):
+        """-> (ms[4], groups[4]) accumulated since the last collect; kinds: 0 featurise+k-NN,
+        1 message MLP, 2 edge-update MLP."""
+        ms = (C.c_float * 4)()
+        cnt = (C.c_int * 4)()
+        _lib.check(self.lib.pst_profile_collect(self._h, ms, cnt), "pst_profile_collect")
+        return list(ms), list(cnt)
+
     def read_status(self) -> int:
         return self.lib.pst_read_status(self._h, self._stream(), self._ws.data_ptr()) if self._ws is not None else 0
 
