@@ -1,5 +1,507 @@
-// placeholder until the tcgen05 kernel lands
+// Edge-level MLPs of the MPNN layers on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Reference op (structure_tokenizer/model/gnn_layers.py:344-361 and :402-436):
+//     MLP_{384->128->128->128}([h_s | h_r | e])  with GELU(tanh) between the linears,
+//   message mode : agg = mean over the K edges of a receiver                (:364-377)
+//   update  mode : e   = MaskedLayerNorm(e + MLP(...))                        (:421-436)
+// The first linear is factorised, [h_s|h_r|e].W1 = (h.W1[0:128])[s] + (h.W1[128:256] + b1)[r] + e.W1[256:384]:
+// the two node-level products (ps, pr) are computed once per residue by the fp32 SGEMM and gathered
+// in this kernel's first epilogue, so only K = 128 goes through the tensor core per edge.  In message
+// mode the third linear commutes with the mean over K (no activation follows it), so it is applied to
+// the per-receiver mean of the second hidden layer by the caller: this kernel returns partial row sums.
+//
+// Structure: persistent CTAs (one per SM, 512 threads).  The three 128x128 16-bit weight matrices of
+// the MLP stay resident in shared memory (96 KB, canonical K-major SWIZZLE_128B UMMA layout, image
+// built once at model load).  Four independent "tile groups" of 4 warps each own a 128-edge tile, a
+// 32 KB A-operand buffer and a 128-column fp32 accumulator in TMEM (4 x 128 = all 512 columns); a
+// group runs   load e -> MMA1 -> epilogue1 (gather+GELU, fp32 regs -> 16-bit smem) -> MMA2 ->
+// epilogue2 -> [MMA3 -> epilogue3 (residual + LayerNorm)]   serially, and the four groups interleave
+// on the SM so one group's MMA overlaps the others' epilogues.  In the 32x32b TMEM load layout each
+// thread owns one accumulator row (= one edge), so the LayerNorm and the gathers are thread-local.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "pst_internal.h"
-int pst_prepare_tc_weights(pst_model*) { return PST_ERR_UNSUPPORTED_CONFIG; }
-int pst_launch_edge_mlp_tc(const pst_model*, cudaStream_t, int, int, float*, const float*, const float*,
-                           const int32_t*, const int32_t*, int, int, float*) { return PST_ERR_UNSUPPORTED_CONFIG; }
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kD = 128;
+constexpr int kGroups = 4;
+constexpr int kThreads = kGroups * 128;
+constexpr uint32_t kMatBytes = 128 * 128 * 2;  // one 16-bit 128x128 operand image
+constexpr uint32_t kKBlockBytes = 128 * 128;    // 128 rows x 64 elements x 2 B
+constexpr uint32_t kSmemW = 3 * kMatBytes;
+constexpr uint32_t kSmemA = kGroups * kMatBytes;
+constexpr uint32_t kSmemVec = 4 * 128 * sizeof(float);  // b2, b3, ln scale, ln offset
+constexpr uint32_t kSmemMisc = 256;
+constexpr uint32_t kSmemTotal = kSmemW + kSmemA + kSmemVec + kSmemMisc;
+static_assert(kSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+
+struct EdgeMlpParams {
+  const uint16_t* w_image;  // 3 x 32 KB pre-swizzled operand images (global)
+  const float* b2;
+  const float* b3;
+  const float* ln_s;
+  const float* ln_o;
+  float* e;                 // [E,128] fp32 (read; written in update mode)
+  const float* ps;          // [R,128]
+  const float* pr;          // [R,128] (includes b1)
+  const int32_t* senders;   // [E] local indices
+  const int32_t* row_base;  // [R]
+  float* partial;           // message mode: [num_tiles][4][128] partial row sums of the 2nd hidden layer
+  int E;
+  int K;
+  int num_tiles;
+  uint32_t idesc;
+};
+
+// byte offset of element (row, k) inside a 128x128 16-bit K-major SWIZZLE_128B operand image
+__host__ __device__ __forceinline__ uint32_t swz_offset(uint32_t row, uint32_t k) {
+  uint32_t kb = k >> 6, kk = k & 63;
+  return kb * kKBlockBytes + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_128B, 8-row atoms of 1024 B: SBO = 1024, LBO unused, version 1 (Blackwell)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_addr) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// GELU, tanh form (jax.nn.gelu default):  x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float a = -2.302208198f;   // -2 * sqrt(2/pi) * log2(e)
+  const float b = -0.1029432397f;  // a * 0.044715
+  float t = x * x;
+  float ex = exp2f(x * fmaf(b, t, a));
+  return __fdividef(x, 1.0f + ex);
+}
+
+template <typename T16>
+struct Pack;
+template <>
+struct Pack<__half> {
+  static __device__ __forceinline__ uint32_t two(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+template <>
+struct Pack<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t two(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+
+// writes 32 consecutive K-elements [k0, k0+32) of `row` into the group's A image
+template <typename T16>
+__device__ __forceinline__ void store_a_chunk(uint8_t* sA, int row, int k0, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 pk;
+    pk.x = Pack<T16>::two(v[c * 8 + 0], v[c * 8 + 1]);
+    pk.y = Pack<T16>::two(v[c * 8 + 2], v[c * 8 + 3]);
+    pk.z = Pack<T16>::two(v[c * 8 + 4], v[c * 8 + 5]);
+    pk.w = Pack<T16>::two(v[c * 8 + 6], v[c * 8 + 7]);
+    *reinterpret_cast<uint4*>(sA + swz_offset(row, k0 + c * 8)) = pk;
+  }
+}
+
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, uint32_t sA_addr, uint32_t sW_addr, uint32_t idesc,
+                                           uint32_t mbar_addr) {
+  tc_fence_after();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {  // K = 128 = 8 x UMMA_K(16); 4 steps per 64-element swizzle block
+    uint32_t off = (j >> 2) * kKBlockBytes + (j & 3) * 32;
+    umma_f16(tmem_acc, make_smem_desc(sA_addr + off), make_smem_desc(sW_addr + off), idesc, j > 0 ? 1u : 0u);
+  }
+  umma_commit(mbar_addr);
+}
+
+template <typename T16, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sAall = smem + kSmemW;
+  float* sVec = reinterpret_cast<float*>(smem + kSmemW + kSmemA);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemW + kSmemA + kSmemVec);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kGroups);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int g = warp >> 2;          // tile group
+  const int gt = tid & 127;         // thread within the group == accumulator row
+  const int wq = warp & 3;          // TMEM lane quarter this warp may access
+  uint8_t* sA = sAall + g * kMatBytes;
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.w_image);
+    uint4* dst = reinterpret_cast<uint4*>(sW);
+    const int n16 = (MODE == 0 ? 2 : 3) * (int)(kMatBytes / 16);
+    for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
+    if (tid < 128) {
+      sVec[tid] = p.b2[tid];
+      sVec[128 + tid] = MODE == 1 ? p.b3[tid] : 0.f;
+      sVec[256 + tid] = MODE == 1 ? p.ln_s[tid] : 0.f;
+      sVec[384 + tid] = MODE == 1 ? p.ln_o[tid] : 0.f;
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc = tmem_base + (uint32_t)(g * 128);                 // column offset of this group
+  const uint32_t tmem_row = tmem_acc + ((uint32_t)(wq * 32) << 16);          // + lane quarter of this warp
+  const uint32_t sA_addr = smem_u32(sA);
+  const uint32_t sW_addr = smem_u32(sW);
+  const uint32_t mbar_addr = smem_u32(&mbar[g]);
+  uint32_t parity = 0;
+
+  for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
+    const int row0 = tile * kTileM;
+    // ---- 1. e tile (fp32, global) -> 16-bit A image; 16 threads per row, 8 rows per pass --------
+    {
+      const int sub = gt >> 4, c8 = gt & 15;
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const int r = it * 8 + sub;
+        const int er = row0 + r;
+        float4 x0 = make_float4(0, 0, 0, 0), x1 = x0;
+        if (er < p.E) {
+          const float4* src = reinterpret_cast<const float4*>(p.e + (size_t)er * kD + c8 * 8);
+          x0 = src[0];
+          x1 = src[1];
+        }
+        uint4 pk;
+        pk.x = Pack<T16>::two(x0.x, x0.y);
+        pk.y = Pack<T16>::two(x0.z, x0.w);
+        pk.z = Pack<T16>::two(x1.x, x1.y);
+        pk.w = Pack<T16>::two(x1.z, x1.w);
+        *reinterpret_cast<uint4*>(sA + swz_offset(r, c8 * 8)) = pk;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    group_sync(g);
+    // ---- 2. GEMM 1: e . W1[256:384] ----------------------------------------------------------------
+    if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr, p.idesc, mbar_addr);
+    const int er = row0 + gt;
+    const bool valid = er < p.E;
+    const int recv = valid ? er / p.K : 0;
+    const float* ps_row = p.ps + (size_t)(valid ? p.row_base[recv] + p.senders[er] : 0) * kD;
+    const float* pr_row = p.pr + (size_t)recv * kD;
+    mbar_wait(mbar_addr, parity);
+    parity ^= 1;
+    tc_fence_after();
+    // ---- 3. epilogue 1: + ps[sender] + pr[receiver] (b1 folded), GELU -> A image ------------------------
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      float v[32];
+      tmem_ld32(tmem_row + q * 32, v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(ps_row + q * 32 + c * 4));
+        float4 b = __ldg(reinterpret_cast<const float4*>(pr_row + q * 32 + c * 4));
+        v[c * 4 + 0] = gelu_fast(v[c * 4 + 0] + a.x + b.x);
+        v[c * 4 + 1] = gelu_fast(v[c * 4 + 1] + a.y + b.y);
+        v[c * 4 + 2] = gelu_fast(v[c * 4 + 2] + a.z + b.z);
+        v[c * 4 + 3] = gelu_fast(v[c * 4 + 3] + a.w + b.w);
+      }
+      store_a_chunk<T16>(sA, gt, q * 32, v);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    group_sync(g);
+    // ---- 4. GEMM 2 ----------------------------------------------------------------------------------
+    if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + kMatBytes, p.idesc, mbar_addr);
+    mbar_wait(mbar_addr, parity);
+    parity ^= 1;
+    tc_fence_after();
+    if (MODE == 1) {
+      // ---- 5a. epilogue 2: + b2, GELU -> A image; GEMM 3; epilogue 3: residual + LayerNorm -------------
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float v[32];
+        tmem_ld32(tmem_row + q * 32, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = gelu_fast(v[c] + sVec[q * 32 + c]);
+        store_a_chunk<T16>(sA, gt, q * 32, v);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      group_sync(g);
+      if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + 2 * kMatBytes, p.idesc, mbar_addr);
+      mbar_wait(mbar_addr, parity);
+      parity ^= 1;
+      tc_fence_after();
+      float* e_row = p.e + (size_t)(valid ? er : 0) * kD;
+      float sum = 0.f, sumsq = 0.f;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float v[32];
+        tmem_ld32(tmem_row + q * 32, v);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 r = valid ? *reinterpret_cast<const float4*>(e_row + q * 32 + c * 4) : make_float4(0, 0, 0, 0);
+          v[c * 4 + 0] += sVec[128 + q * 32 + c * 4 + 0] + r.x;
+          v[c * 4 + 1] += sVec[128 + q * 32 + c * 4 + 1] + r.y;
+          v[c * 4 + 2] += sVec[128 + q * 32 + c * 4 + 2] + r.z;
+          v[c * 4 + 3] += sVec[128 + q * 32 + c * 4 + 3] + r.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          sum += v[c];
+          sumsq = fmaf(v[c], v[c], sumsq);
+        }
+        tmem_st32(tmem_row + q * 32, v);
+      }
+      const float mean = sum * (1.0f / kD);
+      const float var = fmaxf(sumsq * (1.0f / kD) - mean * mean, 0.f);
+      const float inv = rsqrtf(var + 1e-5f);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float v[32];
+        tmem_ld32(tmem_row + q * 32, v);
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 o;
+            o.x = sVec[256 + q * 32 + c * 4 + 0] * inv * (v[c * 4 + 0] - mean) + sVec[384 + q * 32 + c * 4 + 0];
+            o.y = sVec[256 + q * 32 + c * 4 + 1] * inv * (v[c * 4 + 1] - mean) + sVec[384 + q * 32 + c * 4 + 1];
+            o.z = sVec[256 + q * 32 + c * 4 + 2] * inv * (v[c * 4 + 2] - mean) + sVec[384 + q * 32 + c * 4 + 2];
+            o.w = sVec[256 + q * 32 + c * 4 + 3] * inv * (v[c * 4 + 3] - mean) + sVec[384 + q * 32 + c * 4 + 3];
+            *reinterpret_cast<float4*>(e_row + q * 32 + c * 4) = o;
+          }
+        }
+      }
+    } else {
+      // ---- 5b. epilogue 2 (message mode): + b2, GELU, partial sums over the rows of each receiver ------
+      // scratch: the group's A buffer is free now; [128 rows][33] floats
+      float* scratch = reinterpret_cast<float*>(sA);
+      float* part = scratch + 128 * 33;  // [4 quarters][4 segments][32 cols]
+      const int first_recv = row0 / p.K;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float v[32];
+        tmem_ld32(tmem_row + q * 32, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) scratch[gt * 33 + c] = valid ? gelu_fast(v[c] + sVec[q * 32 + c]) : 0.f;
+        group_sync(g);
+        {
+          const int col = gt & 31, quarter = gt >> 5;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int r = 0; r < 32; ++r) {
+            const int rr = quarter * 32 + r;
+            const int seg = (row0 + rr) / p.K - first_recv;
+            const float x = scratch[rr * 33 + col];
+            acc[0] += seg == 0 ? x : 0.f;
+            acc[1] += seg == 1 ? x : 0.f;
+            acc[2] += seg == 2 ? x : 0.f;
+            acc[3] += seg == 3 ? x : 0.f;
+          }
+#pragma unroll
+          for (int s = 0; s < 4; ++s) part[(quarter * 4 + s) * 32 + col] = acc[s];
+        }
+        group_sync(g);
+        {
+          const int s = gt >> 5, col = gt & 31;  // 4 segments x 32 columns
+          float t = part[(0 * 4 + s) * 32 + col] + part[(1 * 4 + s) * 32 + col] + part[(2 * 4 + s) * 32 + col] +
+                    part[(3 * 4 + s) * 32 + col];
+          p.partial[((size_t)tile * 4 + s) * kD + q * 32 + col] = t;
+        }
+        group_sync(g);
+      }
+    }
+    // TMEM reads of this tile must be complete before the next tile's MMA overwrites the accumulator:
+    // ordered by the tcgen05.fence::before_thread_sync + group barrier at the top of the next iteration.
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// tbar[r] = (sum of the partial row sums that cover receiver r) / K
+__global__ void combine_partials_kernel(const float* __restrict__ partial, int K, int R, float* __restrict__ tbar) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const int e0 = row * K, e1 = e0 + K - 1;
+  const int t0 = e0 / kTileM, t1 = e1 / kTileM;
+  float4 s = make_float4(0, 0, 0, 0);
+  for (int t = t0; t <= t1; ++t) {
+    const int seg = row - (t * kTileM) / K;
+    float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)t * 4 + seg) * kD + lane * 4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const float kf = (float)K;
+  *reinterpret_cast<float4*>(tbar + (size_t)row * kD + lane * 4) = make_float4(s.x / kf, s.y / kf, s.z / kf, s.w / kf);
+}
+
+template <typename T16>
+__global__ void build_weight_image_kernel(const float* __restrict__ w, uint16_t* __restrict__ image) {
+  // w: fp32 [128 (k), 128 (n)] row-major; image element (n, k) at swz_offset(n, k)
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * 128) return;
+  int k = idx >> 7, n = idx & 127;
+  T16 v = T16(w[idx]);
+  image[swz_offset(n, k) >> 1] = *reinterpret_cast<uint16_t*>(&v);
+}
+
+}  // namespace
+
+int pst_prepare_tc_weights(pst_model* m) {
+  const int layers = m->cfg.gnn_layers;
+  const size_t per_mlp = 3 * (size_t)kMatBytes;
+  const size_t total = (size_t)layers * 2 * per_mlp;
+  if (cudaMalloc(&m->tc_dev, total) != cudaSuccess) return PST_ERR_CUDA;
+  m->tc.w = m->tc_dev;
+  for (int l = 0; l < layers; ++l) {
+    const PstLayerW& L = m->w.layer[l];
+    const float* src[2][3] = {{L.msg_w1 + 2 * kD * kD, L.msg_w2, L.msg_w3}, {L.edge_w1 + 2 * kD * kD, L.edge_w2, L.edge_w3}};
+    for (int t = 0; t < 2; ++t)
+      for (int j = 0; j < 3; ++j) {
+        uint16_t* dst = m->tc_dev + ((size_t)(l * 2 + t) * per_mlp + (size_t)j * kMatBytes) / 2;
+        if (m->cfg.precision == PST_PREC_FP16)
+          build_weight_image_kernel<__half><<<64, 256>>>(src[t][j], dst);
+        else
+          build_weight_image_kernel<__nv_bfloat16><<<64, 256>>>(src[t][j], dst);
+      }
+  }
+  if (cudaGetLastError() != cudaSuccess) return PST_ERR_CUDA;
+  cudaError_t e1 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+  cudaError_t e2 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+  cudaError_t e3 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+  cudaError_t e4 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) return PST_ERR_CUDA;
+  return PST_OK;
+}
+
+size_t pst_tc_partial_floats(int R, int K) {
+  size_t tiles = ((size_t)R * K + kTileM - 1) / kTileM;
+  return tiles * 4 * kD;
+}
+
+// mode 0: writes tbar (mean over K of the 2nd hidden layer) into agg_out[R,128]; the caller applies W3, b3.
+// mode 1: e <- LN(e + MLP).
+int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, float* e, const float* ps,
+                           const float* pr, const int32_t* senders, const int32_t* row_base, float* partial, int R,
+                           float* agg_out) {
+  const int K = m->cfg.num_neighbor;
+  const PstLayerW& L = m->w.layer[layer];
+  EdgeMlpParams p{};
+  p.w_image = m->tc.w + ((size_t)(layer * 2 + mode) * 3 * kMatBytes) / 2;
+  p.b2 = mode == 0 ? L.msg_b2 : L.edge_b2;
+  p.b3 = mode == 0 ? L.msg_b3 : L.edge_b3;
+  p.ln_s = L.ln2_s;
+  p.ln_o = L.ln2_o;
+  p.e = e;
+  p.ps = ps;
+  p.pr = pr;
+  p.senders = senders;
+  p.row_base = row_base;
+  p.partial = partial;
+  p.E = R * K;
+  p.K = K;
+  p.num_tiles = (p.E + kTileM - 1) / kTileM;
+  const uint32_t fmt = m->cfg.precision == PST_PREC_FP16 ? 0u : 1u;  // F16 / BF16
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kD >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  if (p.num_tiles == 0) return 0;
+  if (K < 43) return PST_ERR_UNSUPPORTED_CONFIG;  // a 128-row tile must touch at most 4 receivers
+  int grid = m->num_sms;
+  const int need = (p.num_tiles + kGroups - 1) / kGroups;
+  if (grid > need) grid = need;
+  const bool half = m->cfg.precision == PST_PREC_FP16;
+  if (mode == 0) {
+    if (half) edge_mlp_tc_kernel<__half, 0><<<grid, kThreads, kSmemTotal, st>>>(p);
+    else edge_mlp_tc_kernel<__nv_bfloat16, 0><<<grid, kThreads, kSmemTotal, st>>>(p);
+    combine_partials_kernel<<<(R + 7) / 8, 256, 0, st>>>(partial, K, R, agg_out);
+    return 2;
+  }
+  if (half) edge_mlp_tc_kernel<__half, 1><<<grid, kThreads, kSmemTotal, st>>>(p);
+  else edge_mlp_tc_kernel<__nv_bfloat16, 1><<<grid, kThreads, kSmemTotal, st>>>(p);
+  return 1;
+}

@@ -342,9 +342,12 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     L.gemm(ws.h, w.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.msg_b1));
     PstSpan* span = new PstSpan(m, st, 1);
     if (tc) {
-      int n = pst_launch_edge_mlp_tc(m, st, l, 0, ws.e, ws.ps, ws.pr, senders, offsets, B, R, ws.agg);
+      // tensor-core path returns the per-receiver mean of the 2nd hidden layer; the 3rd linear
+      // commutes with that mean (no activation follows it): agg = mean_K(T2) . W3 + b3
+      int n = pst_launch_edge_mlp_tc(m, st, l, 0, ws.e, ws.ps, ws.pr, senders, row_base, ws.partial, R, ws.tmp);
       if (n < 0) return n;
       L.count += n;
+      L.gemm(ws.tmp, w.msg_w3, ws.agg, R, D, D, Launcher::epi(w.msg_b3));
     } else {
       GemmEpi g = Launcher::epi(nullptr, 1);
       g.gather_s = ws.ps; g.gather_r = ws.pr; g.senders = senders; g.row_base = row_base; g.knn = K;
@@ -365,7 +368,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     L.gemm(ws.h, w.edge_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.edge_b1));
     span = new PstSpan(m, st, 2);
     if (tc) {
-      int n = pst_launch_edge_mlp_tc(m, st, l, 1, ws.e, ws.ps, ws.pr, senders, offsets, B, R, nullptr);
+      int n = pst_launch_edge_mlp_tc(m, st, l, 1, ws.e, ws.ps, ws.pr, senders, row_base, ws.partial, R, nullptr);
       if (n < 0) return n;
       L.count += n;
     } else {

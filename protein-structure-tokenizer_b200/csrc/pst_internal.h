@@ -97,6 +97,7 @@ struct PstWorkspace {
   float* e;              // [E,128]
   float* t1;             // [E,128]   (fp32 mode only)
   float* t2;             // [E,128]   (fp32 mode only)
+  float* partial;        // [tiles,4,128] (tensor-core modes only)
   float* h;              // [R,128]
   float* agg;            // [R,128]
   float* ps;             // [R,128]
@@ -138,7 +139,8 @@ int pst_launch_indexes_to_codes(const pst_model* m, cudaStream_t st, const int32
 // mode 1: edge update -> e = LN(e + MLP).  Returns kernels launched, <0 on error.
 int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, float* e,
                            const float* ps, const float* pr, const int32_t* senders,
-                           const int32_t* offsets, int B, int R, float* agg_out);
+                           const int32_t* row_base, float* partial, int R, float* agg_out);
+size_t pst_tc_partial_floats(int R, int K);
 
 #define PST_CUDA_OK(expr)                                  \
   do {                                                     \

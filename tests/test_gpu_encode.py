@@ -116,3 +116,42 @@ def test_tokenize_end_to_end_matches_oracle(built_lib, codebook, df):
         total += len(tr)
     assert agree / total > 0.995
     assert tok.launches > 0
+
+
+@pytest.mark.parametrize("precision,codebook,df,mean_tol,max_tol,min_agree", [
+    ("fp16", 4096, 1, 5e-4, 6e-3, 0.995),
+    ("fp16", 64000, 4, 5e-4, 6e-3, 0.99),
+    ("bf16", 4096, 1, 5e-3, 5e-2, 0.95),
+])
+def test_tensor_core_modes_match_oracle(built_lib, precision, codebook, df, mean_tol, max_tol, min_agree):
+    """tcgen05 edge-level MLPs (16-bit operands, fp32 accumulate) against the fp32 oracle.
+    Stated tolerance on the pre-quantisation latents z (|z| ~ 1): fp16 operands mean |dz| <= 5e-4,
+    max <= 6e-3; bf16 operands mean <= 5e-3, max <= 5e-2."""
+    import torch
+    from oracle import model as om
+
+    lengths = [64, 101, 256, 50, 190, 77]
+    cfg, params, tok, bbs, graphs = _setup(codebook, df, precision, lengths)
+    ocfg = _oracle_cfg(cfg)
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)
+    toff = tok.token_offsets(offs)
+    feats = np.concatenate([g["edge_features"].astype(np.float32) for g in graphs])
+    send = np.concatenate([g["senders"].astype(np.int32) for g in graphs])
+    z = tok.encode_graph_device(torch.from_numpy(feats).cuda(), torch.from_numpy(send).cuda(), torch.from_numpy(offs).cuda(),
+                                torch.from_numpy(toff).cuda(), len(lengths), int(offs[-1]), int(toff[-1]))
+    tokens = tok.quantize_device(z)
+    torch.cuda.synchronize()
+    z, tokens = z.cpu().numpy(), tokens.cpu().numpy()
+    C = len(cfg.levels)
+    errs, agree, total = [], 0, 0
+    for i, g in enumerate(graphs):
+        zr = om.encode(params, ocfg, g["edge_features"], g["senders"], g["n_node"])
+        sl = slice(toff[i], toff[i + 1])
+        errs.append(np.abs(z[sl, :C] - zr).ravel())
+        tr = om.fsq_tokens(zr, cfg.levels)
+        agree += int((tokens[sl].astype(np.uint32) == tr).sum())
+        total += len(tr)
+    errs = np.concatenate(errs)
+    assert np.isfinite(z).all()
+    assert errs.mean() <= mean_tol and errs.max() <= max_tol, (float(errs.mean()), float(errs.max()))
+    assert agree / total >= min_agree, agree / total
