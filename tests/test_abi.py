@@ -1,0 +1,88 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/pst_abi.h declares.
+No compute call is made here (there is no GPU); host-only entry points are exercised."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "pst_abi.h")) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pst_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    lib = C.CDLL(built_lib)
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in pst_abi.h but not exported"
+
+
+def test_python_binding_covers_the_header(built_lib):
+    from pst import _lib
+
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+    lib = _lib.load()
+    assert lib.pst_abi_version() == 1
+    assert lib.pst_status_string(-3).decode().startswith("structure length")
+
+
+def test_blob_size_matches_packer(built_lib):
+    from pst import _lib
+    from pst.config import TokenizerConfig
+    from pst.weights import init_params, pack_weights
+
+    lib = _lib.load()
+    for codebook, df, seq in ((4096, 1, 512), (64000, 4, 512), (432, 1, 512), (64000, 1, 1024)):
+        cfg = TokenizerConfig.named(codebook, df, seq_max_size=seq)
+        c = _lib.PstConfig()
+        c.abi_version = 1
+        c.seq_max_size, c.max_out_len, c.num_neighbor = cfg.seq_max_size, cfg.max_out_len, cfg.num_neighbor
+        c.downsampling_ratio, c.num_levels = cfg.downsampling_ratio, len(cfg.levels)
+        for i, l in enumerate(cfg.levels):
+            c.levels[i] = l
+        c.gnn_layers, c.num_blocks, c.precision, c.max_len = 3, 3, 1, cfg.max_len
+        blob = pack_weights(init_params(cfg, 0, "ref"), cfg)
+        assert lib.pst_weight_blob_floats(C.byref(c)) == blob.size
+
+
+def test_bad_config_and_no_device_are_reported_not_crashed(built_lib):
+    from pst import _lib
+
+    lib = _lib.load()
+    c = _lib.PstConfig()  # abi_version 0 -> unsupported
+    assert lib.pst_weight_blob_floats(C.byref(c)) == 0
+    h = C.c_void_p()
+    blob = np.zeros(4, np.float32)
+    assert lib.pst_model_create(C.byref(c), blob.ctypes.data, 4, 0, C.byref(h)) == -2
+    assert not h.value
+
+
+def test_product_fails_loudly_without_cuda(built_lib):
+    import torch
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    cfg = TokenizerConfig.named(4096, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        StructureTokenizer(cfg, init_params(cfg, 0, "ref"))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "protein-structure-tokenizer_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                with open(os.path.join(d, f)) as fh:
+                    src = fh.read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(d, f)

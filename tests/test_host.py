@@ -1,0 +1,85 @@
+"""Host-side logic (CPU): config composer, weight packing, synthetic generator."""
+import numpy as np
+import pytest
+
+
+def test_config_composer_matches_cli_selection():
+    from pst.config import CODEBOOK_SURNAME, TokenizerConfig, load_config
+
+    for size, df in ((4096, 1), (64000, 4), (432, 1), (1728, 1), (4096, 2)):
+        cfg = load_config("vq3d_inference", overrides=[f"model=gnn/ablation_{CODEBOOK_SURNAME[size]}_df_{df}.yaml", f"data=ablation_df_{df}.yaml"])
+        tc = TokenizerConfig.from_reference_cfg(cfg)
+        assert tc == TokenizerConfig.named(size, df)
+        assert tc.num_codes == size and cfg.model.model.codebook.num_codes == size
+        assert cfg.data.data.graph_max_neighbor == 50 and cfg.data.data.seq_max_size == 512
+        assert cfg.model.weight_paths == f"weights/{CODEBOOK_SURNAME[size]}_df_{df}/"
+    assert load_config("vq3d_inference").random_seed == 0
+
+
+def test_unsupported_configs_are_rejected():
+    from pst.config import TokenizerConfig, load_config
+
+    cfg = load_config("vq3d_inference")
+    cfg.model.model.encoder.gnn.gnn_layer.layer_cls = "GNNLayer"
+    with pytest.raises(NotImplementedError):
+        TokenizerConfig.from_reference_cfg(cfg)
+    with pytest.raises(ValueError):
+        TokenizerConfig(precision="int8")
+
+
+def test_init_params_follow_reference_rules():
+    from pst.config import TokenizerConfig
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(4096, 1)
+    p = init_params(cfg, 0, "ref")
+    w = p["mpnn_layer_1/edge_mlp/linear_0/w"]
+    assert w.shape == (384, 128)
+    std = np.sqrt(1 / 384)
+    assert abs(w.std() - std) / std < 0.05 and np.abs(w).max() <= 2 * std / 0.8796 + 1e-6
+    assert (p["mpnn_layer/node_mlp_0/linear_0/b"] == 0).all()
+    att = "cross_attn_downsampling/cross_attn_scaler_iteration/cross_attention/attention"
+    assert (p[f"{att}/gating_w"] == 0).all() and (p[f"{att}/gating_b"] == 1).all()
+    assert p[f"{att}/query_w"].shape == (3, 128, 4, 32)
+    q = p[f"{att}/query_w"]
+    assert abs(q.std() - np.sqrt(1 / 512)) / np.sqrt(1 / 512) < 0.05  # fan_in = 4*128 (Haiku conv-style rule)
+    s = init_params(cfg, 0, "spread")
+    assert np.allclose(s["down_proj/w"], 12 * p["down_proj/w"])
+    assert len(p) == 95
+
+
+def test_pack_weights_layout_and_suffix_matching():
+    from pst.config import TokenizerConfig
+    from pst.weights import init_params, pack_weights, pe_table
+
+    cfg = TokenizerConfig.named(4096, 1)
+    p = init_params(cfg, 1, "rich")
+    blob = pack_weights(p, cfg)
+    prefixed = {"vq3_d/~/" + k: v for k, v in p.items()}
+    assert np.array_equal(pack_weights(prefixed, cfg), blob)
+    node = blob[: 512 * 128].reshape(512, 128)
+    ref = pe_table(np.arange(512), 512) @ p["structure_encoder/init_node_embed/w"] + p["structure_encoder/init_node_embed/b"]
+    assert np.abs(node - ref).max() < 1e-5
+    wf = blob[512 * 128 + 1023 * 128 :][: 32 * 128].reshape(32, 128)
+    assert np.array_equal(wf[:27], p["structure_encoder/init_edge_embed/w"][128:]) and (wf[27:] == 0).all()
+    assert np.array_equal(blob[-8:-2], p["down_proj/b"]) and (blob[-2:] == 0).all()
+
+
+def test_synthetic_backbones_are_seeded_and_physical():
+    from pst import synthetic as syn
+
+    a = syn.make_backbones(123, [64, 96])
+    b = syn.make_backbones(123, [64, 96])
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    bb = a[1]
+    assert bb.dtype == np.float32 and bb.shape == (96, 4, 3)
+    assert np.array_equal(np.round(bb.astype(np.float64), 3).astype(np.float32), bb)
+    ca = bb[:, 1].astype(np.float64)
+    bond = np.linalg.norm(ca[1:] - ca[:-1], axis=-1)
+    assert np.abs(bond - 3.8).max() < 0.01
+    d = np.linalg.norm(ca[:, None] - ca[None], axis=-1) + 99 * np.eye(96)
+    assert d.min() > 3.4
+    atoms, offs = syn.pack_backbones(a)
+    assert atoms.shape == (160, 4, 3) and list(offs) == [0, 64, 160]
+    L = syn.bucketed_lengths(1, 1000)
+    assert L.min() >= 64 and L.max() <= 2048 and (L % 64 == 0).all()
