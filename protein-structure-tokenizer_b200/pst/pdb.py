@@ -1,0 +1,147 @@
+"""PDB text -> atom37 arrays for the tokenizer (host side of boundary B2).
+
+Mirrors `protein_structure_from_pdb_string` of the reference
+(structure_tokenizer/data/protein_structure_sample.py:166-248) and the BioPython PDBParser
+behaviour it depends on: ATOM/HETATM records of a single model, every chain concatenated in
+file order, atoms kept iff their name is one of the 37 atom37 types
+(data/residue_constants.py:539-577), unknown residue names mapped to UNK (N, CA, C, CB expected),
+ValueError on insertion codes and on multi-model files, coordinates stored as float32.
+Also the residue filter of data/preprocessing.py:72,99-117 (`valid_backbone`).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, NamedTuple, Tuple
+
+import numpy as np
+
+ATOM_TYPES: Tuple[str, ...] = (
+    "N", "CA", "C", "CB", "O", "CG", "CG1", "CG2", "OG", "OG1", "SG", "CD", "CD1", "CD2", "ND1", "ND2", "OD1", "OD2",
+    "SD", "CE", "CE1", "CE2", "CE3", "NE", "NE1", "NE2", "OE1", "OE2", "CH2", "NH1", "NH2", "OH", "CZ", "CZ2", "CZ3",
+    "NZ", "OXT",
+)
+ATOM_ORDER: Dict[str, int] = {n: i for i, n in enumerate(ATOM_TYPES)}
+N_INDEX, CA_INDEX, C_INDEX, CB_INDEX, O_INDEX = 0, 1, 2, 3, 4
+
+RESIDUE_ATOMS: Dict[str, Tuple[str, ...]] = {
+    "ALA": ("C", "CA", "CB", "N", "O"),
+    "ARG": ("C", "CA", "CB", "CG", "CD", "CZ", "N", "NE", "O", "NH1", "NH2"),
+    "ASP": ("C", "CA", "CB", "CG", "N", "O", "OD1", "OD2"),
+    "ASN": ("C", "CA", "CB", "CG", "N", "ND2", "O", "OD1"),
+    "CYS": ("C", "CA", "CB", "N", "O", "SG"),
+    "GLU": ("C", "CA", "CB", "CG", "CD", "N", "O", "OE1", "OE2"),
+    "GLN": ("C", "CA", "CB", "CG", "CD", "N", "NE2", "O", "OE1"),
+    "GLY": ("C", "CA", "N", "O"),
+    "HIS": ("C", "CA", "CB", "CG", "CD2", "CE1", "N", "ND1", "NE2", "O"),
+    "ILE": ("C", "CA", "CB", "CG1", "CG2", "CD1", "N", "O"),
+    "LEU": ("C", "CA", "CB", "CG", "CD1", "CD2", "N", "O"),
+    "LYS": ("C", "CA", "CB", "CG", "CD", "CE", "N", "NZ", "O"),
+    "MET": ("C", "CA", "CB", "CG", "CE", "N", "O", "SD"),
+    "PHE": ("C", "CA", "CB", "CG", "CD1", "CD2", "CE1", "CE2", "CZ", "N", "O"),
+    "PRO": ("C", "CA", "CB", "CG", "CD", "N", "O"),
+    "SER": ("C", "CA", "CB", "N", "O", "OG"),
+    "THR": ("C", "CA", "CB", "CG2", "N", "O", "OG1"),
+    "TRP": ("C", "CA", "CB", "CG", "CD1", "CD2", "CE2", "CE3", "CZ2", "CZ3", "CH2", "N", "NE1", "O"),
+    "TYR": ("C", "CA", "CB", "CG", "CD1", "CD2", "CE1", "CE2", "CZ", "N", "O", "OH"),
+    "VAL": ("C", "CA", "CB", "CG1", "CG2", "N", "O"),
+}
+RESTYPE_ORDER = {r: i for i, r in enumerate(
+    ("ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE", "LEU", "LYS", "MET", "PHE", "PRO", "SER",
+     "THR", "TRP", "TYR", "VAL"))}
+_EXISTS = {r: np.isin(np.array(ATOM_TYPES), atoms) for r, atoms in RESIDUE_ATOMS.items()}
+_EXISTS["UNK"] = np.array([True] * 4 + [False] * 33)
+
+
+class StructureSample(NamedTuple):
+    nb_residues: int
+    aatype: np.ndarray               # int32 [n] (20 = unknown)
+    atom37_positions: np.ndarray     # float32 [n, 37, 3]
+    atom37_gt_exists: np.ndarray     # bool [n, 37]
+    atom37_atom_exists: np.ndarray   # bool [n, 37]
+
+    def valid_backbone(self) -> np.ndarray:
+        g = self.atom37_gt_exists
+        return g[:, CA_INDEX] & g[:, N_INDEX] & g[:, C_INDEX] & g[:, O_INDEX]
+
+    def device_arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(atoms f32 [n_valid, 37, 3], mask u8 [n_valid, 37]) -- what pst_featurize_knn / pst_tokenize take."""
+        keep = self.valid_backbone()
+        mask = (self.atom37_gt_exists & self.atom37_atom_exists)[keep]
+        return np.ascontiguousarray(self.atom37_positions[keep], np.float32), np.ascontiguousarray(mask, np.uint8)
+
+
+def structure_from_pdb_string(pdb_str: str) -> StructureSample:
+    residues: Dict[Tuple[str, str, int, str], dict] = {}
+    chain_order: List[str] = []
+    models = 0
+    in_model = False
+    loose_atoms = False
+    for line in pdb_str.splitlines():
+        tag = line[:6]
+        if tag.startswith("MODEL"):
+            models += 1
+            in_model = True
+            continue
+        if tag.startswith("ENDMDL"):
+            in_model = False
+            continue
+        if tag != "ATOM  " and tag != "HETATM":
+            continue
+        if not in_model:
+            loose_atoms = True
+        resname = line[17:20].strip()
+        chain = line[21]
+        het = " " if tag == "ATOM  " else ("W" if resname in ("HOH", "WAT") else "H_" + resname)
+        key = (chain, het, int(line[22:26]), line[26])
+        res = residues.get(key)
+        if res is None:
+            if chain not in chain_order:
+                chain_order.append(chain)
+            res = residues[key] = {"resname": resname, "atoms": {}}
+        name = line[12:16].strip()
+        altloc = line[16]
+        try:
+            occ = float(line[54:60])
+        except ValueError:
+            occ = 1.0
+        prev = res["atoms"].get(name)
+        if prev is None or (altloc != " " and prev[2] != " " and occ > prev[1]):
+            xyz = (np.float32(line[30:38]), np.float32(line[38:46]), np.float32(line[46:54]))
+            res["atoms"][name] = (xyz, occ, altloc)
+    n_models = models if models > 0 else (1 if loose_atoms else 0)
+    if n_models != 1:
+        raise ValueError(f"Only single model PDBs are supported. Found {n_models} models.")
+
+    pos_l, gt_l, ex_l, aa_l = [], [], [], []
+    for chain in chain_order:  # BioPython groups residues by chain, chains in order of first appearance
+        for (c, het, resseq, icode), res in residues.items():
+            if c != chain:
+                continue
+            if icode != " ":
+                raise ValueError(f"PDB contains an insertion code at chain {chain} and residue index {resseq}. These are not supported.")
+            rn = res["resname"] if res["resname"] in RESIDUE_ATOMS else "UNK"
+            pos = np.zeros((37, 3), np.float32)
+            gt = np.zeros(37, bool)
+            for name, (xyz, _, _) in res["atoms"].items():
+                slot = ATOM_ORDER.get(name)
+                if slot is not None:
+                    pos[slot] = xyz
+                    gt[slot] = True
+            if not gt.any():
+                continue
+            pos_l.append(pos)
+            gt_l.append(gt)
+            ex_l.append(_EXISTS[rn])
+            aa_l.append(RESTYPE_ORDER.get(rn, 20))
+    n = len(pos_l)
+    return StructureSample(
+        nb_residues=n,
+        aatype=np.asarray(aa_l, np.int32),
+        atom37_positions=np.asarray(pos_l, np.float32).reshape(n, 37, 3),
+        atom37_gt_exists=np.asarray(gt_l, bool).reshape(n, 37),
+        atom37_atom_exists=np.asarray(ex_l, bool).reshape(n, 37),
+    )
+
+
+def structure_from_pdb_file(path: str) -> StructureSample:
+    with open(path, "r") as fh:
+        return structure_from_pdb_string(fh.read())

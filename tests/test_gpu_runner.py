@@ -1,0 +1,68 @@
+"""InferenceRunner mirror end to end on the GPU: PDB files in, `<stem>_tokens.npy` out (reference file format)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tokenize_directory_of_pdbs(built_lib, tmp_path):
+    from oracle import featurize as fz
+    from oracle import model as om
+    from pst import synthetic as syn
+    from pst.config import load_config
+    from pst.inference_runner import InferenceRunner
+    from test_pdb import _pdb_from_backbone
+
+    pdb_dir = tmp_path / "pdbs"
+    pdb_dir.mkdir()
+    bbs = syn.make_backbones(31, [70, 120, 55])
+    for i, bb in enumerate(bbs):
+        (pdb_dir / f"S{i}.pdb").write_text(_pdb_from_backbone(bb))
+    cfg = load_config("vq3d_inference", overrides=["model=gnn/ablation_4k_df_1.yaml", "data=ablation_df_1.yaml"])
+    runner = InferenceRunner()
+    devices, n = runner.prepare_devices("gpu")
+    fn = runner.prepare_tokenize_fn(cfg, devices[:1], precision="fp32")
+    params = runner.load_params(str(tmp_path / "nope"), devices, cfg=fn.cfg, allow_random_init=True)
+    out_dir = str(tmp_path / "tokens")
+    files = sorted(str(p) for p in pdb_dir.iterdir())
+    runner.tokenize(None, fn, params, files, out_dir, 1, cfg.data.data, batch_size_per_device=2)
+    ocfg = om.OracleConfig(levels=list(fn.cfg.levels))
+    for i, bb in enumerate(bbs):
+        t = np.load(os.path.join(out_dir, f"S{i}_tokens.npy"))
+        assert t.dtype == np.uint32 and t.shape == (1, bb.shape[0])
+        pos, gt, ex = syn.backbone_to_atom37(bb)
+        g = fz.featurize(pos, gt, ex, 50)
+        ref = om.fsq_tokens(om.encode(params, ocfg, g["edge_features"], g["senders"], g["n_node"]), fn.cfg.levels)
+        assert (t[0] == ref).mean() > 0.99
+    with pytest.raises(FileExistsError):
+        runner.tokenize(None, fn, params, files, out_dir, 1, cfg.data.data)
+    with pytest.raises(FileNotFoundError):
+        runner.load_params(str(tmp_path / "nope"), devices)
+
+
+def test_casp14_tokens_fp16_agree_with_oracle(built_lib, casp14):
+    """BASELINE config 1 inputs (bundled CASP14 structures, 4k codebook, df=1) through the default fp16 mode."""
+    from conftest import valid_atoms
+    from oracle import featurize as fz
+    from oracle import model as om
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(4096, 1, precision="fp16")
+    params = init_params(cfg, 0, "spread")
+    tok = StructureTokenizer(cfg, params)
+    names = sorted(casp14)[:12]
+    structs, masks = zip(*[valid_atoms(casp14[n]) for n in names])
+    out = tok.tokenize(structs, masks)
+    ocfg = om.OracleConfig()
+    agree = total = 0
+    for n, t in zip(names, out):
+        e = casp14[n]
+        g = fz.featurize(e["pos"], e["gt"], e["exists"], 50)
+        ref = om.fsq_tokens(om.encode(params, ocfg, g["edge_features"], g["senders"], g["n_node"]), cfg.levels)
+        agree += int((t == ref).sum())
+        total += len(ref)
+    assert agree / total >= 0.995, agree / total

@@ -1,0 +1,96 @@
+"""PDB parser of the product against the oracle's independent restatement (CPU)."""
+import numpy as np
+import pytest
+
+from oracle import pdb_ref
+from pst import pdb as ppdb
+
+
+def _atom(serial, name, resname, chain, resseq, xyz, rec="ATOM", altloc=" ", icode=" ", occ=1.0, element="C"):
+    name_f = name if len(name) == 4 else " " + name.ljust(3)
+    return (f"{rec:<6}{serial:>5} {name_f}{altloc}{resname:>3} {chain}{resseq:>4}{icode}   "
+            f"{xyz[0]:8.3f}{xyz[1]:8.3f}{xyz[2]:8.3f}{occ:6.2f}{20.0:6.2f}          {element:>2}")
+
+
+def _pdb_from_backbone(bb, resname="GLY", chain="A"):
+    lines, s = [], 1
+    for i, res in enumerate(bb):
+        for name, xyz in zip(("N", "CA", "C", "O"), res):
+            lines.append(_atom(s, name, resname, chain, i + 1, xyz, element=name[0]))
+            s += 1
+    return "\n".join(lines + ["END"])
+
+
+def _same(a, b):
+    assert a.nb_residues == b["nb_residues"]
+    assert np.array_equal(a.atom37_positions.astype(np.float64), b["atom37_positions"])
+    assert np.array_equal(a.atom37_gt_exists, b["atom37_gt_exists"])
+    assert np.array_equal(a.atom37_atom_exists, b["atom37_atom_exists"])
+    assert np.array_equal(a.aatype, b["aatype"])
+
+
+def test_round_trip_of_a_synthetic_chain():
+    from pst import synthetic as syn
+
+    bb = syn.make_backbones(9, [60])[0]
+    text = _pdb_from_backbone(bb)
+    s = ppdb.structure_from_pdb_string(text)
+    _same(s, pdb_ref.parse_pdb(text))
+    atoms, mask = s.device_arrays()
+    assert atoms.shape == (60, 37, 3) and mask.sum() == 240
+    assert np.array_equal(atoms[:, [0, 1, 2, 4]], bb)  # 3-decimal fp32 coordinates survive the text round trip
+    assert (s.aatype == 7).all()
+
+
+def test_tricky_records():
+    L = []
+    L.append(_atom(1, "N", "ALA", "A", 1, (0, 0, 0)))
+    L.append(_atom(2, "CA", "ALA", "A", 1, (1.4, 0, 0)))
+    L.append(_atom(3, "C", "ALA", "A", 1, (2.0, 1.4, 0)))
+    L.append(_atom(4, "O", "ALA", "A", 1, (1.5, 2.4, 0)))
+    L.append(_atom(5, "CB", "ALA", "A", 1, (1.9, -0.8, 1.2)))
+    L.append(_atom(6, "HA", "ALA", "A", 1, (1.6, -0.5, -0.9), element="H"))      # hydrogen: dropped
+    L.append(_atom(7, "N", "MSE", "A", 2, (3.3, 1.5, 0)))                          # unknown residue -> UNK
+    L.append(_atom(8, "CA", "MSE", "A", 2, (4.0, 2.8, 0)))
+    L.append(_atom(9, "C", "MSE", "A", 2, (5.5, 2.6, 0)))
+    L.append(_atom(10, "O", "MSE", "A", 2, (6.0, 1.5, 0)))
+    L.append(_atom(11, "SE", "MSE", "A", 2, (4.0, 4.8, 1.0)))                      # not an atom37 name
+    L.append(_atom(12, "N", "SER", "A", 3, (6.2, 3.7, 0)))
+    L.append(_atom(13, "CA", "SER", "A", 3, (7.6, 3.7, 0), altloc="A", occ=0.4))
+    L.append(_atom(14, "CA", "SER", "A", 3, (7.7, 3.8, 0.1), altloc="B", occ=0.6))  # higher occupancy wins
+    L.append(_atom(15, "C", "SER", "A", 3, (8.2, 5.1, 0)))                          # O missing -> invalid residue
+    L.append(_atom(16, "O", "HOH", "A", 101, (20, 20, 20), rec="HETATM", element="O"))  # water: kept by the parser, dropped later
+    L.append(_atom(17, "N", "GLY", "B", 1, (30, 0, 0)))
+    L.append(_atom(18, "CA", "GLY", "B", 1, (31.4, 0, 0)))
+    L.append(_atom(19, "C", "GLY", "B", 1, (32.0, 1.4, 0)))
+    L.append(_atom(20, "O", "GLY", "B", 1, (31.5, 2.4, 0)))
+    text = "\n".join(L)
+    s = ppdb.structure_from_pdb_string(text)
+    _same(s, pdb_ref.parse_pdb(text))
+    assert s.nb_residues == 5
+    assert list(s.aatype) == [0, 20, 15, 20, 7]
+    assert list(s.valid_backbone()) == [True, True, False, False, True]
+    assert np.allclose(s.atom37_positions[2, 1], [7.7, 3.8, 0.1])
+    atoms, mask = s.device_arrays()
+    assert atoms.shape[0] == 3
+    assert mask[0].sum() == 5 and mask[1].sum() == 3  # UNK: O is excluded from the centroid mask
+
+
+def test_errors_match_the_reference():
+    ok = [_atom(1, "N", "GLY", "A", 1, (0, 0, 0)), _atom(2, "CA", "GLY", "A", 1, (1, 0, 0))]
+    ins = ok + [_atom(3, "N", "GLY", "A", 2, (3, 0, 0), icode="A")]
+    for parse in (ppdb.structure_from_pdb_string, pdb_ref.parse_pdb):
+        with pytest.raises(ValueError, match="insertion code"):
+            parse("\n".join(ins))
+        multi = "MODEL        1\n" + "\n".join(ok) + "\nENDMDL\nMODEL        2\n" + "\n".join(ok) + "\nENDMDL"
+        with pytest.raises(ValueError, match="single model"):
+            parse(multi)
+        single = "MODEL        1\n" + "\n".join(ok) + "\nENDMDL"
+        assert (parse(single).nb_residues if parse is ppdb.structure_from_pdb_string else parse(single)["nb_residues"]) == 1
+
+
+def test_parsed_casp14_fixture_is_what_the_parser_produces(casp14):
+    # the committed atom37 fixtures were produced by oracle/pdb_ref.py from the bundled files; sanity-check their shape
+    assert len(casp14) == 31
+    assert sum(e["pos"].shape[0] for e in casp14.values()) == 5618
+    assert sum(e["n_valid"] for e in casp14.values()) == 5616
