@@ -100,7 +100,7 @@ PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T) {
   ws.prep = (double*)take((size_t)R * PST_PREP_STRIDE * sizeof(double));
   ws.senders = (int32_t*)take(E * sizeof(int32_t));
   ws.edge_feat = (float*)take(E * PST_EDGE_FEATURES * sizeof(float));
-  ws.e = (float*)take(E * D * sizeof(float));
+  ws.e = (float*)take(E * D * (fp32 ? sizeof(float) : sizeof(uint16_t)));
   ws.t1 = (float*)take(fp32 ? E * D * sizeof(float) : 0);
   ws.t2 = (float*)take(fp32 ? E * D * sizeof(float) : 0);
   ws.partial = (float*)take(fp32 ? 0 : pst_tc_partial_floats(R, (int)K) * sizeof(float));

@@ -34,7 +34,7 @@ constexpr uint32_t kKBlockBytes = 128 * 128;    // 128 rows x 64 elements x 2 B
 constexpr uint32_t kSmemW = 3 * kMatBytes;
 constexpr uint32_t kSmemA = kGroups * kMatBytes;
 constexpr uint32_t kSmemVec = 4 * 128 * sizeof(float);  // b2, b3, ln scale, ln offset
-constexpr uint32_t kSmemMisc = 256;
+constexpr uint32_t kSmemMisc = 64;  // mbarriers + TMEM slot
 constexpr uint32_t kSmemTotal = kSmemW + kSmemA + kSmemVec + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 
@@ -44,7 +44,7 @@ struct EdgeMlpParams {
   const float* b3;
   const float* ln_s;
   const float* ln_o;
-  float* e;                 // [E,128] fp32 (read; written in update mode)
+  uint16_t* e;              // [E,128] 16-bit edge state (read; rewritten in update mode)
   const float* ps;          // [R,128]
   const float* pr;          // [R,128] (includes b1)
   const int32_t* senders;   // [E] local indices
@@ -137,13 +137,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// GELU, tanh form (jax.nn.gelu default):  x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)
+// GELU, tanh form (jax.nn.gelu default): 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3).
+// tanh.approx.f32 (one MUFU op, relative error 2^-11) is below the 16-bit rounding the result gets
+// when it is repacked as the next GEMM's operand; measured with the oracle: no change in token agreement.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float a = -2.302208198f;   // -2 * sqrt(2/pi) * log2(e)
-  const float b = -0.1029432397f;  // a * 0.044715
-  float t = x * x;
-  float ex = exp2f(x * fmaf(b, t, a));
-  return __fdividef(x, 1.0f + ex);
+  const float c0 = 0.7978845608f, c1 = 0.0356774081f;  // sqrt(2/pi), sqrt(2/pi) * 0.044715
+  float u = x * fmaf(c1, x * x, c0);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 template <typename T16>
@@ -163,6 +166,17 @@ struct Pack<__nv_bfloat16> {
   }
 };
 
+template <typename T16>
+struct Unpack;
+template <>
+struct Unpack<__half> {
+  static __device__ __forceinline__ float2 two(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+};
+template <>
+struct Unpack<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 two(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
+};
+
 // writes 32 consecutive K-elements [k0, k0+32) of `row` into the group's A image
 template <typename T16>
 __device__ __forceinline__ void store_a_chunk(uint8_t* sA, int row, int k0, const float (&v)[32]) {
@@ -178,14 +192,34 @@ __device__ __forceinline__ void store_a_chunk(uint8_t* sA, int row, int k0, cons
 }
 
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, uint32_t sA_addr, uint32_t sW_addr, uint32_t idesc,
-                                           uint32_t mbar_addr) {
+                                           uint32_t mbar_addr, uint32_t accumulate_first) {
   tc_fence_after();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {  // K = 128 = 8 x UMMA_K(16); 4 steps per 64-element swizzle block
     uint32_t off = (j >> 2) * kKBlockBytes + (j & 3) * 32;
-    umma_f16(tmem_acc, make_smem_desc(sA_addr + off), make_smem_desc(sW_addr + off), idesc, j > 0 ? 1u : 0u);
+    umma_f16(tmem_acc, make_smem_desc(sA_addr + off), make_smem_desc(sW_addr + off), idesc, j > 0 ? 1u : accumulate_first);
   }
   umma_commit(mbar_addr);
+}
+
+// ---- staging through the group's (currently free) 32 KB A buffer ---------------------------------
+// Global traffic is always issued row-coalesced (16 threads x float4 = 256 B of one row per request);
+// the thread-per-row view the TMEM 32x32b layout needs is obtained by a shared-memory transpose:
+// staging tile S = [128 rows][64 fp32], float4 slot j of row r stored at slot j ^ (r & 7)
+// (conflict-free for both the 16-threads-per-row and the thread-per-row access).
+__device__ __forceinline__ float4* stage_slot(float* S, int row, int j) {
+  return reinterpret_cast<float4*>(S + row * 64 + ((j ^ (row & 7)) << 2));
+}
+
+__device__ __forceinline__ void load_e_tile(uint8_t* sA, const uint16_t* e, int row0, int E, int sub, int c16) {
+#pragma unroll 8
+  for (int it = 0; it < 16; ++it) {
+    const int r = it * 8 + sub;
+    const int err = row0 + r;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (err < E) x = *(reinterpret_cast<const uint4*>(e + (size_t)err * kD) + c16);
+    *reinterpret_cast<uint4*>(sA + swz_offset(r, c16 * 8)) = x;
+  }
 }
 
 template <typename T16, int MODE>
@@ -203,6 +237,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   const int gt = tid & 127;         // thread within the group == accumulator row
   const int wq = warp & 3;          // TMEM lane quarter this warp may access
   uint8_t* sA = sAall + g * kMatBytes;
+  float* S = reinterpret_cast<float*>(sA);
+  const int sub = gt >> 4, c16 = gt & 15;  // 16 threads per row, 8 rows per pass
 
   // ---- one-time setup -------------------------------------------------------------------------
   {
@@ -240,61 +276,64 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
 
   for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
     const int row0 = tile * kTileM;
-    // ---- 1. e tile (fp32, global) -> 16-bit A image; 16 threads per row, 8 rows per pass --------
-    {
-      const int sub = gt >> 4, c8 = gt & 15;
-#pragma unroll 4
+    const int er = row0 + gt;
+    const bool valid = er < p.E;
+    tc_fence_before();  // previous tile's TMEM loads are complete (wait::ld) before anyone overwrites the accumulator
+    group_sync(g);
+    tc_fence_after();
+    // ---- 0. accumulator <- (h.W1a)[sender] + (h.W1b + b1)[receiver], staged through S ---------------
+#pragma unroll 1
+    for (int hq = 0; hq < 2; ++hq) {
+#pragma unroll 8
       for (int it = 0; it < 16; ++it) {
         const int r = it * 8 + sub;
-        const int er = row0 + r;
-        float4 x0 = make_float4(0, 0, 0, 0), x1 = x0;
-        if (er < p.E) {
-          const float4* src = reinterpret_cast<const float4*>(p.e + (size_t)er * kD + c8 * 8);
-          x0 = src[0];
-          x1 = src[1];
+        const int err = row0 + r;
+        int recv = 0, srow = 0;
+        if (err < p.E) {
+          recv = err / p.K;
+          srow = __ldg(p.row_base + recv) + __ldg(p.senders + err);
         }
-        uint4 pk;
-        pk.x = Pack<T16>::two(x0.x, x0.y);
-        pk.y = Pack<T16>::two(x0.z, x0.w);
-        pk.z = Pack<T16>::two(x1.x, x1.y);
-        pk.w = Pack<T16>::two(x1.z, x1.w);
-        *reinterpret_cast<uint4*>(sA + swz_offset(r, c8 * 8)) = pk;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.ps + (size_t)srow * kD + hq * 64) + c16);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.pr + (size_t)recv * kD + hq * 64) + c16);
+        *stage_slot(S, r, c16) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
       }
+      group_sync(g);
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = *stage_slot(S, gt, q * 8 + j);
+          v[j * 4 + 0] = x.x; v[j * 4 + 1] = x.y; v[j * 4 + 2] = x.z; v[j * 4 + 3] = x.w;
+        }
+        tmem_st32(tmem_row + hq * 64 + q * 32, v);
+      }
+      group_sync(g);
     }
+    // ---- 1. e tile (16-bit, global) -> A image: 16-byte copies, 16 threads per row, 8 rows per pass ----
+    load_e_tile(sA, p.e, row0, p.E, sub, c16);
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
-    // ---- 2. GEMM 1: e . W1[256:384] ----------------------------------------------------------------
-    if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr, p.idesc, mbar_addr);
-    const int er = row0 + gt;
-    const bool valid = er < p.E;
-    const int recv = valid ? er / p.K : 0;
-    const float* ps_row = p.ps + (size_t)(valid ? p.row_base[recv] + p.senders[er] : 0) * kD;
-    const float* pr_row = p.pr + (size_t)recv * kD;
+    // ---- 2. GEMM 1: acc += e . W1[256:384] -----------------------------------------------------------
+    if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr, p.idesc, mbar_addr, /*accumulate_first=*/1u);
     mbar_wait(mbar_addr, parity);
     parity ^= 1;
     tc_fence_after();
-    // ---- 3. epilogue 1: + ps[sender] + pr[receiver] (b1 folded), GELU -> A image ------------------------
+    // ---- 3. epilogue 1: GELU -> A image ------------------------------------------------------------------
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       float v[32];
       tmem_ld32(tmem_row + q * 32, v);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(ps_row + q * 32 + c * 4));
-        float4 b = __ldg(reinterpret_cast<const float4*>(pr_row + q * 32 + c * 4));
-        v[c * 4 + 0] = gelu_fast(v[c * 4 + 0] + a.x + b.x);
-        v[c * 4 + 1] = gelu_fast(v[c * 4 + 1] + a.y + b.y);
-        v[c * 4 + 2] = gelu_fast(v[c * 4 + 2] + a.z + b.z);
-        v[c * 4 + 3] = gelu_fast(v[c * 4 + 3] + a.w + b.w);
-      }
+      for (int c = 0; c < 32; ++c) v[c] = gelu_fast(v[c]);
       store_a_chunk<T16>(sA, gt, q * 32, v);
     }
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
     // ---- 4. GEMM 2 ----------------------------------------------------------------------------------
-    if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + kMatBytes, p.idesc, mbar_addr);
+    if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + kMatBytes, p.idesc, mbar_addr, 0u);
     mbar_wait(mbar_addr, parity);
     parity ^= 1;
     tc_fence_after();
@@ -311,23 +350,29 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       fence_proxy_async();
       tc_fence_before();
       group_sync(g);
-      if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + 2 * kMatBytes, p.idesc, mbar_addr);
+      if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + 2 * kMatBytes, p.idesc, mbar_addr, 0u);
       mbar_wait(mbar_addr, parity);
       parity ^= 1;
       tc_fence_after();
-      float* e_row = p.e + (size_t)(valid ? er : 0) * kD;
+      // pass 1: x = acc + b3 + e.  The tile is re-read row-coalesced (an L2 hit) into the free A buffer,
+      // in the same swizzled image, so each thread finds its own row conflict-free; statistics; x -> TMEM.
+      load_e_tile(sA, p.e, row0, p.E, sub, c16);
+      group_sync(g);
       float sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         float v[32];
         tmem_ld32(tmem_row + q * 32, v);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 r = valid ? *reinterpret_cast<const float4*>(e_row + q * 32 + c * 4) : make_float4(0, 0, 0, 0);
-          v[c * 4 + 0] += sVec[128 + q * 32 + c * 4 + 0] + r.x;
-          v[c * 4 + 1] += sVec[128 + q * 32 + c * 4 + 1] + r.y;
-          v[c * 4 + 2] += sVec[128 + q * 32 + c * 4 + 2] + r.z;
-          v[c * 4 + 3] += sVec[128 + q * 32 + c * 4 + 3] + r.w;
+        for (int j = 0; j < 4; ++j) {
+          const uint4 pk = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
+          const float* b3 = sVec + 128 + q * 32 + j * 8;
+          const float2 e0 = Unpack<T16>::two(pk.x), e1 = Unpack<T16>::two(pk.y), e2 = Unpack<T16>::two(pk.z),
+                       e3 = Unpack<T16>::two(pk.w);
+          v[j * 8 + 0] += b3[0] + e0.x; v[j * 8 + 1] += b3[1] + e0.y;
+          v[j * 8 + 2] += b3[2] + e1.x; v[j * 8 + 3] += b3[3] + e1.y;
+          v[j * 8 + 4] += b3[4] + e2.x; v[j * 8 + 5] += b3[5] + e2.y;
+          v[j * 8 + 6] += b3[6] + e3.x; v[j * 8 + 7] += b3[7] + e3.y;
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -339,62 +384,73 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       const float mean = sum * (1.0f / kD);
       const float var = fmaxf(sumsq * (1.0f / kD) - mean * mean, 0.f);
       const float inv = rsqrtf(var + 1e-5f);
+      // pass 2: normalise -> 16-bit image of the new edge state (each thread touches only its own row of
+      // the buffer, so no barrier is needed between the passes), then a row-coalesced copy-out.
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         float v[32];
         tmem_ld32(tmem_row + q * 32, v);
-        if (valid) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 o;
-            o.x = sVec[256 + q * 32 + c * 4 + 0] * inv * (v[c * 4 + 0] - mean) + sVec[384 + q * 32 + c * 4 + 0];
-            o.y = sVec[256 + q * 32 + c * 4 + 1] * inv * (v[c * 4 + 1] - mean) + sVec[384 + q * 32 + c * 4 + 1];
-            o.z = sVec[256 + q * 32 + c * 4 + 2] * inv * (v[c * 4 + 2] - mean) + sVec[384 + q * 32 + c * 4 + 2];
-            o.w = sVec[256 + q * 32 + c * 4 + 3] * inv * (v[c * 4 + 3] - mean) + sVec[384 + q * 32 + c * 4 + 3];
-            *reinterpret_cast<float4*>(e_row + q * 32 + c * 4) = o;
-          }
-        }
+        for (int c = 0; c < 32; ++c)
+          v[c] = sVec[256 + q * 32 + c] * inv * (v[c] - mean) + sVec[384 + q * 32 + c];
+        store_a_chunk<T16>(sA, gt, q * 32, v);
       }
+      group_sync(g);
+#pragma unroll 8
+      for (int it = 0; it < 16; ++it) {
+        const int r = it * 8 + sub;
+        const int err = row0 + r;
+        if (err < p.E)
+          *(reinterpret_cast<uint4*>(p.e + (size_t)err * kD) + c16) = *reinterpret_cast<const uint4*>(sA + swz_offset(r, c16 * 8));
+      }
+      group_sync(g);
     } else {
       // ---- 5b. epilogue 2 (message mode): + b2, GELU, partial sums over the rows of each receiver ------
-      // scratch: the group's A buffer is free now; [128 rows][33] floats
-      float* scratch = reinterpret_cast<float*>(sA);
-      float* part = scratch + 128 * 33;  // [4 quarters][4 segments][32 cols]
+      float* part = reinterpret_cast<float*>(sW + 2 * kMatBytes) + g * (4 * 64);  // W3 slot is free in message mode
       const int first_recv = row0 / p.K;
+      const int col = gt & 63, half = gt >> 6;
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float v[32];
-        tmem_ld32(tmem_row + q * 32, v);
+      for (int hq = 0; hq < 2; ++hq) {
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+          float v[32];
+          tmem_ld32(tmem_row + hq * 64 + q * 32, v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) scratch[gt * 33 + c] = valid ? gelu_fast(v[c] + sVec[q * 32 + c]) : 0.f;
-        group_sync(g);
-        {
-          const int col = gt & 31, quarter = gt >> 5;
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int r = 0; r < 32; ++r) {
-            const int rr = quarter * 32 + r;
-            const int seg = (row0 + rr) / p.K - first_recv;
-            const float x = scratch[rr * 33 + col];
-            acc[0] += seg == 0 ? x : 0.f;
-            acc[1] += seg == 1 ? x : 0.f;
-            acc[2] += seg == 2 ? x : 0.f;
-            acc[3] += seg == 3 ? x : 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const float* b2 = sVec + hq * 64 + q * 32 + j * 4;
+            float4 o;
+            o.x = valid ? gelu_fast(v[j * 4 + 0] + b2[0]) : 0.f;
+            o.y = valid ? gelu_fast(v[j * 4 + 1] + b2[1]) : 0.f;
+            o.z = valid ? gelu_fast(v[j * 4 + 2] + b2[2]) : 0.f;
+            o.w = valid ? gelu_fast(v[j * 4 + 3] + b2[3]) : 0.f;
+            *stage_slot(S, gt, q * 8 + j) = o;
           }
-#pragma unroll
-          for (int s = 0; s < 4; ++s) part[(quarter * 4 + s) * 32 + col] = acc[s];
         }
         group_sync(g);
-        {
-          const int s = gt >> 5, col = gt & 31;  // 4 segments x 32 columns
-          float t = part[(0 * 4 + s) * 32 + col] + part[(1 * 4 + s) * 32 + col] + part[(2 * 4 + s) * 32 + col] +
-                    part[(3 * 4 + s) * 32 + col];
-          p.partial[((size_t)tile * 4 + s) * kD + q * 32 + col] = t;
+        // thread = (column, row half): sums of its 64 rows split at the receiver boundaries
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          int lo = (first_recv + s) * p.K - row0, hi = lo + p.K;
+          lo = max(lo, half * 64);
+          hi = min(hi, half * 64 + 64);
+          float a = 0.f;
+          for (int r = lo; r < hi; ++r) a += S[r * 64 + ((((col >> 2) ^ (r & 7)) << 2) | (col & 3))];
+          acc[s] = a;
+        }
+        if (half == 1) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) part[s * 64 + col] = acc[s];
+        }
+        group_sync(g);
+        if (half == 0) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            p.partial[((size_t)tile * 4 + s) * kD + hq * 64 + col] = acc[s] + part[s * 64 + col];
         }
         group_sync(g);
       }
     }
-    // TMEM reads of this tile must be complete before the next tile's MMA overwrites the accumulator:
-    // ordered by the tcgen05.fence::before_thread_sync + group barrier at the top of the next iteration.
   }
 
   tc_fence_before();
@@ -467,7 +523,7 @@ size_t pst_tc_partial_floats(int R, int K) {
 
 // mode 0: writes tbar (mean over K of the 2nd hidden layer) into agg_out[R,128]; the caller applies W3, b3.
 // mode 1: e <- LN(e + MLP).
-int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, float* e, const float* ps,
+int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e, const float* ps,
                            const float* pr, const int32_t* senders, const int32_t* row_base, float* partial, int R,
                            float* agg_out) {
   const int K = m->cfg.num_neighbor;

@@ -9,6 +9,9 @@
 //   resampler          model/modules.py:281-382 (Attention), 393-424, 211-262 (Transition), 545-636
 //   local mask         model/model.py:264-318,382-401 (token t <-> residues [t*df, t*df+df))
 //   head               model/model.py:169-174 (x/(||x||+1e-6)), 148-164 (down_proj)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "pst_internal.h"
 
 namespace {
@@ -213,28 +216,48 @@ __global__ void token_embed_kernel(const float* __restrict__ table, const int32_
 }
 
 // e0[e] = edge_pe_table[s - r + (n-1)] + f27[e] . Wf        (structure_encoder.py:94-105)
-// One block per receiver row (K edges); thread = output channel.
+// One block per receiver row (K edges); thread = output channel, its 27 weights in registers, the
+// edge's features broadcast from shared memory as float4.  OutT = float (fp32 mode) or a 16-bit
+// type (tensor-core modes keep the edge state in the operand precision of the edge MLPs).
+template <typename OutT>
+__device__ __forceinline__ OutT to_out(float v);
+template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename OutT>
 __global__ void __launch_bounds__(128)
 edge_embed_kernel(const float* __restrict__ feat, const int32_t* __restrict__ senders,
                   const int32_t* __restrict__ row_base, const float* __restrict__ pe_table,
-                  const float* __restrict__ wf, int K, int seq_max, float* __restrict__ e) {
-  extern __shared__ float s_feat[];  // [K][27] then senders
-  int* s_send = reinterpret_cast<int*>(s_feat + K * PST_EDGE_FEATURES);
+                  const float* __restrict__ wf, int K, int seq_max, OutT* __restrict__ e) {
+  extern __shared__ __align__(16) float s_feat[];  // [K][28] then senders
+  int* s_send = reinterpret_cast<int*>(s_feat + K * 28);
   const int r = blockIdx.x;
   const int c = threadIdx.x;
-  for (int t = c; t < K * PST_EDGE_FEATURES; t += 128) s_feat[t] = feat[(size_t)r * K * PST_EDGE_FEATURES + t];
+  for (int t = c; t < K * 28; t += 128) {
+    int k = t / 28, f = t - k * 28;
+    s_feat[t] = f < PST_EDGE_FEATURES ? feat[((size_t)r * K + k) * PST_EDGE_FEATURES + f] : 0.f;
+  }
   for (int t = c; t < K; t += 128) s_send[t] = senders[(size_t)r * K + t];
-  float w[PST_EDGE_FEATURES];
+  float w[28];
 #pragma unroll
-  for (int f = 0; f < PST_EDGE_FEATURES; ++f) w[f] = wf[f * D + c];
+  for (int f = 0; f < 28; ++f) w[f] = f < PST_EDGE_FEATURES ? wf[f * D + c] : 0.f;
   __syncthreads();
   const int local_r = r - row_base[r];
+#pragma unroll 2
   for (int k = 0; k < K; ++k) {
-    int diff = s_send[k] - local_r + (seq_max - 1);
-    float acc = 0.f;
+    const int diff = s_send[k] - local_r + (seq_max - 1);
+    float acc = pe_table[(size_t)diff * D + c];
+    const float4* fk = reinterpret_cast<const float4*>(s_feat + k * 28);
 #pragma unroll
-    for (int f = 0; f < PST_EDGE_FEATURES; ++f) acc = fmaf(s_feat[k * PST_EDGE_FEATURES + f], w[f], acc);
-    e[((size_t)r * K + k) * D + c] = pe_table[(size_t)diff * D + c] + acc;
+    for (int j = 0; j < 7; ++j) {
+      const float4 x = fk[j];
+      acc = fmaf(x.x, w[j * 4 + 0], acc);
+      acc = fmaf(x.y, w[j * 4 + 1], acc);
+      acc = fmaf(x.z, w[j * 4 + 2], acc);
+      acc = fmaf(x.w, w[j * 4 + 3], acc);
+    }
+    e[((size_t)r * K + k) * D + c] = to_out<OutT>(acc);
   }
 }
 
@@ -330,9 +353,16 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   node_embed_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->w.node_table, row_base, ws.h, R);
   ++L.count;
   {
-    size_t smem = (size_t)K * PST_EDGE_FEATURES * sizeof(float) + (size_t)K * sizeof(int);
-    edge_embed_kernel<<<R, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
-                                            cfg.seq_max_size, ws.e);
+    size_t smem = (size_t)K * 28 * sizeof(float) + (size_t)K * sizeof(int);
+    if (cfg.precision == PST_PREC_FP32)
+      edge_embed_kernel<float><<<R, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
+                                                     cfg.seq_max_size, ws.e);
+    else if (cfg.precision == PST_PREC_FP16)
+      edge_embed_kernel<__half><<<R, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
+                                                      cfg.seq_max_size, reinterpret_cast<__half*>(ws.e));
+    else
+      edge_embed_kernel<__nv_bfloat16><<<R, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w,
+                                                             K, cfg.seq_max_size, reinterpret_cast<__nv_bfloat16*>(ws.e));
     ++L.count;
   }
   for (int l = 0; l < cfg.gnn_layers; ++l) {
@@ -344,7 +374,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     if (tc) {
       // tensor-core path returns the per-receiver mean of the 2nd hidden layer; the 3rd linear
       // commutes with that mean (no activation follows it): agg = mean_K(T2) . W3 + b3
-      int n = pst_launch_edge_mlp_tc(m, st, l, 0, ws.e, ws.ps, ws.pr, senders, row_base, ws.partial, R, ws.tmp);
+      int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ws.ps, ws.pr, senders, row_base, ws.partial, R, ws.tmp);
       if (n < 0) return n;
       L.count += n;
       L.gemm(ws.tmp, w.msg_w3, ws.agg, R, D, D, Launcher::epi(w.msg_b3));
@@ -368,7 +398,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     L.gemm(ws.h, w.edge_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.edge_b1));
     span = new PstSpan(m, st, 2);
     if (tc) {
-      int n = pst_launch_edge_mlp_tc(m, st, l, 1, ws.e, ws.ps, ws.pr, senders, row_base, ws.partial, R, nullptr);
+      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), ws.ps, ws.pr, senders, row_base, ws.partial, R, nullptr);
       if (n < 0) return n;
       L.count += n;
     } else {

@@ -94,7 +94,7 @@ struct PstWorkspace {
   double* prep;          // [R,16]
   int32_t* senders;      // [E]
   float* edge_feat;      // [E,27]
-  float* e;              // [E,128]
+  float* e;              // [E,128] fp32 (fp32 mode) or 16-bit (tensor-core modes: same pointer, half the bytes)
   float* t1;             // [E,128]   (fp32 mode only)
   float* t2;             // [E,128]   (fp32 mode only)
   float* partial;        // [tiles,4,128] (tensor-core modes only)
@@ -137,7 +137,7 @@ int pst_launch_indexes_to_codes(const pst_model* m, cudaStream_t st, const int32
 
 // tensor-core edge MLP (edge_mlp_tc.cu).  mode 0: message MLP -> agg[R,128] = mean_K;
 // mode 1: edge update -> e = LN(e + MLP).  Returns kernels launched, <0 on error.
-int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, float* e,
+int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e,
                            const float* ps, const float* pr, const int32_t* senders,
                            const int32_t* row_base, float* partial, int R, float* agg_out);
 size_t pst_tc_partial_floats(int R, int K);
