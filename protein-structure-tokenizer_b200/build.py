@@ -17,6 +17,7 @@ SOURCES = {
     "featurize.cu": ["-fmad=false"],
     "encoder_fp32.cu": [],
     "edge_mlp_tc.cu": [],
+    "linear_tc.cu": [],
     "quantize.cu": [],
     "api.cu": [],
 }

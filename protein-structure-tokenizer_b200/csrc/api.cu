@@ -164,6 +164,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   m->device = device;
   m->launch_count = 0;
   m->tc_dev = nullptr;
+  m->linear_tc = nullptr;
   m->prof_on = false;
   m->prof_n = 0;
   for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i) m->prof_ev[i] = nullptr;
@@ -194,6 +195,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   }
   if (cfg->precision != PST_PREC_FP32) {
     int rc = pst_prepare_tc_weights(m);
+    if (rc == PST_OK) rc = pst_prepare_linear_tc(m);
     if (rc != PST_OK) { pst_model_destroy(m); return rc; }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) { pst_model_destroy(m); return PST_ERR_CUDA; }
@@ -206,6 +208,7 @@ void pst_model_destroy(pst_model* m) {
   cudaSetDevice(m->device);
   if (m->blob_dev) cudaFree(m->blob_dev);
   if (m->tc_dev) cudaFree(m->tc_dev);
+  pst_destroy_linear_tc(m);
   for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i)
     if (m->prof_ev[i]) cudaEventDestroy(m->prof_ev[i]);
   delete m;

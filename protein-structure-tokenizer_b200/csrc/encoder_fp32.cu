@@ -317,9 +317,14 @@ __global__ void head_kernel(const float* __restrict__ res, const float* __restri
 
 struct Launcher {
   cudaStream_t st;
+  const pst_model* model = nullptr;  // set in the tensor-core modes: plain linears go to linear_tc.cu
   int count = 0;
   void gemm(const float* A, const float* W, float* C, int M, int N, int K, GemmEpi ep) {
     if (M <= 0) return;
+    if (model && !ep.gather_s) {
+      int n = pst_launch_linear_tc(model, st, A, W, C, M, N, K, ep.bias, ep.residual, ep.scale, ep.act);
+      if (n > 0) { count += n; return; }
+    }
     dim3 grid((M + 127) / 128, N / 128);
     sgemm_kernel<<<grid, 256, 0, st>>>(A, W, C, M, N, K, ep);
     ++count;
@@ -347,6 +352,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   const int E = R * K;
   const bool tc = cfg.precision != PST_PREC_FP32;
   Launcher L{st};
+  if (tc) L.model = m;
   int32_t* row_base = ws.row_base;
   row_base_kernel<<<(R + 255) / 256, 256, 0, st>>>(offsets, B, R, row_base);
   ++L.count;

@@ -52,6 +52,8 @@ struct PstTcWeights {
   const uint16_t* w;  // [layers][2 (msg,edge)][3][128*128]
 };
 
+struct PstLinearRegistry;
+
 struct pst_model {
   pst_config cfg;
   int device;
@@ -61,6 +63,7 @@ struct pst_model {
   PstWeights w;
   uint16_t* tc_dev;
   PstTcWeights tc;
+  PstLinearRegistry* linear_tc;  // split-fp16 operand images of the node-level weights (tensor-core modes)
   // FSQ constants (model/quantize.py:175-181), fp32
   float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
   int32_t basis[PST_C8], half_width[PST_C8];
@@ -141,6 +144,12 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
                            const float* ps, const float* pr, const int32_t* senders,
                            const int32_t* row_base, float* partial, int R, float* agg_out);
 size_t pst_tc_partial_floats(int R, int K);
+
+// node-level linears on tensor cores (linear_tc.cu)
+int pst_prepare_linear_tc(pst_model* m);
+void pst_destroy_linear_tc(pst_model* m);
+int pst_launch_linear_tc(const pst_model* m, cudaStream_t st, const float* A, const float* W, float* C, int M, int N,
+                         int K, const float* bias, const float* residual, float scale, int act);
 
 #define PST_CUDA_OK(expr)                                  \
   do {                                                     \
