@@ -95,6 +95,7 @@ struct PstWorkspace {
   int32_t* status;       // [4]
   int32_t* row_base;     // [R]
   double* prep;          // [R,16]
+  double* cen4;          // [R,4] centroid (x,y,z,0): compact copy for the k-NN scan
   int32_t* senders;      // [E]
   float* edge_feat;      // [E,27]
   float* e;              // [E,128] fp32 (fp32 mode) or 16-bit (tensor-core modes: same pointer, half the bytes)
@@ -124,7 +125,7 @@ PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T_up
 // ---- kernel launchers (each returns the number of kernels enqueued) --------------
 int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms,
                          const uint8_t* mask, int apr, const int32_t* offsets, int B, int R,
-                         int32_t* senders, float* edge_feat, double* prep, int32_t* status);
+                         int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status);
 
 int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edge_feat,
                            const int32_t* senders, const int32_t* offsets,
