@@ -33,7 +33,7 @@ constexpr uint32_t kMatBytes = 128 * 128 * 2;  // one 16-bit 128x128 operand ima
 constexpr uint32_t kKBlockBytes = 128 * 128;    // 128 rows x 64 elements x 2 B
 constexpr uint32_t kSmemW = 3 * kMatBytes;
 constexpr uint32_t kSmemA = kGroups * kMatBytes;
-constexpr uint32_t kSmemVec = 4 * 128 * sizeof(float);  // b2, b3, ln scale, ln offset
+constexpr uint32_t kSmemVec = 2 * 128 * sizeof(float) + kGroups * 128 * 2 + 64;  // b2, b3; per-group gather table; segment bases
 constexpr uint32_t kSmemMisc = 64;  // mbarriers + TMEM slot
 constexpr uint32_t kSmemTotal = kSmemW + kSmemA + kSmemVec + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
@@ -202,33 +202,71 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, uint32_t sA_addr, 
   umma_commit(mbar_addr);
 }
 
-// ---- staging through the group's (currently free) 32 KB A buffer ---------------------------------
-// Global traffic is always issued row-coalesced (16 threads x float4 = 256 B of one row per request);
-// the thread-per-row view the TMEM 32x32b layout needs is obtained by a shared-memory transpose:
-// staging tile S = [128 rows][64 fp32], float4 slot j of row r stored at slot j ^ (r & 7)
-// (conflict-free for both the 16-threads-per-row and the thread-per-row access).
-__device__ __forceinline__ float4* stage_slot(float* S, int row, int j) {
-  return reinterpret_cast<float4*>(S + row * 64 + ((j ^ (row & 7)) << 2));
+// ---- packed fp32 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two elements per instruction -------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+// GELU (tanh form) of two values: 5 packed ops + 2 MUFU.TANH
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  const float2 x2 = mul2(x, x);
+  const float2 p = fma2(x2, make_float2(0.0713548162f, 0.0713548162f), make_float2(1.5957691216f, 1.5957691216f));
+  const float2 hx = mul2(x, make_float2(0.5f, 0.5f));
+  const float2 u = mul2(hx, p);  // sqrt(2/pi) (x + 0.044715 x^3)
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  return fma2(hx, t, hx);
 }
 
-__device__ __forceinline__ void load_e_tile(uint8_t* sA, const uint16_t* e, int row0, int E, int sub, int c16) {
-#pragma unroll 8
-  for (int it = 0; it < 16; ++it) {
-    const int r = it * 8 + sub;
-    const int err = row0 + r;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (err < E) x = *(reinterpret_cast<const uint4*>(e + (size_t)err * kD) + c16);
-    *reinterpret_cast<uint4*>(sA + swz_offset(r, c16 * 8)) = x;
+__device__ __forceinline__ void tmem_ld32v(uint32_t taddr, float2 (&v)[16]) { tmem_ld32(taddr, *reinterpret_cast<float (*)[32]>(&v)); }
+__device__ __forceinline__ void tmem_st32v(uint32_t taddr, const float2 (&v)[16]) { tmem_st32(taddr, *reinterpret_cast<const float (*)[32]>(&v)); }
+
+// 32 consecutive K-elements [k0, k0+32) of `row` -> the group's 16-bit A image (4 x 16 B, swizzled)
+template <typename T16>
+__device__ __forceinline__ void store_a_chunk2(uint8_t* sA, int row, int k0, const float2 (&v)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 pk;
+    pk.x = Pack<T16>::two(v[c * 4 + 0].x, v[c * 4 + 0].y);
+    pk.y = Pack<T16>::two(v[c * 4 + 1].x, v[c * 4 + 1].y);
+    pk.z = Pack<T16>::two(v[c * 4 + 2].x, v[c * 4 + 2].y);
+    pk.w = Pack<T16>::two(v[c * 4 + 3].x, v[c * 4 + 3].y);
+    *reinterpret_cast<uint4*>(sA + swz_offset(row, k0 + c * 8)) = pk;
   }
 }
 
+// ---- staging through the group's (currently free) 32 KB A buffer ---------------------------------
+// Global traffic is always issued row-coalesced (16 threads x 16 B of one row per request); the
+// thread-per-row view the TMEM 32x32b layout needs is obtained by a shared-memory transpose:
+// fp32 staging tile S = [128 rows][64 fp32], float4 slot j of row r stored at slot j ^ (r & 7)
+// (conflict-free for both the 16-threads-per-row and the thread-per-row access); 16-bit tiles use the
+// operand image layout itself.  In the 16-threads-per-row loops row = it*8 + sub, so (row & 7) == sub
+// and every offset is (loop-invariant constant) + it * stride.
 template <typename T16, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sAall = smem + kSmemW;
-  float* sVec = reinterpret_cast<float*>(smem + kSmemW + kSmemA);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemW + kSmemA + kSmemVec);
+  float* sVec = reinterpret_cast<float*>(smem + kSmemW + kSmemA);                 // b2[128], b3[128]
+  uint16_t* sTabAll = reinterpret_cast<uint16_t*>(smem + kSmemW + kSmemA + 1024);  // [groups][128]
+  int* sBaseAll = reinterpret_cast<int*>(smem + kSmemW + kSmemA + 2048);          // [groups][4]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemW + kSmemA + 2048 + 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kGroups);
 
   const int tid = threadIdx.x;
@@ -238,7 +276,12 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   const int wq = warp & 3;          // TMEM lane quarter this warp may access
   uint8_t* sA = sAall + g * kMatBytes;
   float* S = reinterpret_cast<float*>(sA);
+  uint16_t* sTab = sTabAll + g * 128;
+  int* sBase = sBaseAll + g * 4;
   const int sub = gt >> 4, c16 = gt & 15;  // 16 threads per row, 8 rows per pass
+  const uint32_t offA = (uint32_t)((c16 >> 3) * kKBlockBytes + sub * 128 + (((c16 & 7) ^ sub) << 4));  // + it*1024
+  const uint32_t offS = (uint32_t)(sub * 64 + ((c16 ^ sub) << 2));                                    // + it*512 (floats)
+  const int gx = gt & 7;
 
   // ---- one-time setup -------------------------------------------------------------------------
   {
@@ -249,8 +292,6 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     if (tid < 128) {
       sVec[tid] = p.b2[tid];
       sVec[128 + tid] = MODE == 1 ? p.b3[tid] : 0.f;
-      sVec[256 + tid] = MODE == 1 ? p.ln_s[tid] : 0.f;
-      sVec[384 + tid] = MODE == 1 ? p.ln_o[tid] : 0.f;
     }
   }
   if (tid == 0) {
@@ -278,40 +319,55 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     const int row0 = tile * kTileM;
     const int er = row0 + gt;
     const bool valid = er < p.E;
-    tc_fence_before();  // previous tile's TMEM loads are complete (wait::ld) before anyone overwrites the accumulator
+    const int first_recv = row0 / p.K;
+    const int last_row = min(p.E - row0, kTileM);  // valid rows in this tile
+    // per-row gather indices: local sender (13 bits) | receiver segment within the tile (2 bits)
+    {
+      int t = 0;
+      if (valid) t = __ldg(p.senders + er) | ((er / p.K - first_recv) << 13);
+      sTab[gt] = (uint16_t)t;
+      if (gt < 4) sBase[gt] = __ldg(p.row_base + min(first_recv + gt, (p.E - 1) / p.K));
+    }
+    tc_fence_before();
     group_sync(g);
     tc_fence_after();
     // ---- 0. accumulator <- (h.W1a)[sender] + (h.W1b + b1)[receiver], staged through S ---------------
 #pragma unroll 1
     for (int hq = 0; hq < 2; ++hq) {
+      const float4* ps4 = reinterpret_cast<const float4*>(p.ps + hq * 64) + c16;
+      const float4* pr4 = reinterpret_cast<const float4*>(p.pr + hq * 64) + c16;
 #pragma unroll 8
       for (int it = 0; it < 16; ++it) {
-        const int r = it * 8 + sub;
-        const int err = row0 + r;
-        int recv = 0, srow = 0;
-        if (err < p.E) {
-          recv = err / p.K;
-          srow = __ldg(p.row_base + recv) + __ldg(p.senders + err);
-        }
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p.ps + (size_t)srow * kD + hq * 64) + c16);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.pr + (size_t)recv * kD + hq * 64) + c16);
-        *stage_slot(S, r, c16) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        const int t = sTab[it * 8 + sub];
+        const int seg = t >> 13;
+        const float4 a = __ldg(ps4 + (size_t)(sBase[seg] + (t & 8191)) * (kD / 4));
+        const float4 b = __ldg(pr4 + (size_t)(first_recv + seg) * (kD / 4));
+        *reinterpret_cast<float4*>(S + offS + it * 512) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
       }
       group_sync(g);
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
-        float v[32];
+        float2 v[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 x = *stage_slot(S, gt, q * 8 + j);
-          v[j * 4 + 0] = x.x; v[j * 4 + 1] = x.y; v[j * 4 + 2] = x.z; v[j * 4 + 3] = x.w;
+          const float4 x = *reinterpret_cast<const float4*>(S + gt * 64 + (((q * 8 + j) ^ gx) << 2));
+          v[j * 2] = make_float2(x.x, x.y);
+          v[j * 2 + 1] = make_float2(x.z, x.w);
         }
-        tmem_st32(tmem_row + hq * 64 + q * 32, v);
+        tmem_st32v(tmem_row + hq * 64 + q * 32, v);
       }
       group_sync(g);
     }
     // ---- 1. e tile (16-bit, global) -> A image: 16-byte copies, 16 threads per row, 8 rows per pass ----
-    load_e_tile(sA, p.e, row0, p.E, sub, c16);
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
+#pragma unroll 8
+      for (int it = 0; it < 16; ++it) {
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (it * 8 + sub < last_row) x = src[(size_t)it * 8 * (kD / 8)];
+        *reinterpret_cast<uint4*>(sA + offA + it * 1024) = x;
+      }
+    }
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
@@ -323,11 +379,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     // ---- 3. epilogue 1: GELU -> A image ------------------------------------------------------------------
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
-      float v[32];
-      tmem_ld32(tmem_row + q * 32, v);
+      float2 v[16];
+      tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] = gelu_fast(v[c]);
-      store_a_chunk<T16>(sA, gt, q * 32, v);
+      for (int c = 0; c < 16; ++c) v[c] = gelu2(v[c]);
+      store_a_chunk2<T16>(sA, gt, q * 32, v);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -341,11 +397,15 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       // ---- 5a. epilogue 2: + b2, GELU -> A image; GEMM 3; epilogue 3: residual + LayerNorm -------------
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
-        float v[32];
-        tmem_ld32(tmem_row + q * 32, v);
+        float2 v[16];
+        tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = gelu_fast(v[c] + sVec[q * 32 + c]);
-        store_a_chunk<T16>(sA, gt, q * 32, v);
+        for (int c = 0; c < 8; ++c) {
+          const float4 b = *reinterpret_cast<const float4*>(sVec + q * 32 + c * 4);
+          v[c * 2] = gelu2(add2(v[c * 2], make_float2(b.x, b.y)));
+          v[c * 2 + 1] = gelu2(add2(v[c * 2 + 1], make_float2(b.z, b.w)));
+        }
+        store_a_chunk2<T16>(sA, gt, q * 32, v);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -355,80 +415,90 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       parity ^= 1;
       tc_fence_after();
       // pass 1: x = acc + b3 + e.  The tile is re-read row-coalesced (an L2 hit) into the free A buffer,
-      // in the same swizzled image, so each thread finds its own row conflict-free; statistics; x -> TMEM.
-      load_e_tile(sA, p.e, row0, p.E, sub, c16);
+      // in the operand image layout, so each thread finds its own row conflict-free; statistics; x -> TMEM.
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
+#pragma unroll 8
+        for (int it = 0; it < 16; ++it) {
+          uint4 x = make_uint4(0, 0, 0, 0);
+          if (it * 8 + sub < last_row) x = src[(size_t)it * 8 * (kD / 8)];
+          *reinterpret_cast<uint4*>(sA + offA + it * 1024) = x;
+        }
+      }
       group_sync(g);
-      float sum = 0.f, sumsq = 0.f;
+      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
-        float v[32];
-        tmem_ld32(tmem_row + q * 32, v);
+        float2 v[16];
+        tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 pk = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
-          const float* b3 = sVec + 128 + q * 32 + j * 8;
-          const float2 e0 = Unpack<T16>::two(pk.x), e1 = Unpack<T16>::two(pk.y), e2 = Unpack<T16>::two(pk.z),
-                       e3 = Unpack<T16>::two(pk.w);
-          v[j * 8 + 0] += b3[0] + e0.x; v[j * 8 + 1] += b3[1] + e0.y;
-          v[j * 8 + 2] += b3[2] + e1.x; v[j * 8 + 3] += b3[3] + e1.y;
-          v[j * 8 + 4] += b3[4] + e2.x; v[j * 8 + 5] += b3[5] + e2.y;
-          v[j * 8 + 6] += b3[6] + e3.x; v[j * 8 + 7] += b3[7] + e3.y;
+          const float4 ba = *reinterpret_cast<const float4*>(sVec + 128 + q * 32 + j * 8);
+          const float4 bb = *reinterpret_cast<const float4*>(sVec + 128 + q * 32 + j * 8 + 4);
+          v[j * 4 + 0] = add2(v[j * 4 + 0], add2(Unpack<T16>::two(pk.x), make_float2(ba.x, ba.y)));
+          v[j * 4 + 1] = add2(v[j * 4 + 1], add2(Unpack<T16>::two(pk.y), make_float2(ba.z, ba.w)));
+          v[j * 4 + 2] = add2(v[j * 4 + 2], add2(Unpack<T16>::two(pk.z), make_float2(bb.x, bb.y)));
+          v[j * 4 + 3] = add2(v[j * 4 + 3], add2(Unpack<T16>::two(pk.w), make_float2(bb.z, bb.w)));
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          sum += v[c];
-          sumsq = fmaf(v[c], v[c], sumsq);
+        for (int c = 0; c < 16; ++c) {
+          sum2 = add2(sum2, v[c]);
+          sq2 = fma2(v[c], v[c], sq2);
         }
-        tmem_st32(tmem_row + q * 32, v);
+        tmem_st32v(tmem_row + q * 32, v);
       }
-      const float mean = sum * (1.0f / kD);
-      const float var = fmaxf(sumsq * (1.0f / kD) - mean * mean, 0.f);
+      const float mean = (sum2.x + sum2.y) * (1.0f / kD);
+      const float var = fmaxf((sq2.x + sq2.y) * (1.0f / kD) - mean * mean, 0.f);
       const float inv = rsqrtf(var + 1e-5f);
-      // pass 2: normalise -> 16-bit image of the new edge state (each thread touches only its own row of
-      // the buffer, so no barrier is needed between the passes), then a row-coalesced copy-out.
+      const float2 inv2 = make_float2(inv, inv), nmean2 = make_float2(-mean, -mean);
+      // pass 2: y = v * (inv * scale) + (offset - mean * inv * scale) -> 16-bit image of the new edge state
+      // (each thread touches only its own row of the buffer: no barrier between the passes), then a
+      // row-coalesced copy-out.
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
-        float v[32];
-        tmem_ld32(tmem_row + q * 32, v);
+        float2 v[16];
+        tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          v[c] = sVec[256 + q * 32 + c] * inv * (v[c] - mean) + sVec[384 + q * 32 + c];
-        store_a_chunk<T16>(sA, gt, q * 32, v);
+        for (int c = 0; c < 8; ++c) {
+          const float4 ls = __ldg(reinterpret_cast<const float4*>(p.ln_s + q * 32) + c);
+          const float4 lo = __ldg(reinterpret_cast<const float4*>(p.ln_o + q * 32) + c);
+          const float2 a0 = mul2(make_float2(ls.x, ls.y), inv2), a1 = mul2(make_float2(ls.z, ls.w), inv2);
+          v[c * 2] = fma2(v[c * 2], a0, fma2(nmean2, a0, make_float2(lo.x, lo.y)));
+          v[c * 2 + 1] = fma2(v[c * 2 + 1], a1, fma2(nmean2, a1, make_float2(lo.z, lo.w)));
+        }
+        store_a_chunk2<T16>(sA, gt, q * 32, v);
       }
       group_sync(g);
+      {
+        uint4* dst = reinterpret_cast<uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
 #pragma unroll 8
-      for (int it = 0; it < 16; ++it) {
-        const int r = it * 8 + sub;
-        const int err = row0 + r;
-        if (err < p.E)
-          *(reinterpret_cast<uint4*>(p.e + (size_t)err * kD) + c16) = *reinterpret_cast<const uint4*>(sA + swz_offset(r, c16 * 8));
+        for (int it = 0; it < 16; ++it)
+          if (it * 8 + sub < last_row) dst[(size_t)it * 8 * (kD / 8)] = *reinterpret_cast<const uint4*>(sA + offA + it * 1024);
       }
       group_sync(g);
     } else {
       // ---- 5b. epilogue 2 (message mode): + b2, GELU, partial sums over the rows of each receiver ------
       float* part = reinterpret_cast<float*>(sW + 2 * kMatBytes) + g * (4 * 64);  // W3 slot is free in message mode
-      const int first_recv = row0 / p.K;
       const int col = gt & 63, half = gt >> 6;
 #pragma unroll 1
       for (int hq = 0; hq < 2; ++hq) {
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
-          float v[32];
-          tmem_ld32(tmem_row + hq * 64 + q * 32, v);
+          float2 v[16];
+          tmem_ld32v(tmem_row + hq * 64 + q * 32, v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float* b2 = sVec + hq * 64 + q * 32 + j * 4;
-            float4 o;
-            o.x = valid ? gelu_fast(v[j * 4 + 0] + b2[0]) : 0.f;
-            o.y = valid ? gelu_fast(v[j * 4 + 1] + b2[1]) : 0.f;
-            o.z = valid ? gelu_fast(v[j * 4 + 2] + b2[2]) : 0.f;
-            o.w = valid ? gelu_fast(v[j * 4 + 3] + b2[3]) : 0.f;
-            *stage_slot(S, gt, q * 8 + j) = o;
+            const float4 b = *reinterpret_cast<const float4*>(sVec + hq * 64 + q * 32 + j * 4);
+            float2 o0 = gelu2(add2(v[j * 2], make_float2(b.x, b.y)));
+            float2 o1 = gelu2(add2(v[j * 2 + 1], make_float2(b.z, b.w)));
+            if (!valid) o0 = o1 = make_float2(0.f, 0.f);
+            *reinterpret_cast<float4*>(S + gt * 64 + (((q * 8 + j) ^ gx) << 2)) = make_float4(o0.x, o0.y, o1.x, o1.y);
           }
         }
         group_sync(g);
         // thread = (column, row half): sums of its 64 rows split at the receiver boundaries
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           int lo = (first_recv + s) * p.K - row0, hi = lo + p.K;
