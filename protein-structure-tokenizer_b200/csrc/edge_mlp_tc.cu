@@ -45,8 +45,8 @@ struct EdgeMlpParams {
   const float* ln_s;
   const float* ln_o;
   uint16_t* e;              // [E,128] 16-bit edge state (read; rewritten in update mode)
-  const float* ps;          // [R,128]
-  const float* pr;          // [R,128] (includes b1)
+  const __half* ps;         // [R,128] fp16  (h.W1[0:128])
+  const __half* pr;         // [R,128] fp16  (h.W1[128:256] + b1)
   const int32_t* senders;   // [E] local indices
   const int32_t* row_base;  // [R]
   float* partial;           // message mode: [num_tiles][4][128] partial row sums of the 2nd hidden layer
@@ -331,33 +331,48 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     tc_fence_before();
     group_sync(g);
     tc_fence_after();
-    // ---- 0. accumulator <- (h.W1a)[sender] + (h.W1b + b1)[receiver], staged through S ---------------
-#pragma unroll 1
-    for (int hq = 0; hq < 2; ++hq) {
-      const float4* ps4 = reinterpret_cast<const float4*>(p.ps + hq * 64) + c16;
-      const float4* pr4 = reinterpret_cast<const float4*>(p.pr + hq * 64) + c16;
+    // ---- 0. accumulator <- (h.W1a)[sender] + (h.W1b + b1)[receiver] -----------------------------------
+    // One row-coalesced gather pass: the fp16 sender rows are copied into the A buffer (operand image
+    // layout); each thread then reads its own row, adds the receiver row (the same for 50 consecutive
+    // edges: a broadcast, L1-resident load) and writes the sum into its accumulator row in TMEM.
+    {
+      const uint4* ps4 = reinterpret_cast<const uint4*>(p.ps) + c16;
 #pragma unroll 8
       for (int it = 0; it < 16; ++it) {
         const int t = sTab[it * 8 + sub];
-        const int seg = t >> 13;
-        const float4 a = __ldg(ps4 + (size_t)(sBase[seg] + (t & 8191)) * (kD / 4));
-        const float4 b = __ldg(pr4 + (size_t)(first_recv + seg) * (kD / 4));
-        *reinterpret_cast<float4*>(S + offS + it * 512) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        *reinterpret_cast<uint4*>(sA + offA + it * 1024) = __ldg(ps4 + (size_t)(sBase[t >> 13] + (t & 8191)) * (kD / 8));
       }
-      group_sync(g);
+      if (MODE == 1 || true) {  // warm L2 with the next tile's edge rows (this group's next tile)
+        const int nt = tile + gridDim.x * kGroups;
+        if (nt < p.num_tiles) {
+          const char* nxt = reinterpret_cast<const char*>(p.e + (size_t)nt * kTileM * kD) + gt * 256;
+          if ((size_t)nt * kTileM + gt < (size_t)p.E) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
+          }
+        }
+      }
+    }
+    group_sync(g);
+    {
+      const int myseg = sTab[gt] >> 13;
+      const uint4* pr4 = reinterpret_cast<const uint4*>(p.pr + (size_t)(first_recv + myseg) * kD);
 #pragma unroll 1
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < 4; ++q) {
         float2 v[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 x = *reinterpret_cast<const float4*>(S + gt * 64 + (((q * 8 + j) ^ gx) << 2));
-          v[j * 2] = make_float2(x.x, x.y);
-          v[j * 2 + 1] = make_float2(x.z, x.w);
+        for (int j = 0; j < 4; ++j) {
+          const uint4 a = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
+          const uint4 b = __ldg(pr4 + q * 4 + j);
+          v[j * 4 + 0] = add2(Unpack<__half>::two(a.x), Unpack<__half>::two(b.x));
+          v[j * 4 + 1] = add2(Unpack<__half>::two(a.y), Unpack<__half>::two(b.y));
+          v[j * 4 + 2] = add2(Unpack<__half>::two(a.z), Unpack<__half>::two(b.z));
+          v[j * 4 + 3] = add2(Unpack<__half>::two(a.w), Unpack<__half>::two(b.w));
         }
-        tmem_st32v(tmem_row + hq * 64 + q * 32, v);
+        tmem_st32v(tmem_row + q * 32, v);
       }
-      group_sync(g);
     }
+    group_sync(g);
     // ---- 1. e tile (16-bit, global) -> A image: 16-byte copies, 16 threads per row, 8 rows per pass ----
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
@@ -593,8 +608,8 @@ size_t pst_tc_partial_floats(int R, int K) {
 
 // mode 0: writes tbar (mean over K of the 2nd hidden layer) into agg_out[R,128]; the caller applies W3, b3.
 // mode 1: e <- LN(e + MLP).
-int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e, const float* ps,
-                           const float* pr, const int32_t* senders, const int32_t* row_base, float* partial, int R,
+int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e, const uint16_t* ps,
+                           const uint16_t* pr, const int32_t* senders, const int32_t* row_base, float* partial, int R,
                            float* agg_out) {
   const int K = m->cfg.num_neighbor;
   const PstLayerW& L = m->w.layer[layer];
@@ -605,8 +620,8 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   p.ln_s = L.ln2_s;
   p.ln_o = L.ln2_o;
   p.e = e;
-  p.ps = ps;
-  p.pr = pr;
+  p.ps = reinterpret_cast<const __half*>(ps);
+  p.pr = reinterpret_cast<const __half*>(pr);
   p.senders = senders;
   p.row_base = row_base;
   p.partial = partial;

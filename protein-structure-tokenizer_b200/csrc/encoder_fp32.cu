@@ -319,10 +319,10 @@ struct Launcher {
   cudaStream_t st;
   const pst_model* model = nullptr;  // set in the tensor-core modes: plain linears go to linear_tc.cu
   int count = 0;
-  void gemm(const float* A, const float* W, float* C, int M, int N, int K, GemmEpi ep) {
+  void gemm(const float* A, const float* W, float* C, int M, int N, int K, GemmEpi ep, int out_half = 0) {
     if (M <= 0) return;
     if (model && !ep.gather_s) {
-      int n = pst_launch_linear_tc(model, st, A, W, C, M, N, K, ep.bias, ep.residual, ep.scale, ep.act);
+      int n = pst_launch_linear_tc(model, st, A, W, C, M, N, K, ep.bias, ep.residual, ep.scale, ep.act, out_half);
       if (n > 0) { count += n; return; }
     }
     dim3 grid((M + 127) / 128, N / 128);
@@ -374,13 +374,15 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   for (int l = 0; l < cfg.gnn_layers; ++l) {
     const PstLayerW& w = m->w.layer[l];
     // message MLP, first linear factorised: [h_s|h_r|e].W1 = (h.W1[0:128])[s] + (h.W1[128:256])[r] + e.W1[256:384]
-    L.gemm(ws.h, w.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr));
-    L.gemm(ws.h, w.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.msg_b1));
+    // (tensor-core modes keep the two gathered addend tables in fp16: measured harmless for the tokens)
+    L.gemm(ws.h, w.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr), tc);
+    L.gemm(ws.h, w.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.msg_b1), tc);
     PstSpan* span = new PstSpan(m, st, 1);
     if (tc) {
       // tensor-core path returns the per-receiver mean of the 2nd hidden layer; the 3rd linear
       // commutes with that mean (no activation follows it): agg = mean_K(T2) . W3 + b3
-      int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ws.ps, ws.pr, senders, row_base, ws.partial, R, ws.tmp);
+      int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), reinterpret_cast<const uint16_t*>(ws.ps),
+                                     reinterpret_cast<const uint16_t*>(ws.pr), senders, row_base, ws.partial, R, ws.tmp);
       if (n < 0) return n;
       L.count += n;
       L.gemm(ws.tmp, w.msg_w3, ws.agg, R, D, D, Launcher::epi(w.msg_b3));
@@ -400,11 +402,12 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     L.gemm(ws.u, w.ffn_w2, ws.tmp, R, D, PST_FFN, Launcher::epi(w.ffn_b2));
     L.add_ln(ws.h, ws.tmp, w.ln1_s, w.ln1_o, ws.h, R);
     if (l == cfg.gnn_layers - 1) break;  // the last layer's edge update is never read (model.py:385)
-    L.gemm(ws.h, w.edge_w1, ws.ps, R, D, D, Launcher::epi(nullptr));
-    L.gemm(ws.h, w.edge_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.edge_b1));
+    L.gemm(ws.h, w.edge_w1, ws.ps, R, D, D, Launcher::epi(nullptr), tc);
+    L.gemm(ws.h, w.edge_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.edge_b1), tc);
     span = new PstSpan(m, st, 2);
     if (tc) {
-      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), ws.ps, ws.pr, senders, row_base, ws.partial, R, nullptr);
+      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), reinterpret_cast<const uint16_t*>(ws.ps),
+                                     reinterpret_cast<const uint16_t*>(ws.pr), senders, row_base, ws.partial, R, nullptr);
       if (n < 0) return n;
       L.count += n;
     } else {

@@ -80,6 +80,7 @@ struct LinearParams {
   const float* bias;      // [N] or null
   const float* residual;  // [M,N] or null
   float* C;
+  int out_half;           // 1: C is __half [M,N] (the gathered addend tables of the edge MLPs)
   int M, N, K;
   float scale;
   int act;                // 0 none, 1 gelu(tanh), 2 relu
@@ -195,7 +196,13 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(LinearParams p) {
           const float4 rr = *reinterpret_cast<const float4*>(p.residual + g);
           o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
         }
-        *reinterpret_cast<float4*>(p.C + g) = o;
+        if (p.out_half) {
+          const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.C) + g) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        } else {
+          *reinterpret_cast<float4*>(p.C + g) = o;
+        }
       }
     }
   }
@@ -272,7 +279,7 @@ void pst_destroy_linear_tc(pst_model* m) {
 // Returns 1 if launched, 0 if this weight is not registered (caller falls back to the fp32 SGEMM of the
 // fp32 precision mode -- never a CPU path), <0 on error.
 int pst_launch_linear_tc(const pst_model* m, cudaStream_t st, const float* A, const float* W, float* C, int M, int N, int K,
-                         const float* bias, const float* residual, float scale, int act) {
+                         const float* bias, const float* residual, float scale, int act, int out_half) {
   if (!m->linear_tc || M <= 0) return 0;
   const Entry* e = nullptr;
   for (const auto& x : m->linear_tc->entries)
@@ -280,7 +287,7 @@ int pst_launch_linear_tc(const pst_model* m, cudaStream_t st, const float* A, co
   if (!e || (K % kBK) || (N % kBN)) return 0;
   LinearParams p{};
   p.A = A; p.w_img = e->img; p.bias = bias; p.residual = residual; p.C = C;
-  p.M = M; p.N = N; p.K = K; p.scale = scale; p.act = act;
+  p.M = M; p.N = N; p.K = K; p.scale = scale; p.act = act; p.out_half = out_half;
   p.idesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);  // fp16 x fp16 -> fp32, M = N = 128
   dim3 grid((M + kBM - 1) / kBM, N / kBN);
   linear_tc_kernel<<<grid, 128, kSmem, st>>>(p);

@@ -142,7 +142,7 @@ int pst_launch_indexes_to_codes(const pst_model* m, cudaStream_t st, const int32
 // tensor-core edge MLP (edge_mlp_tc.cu).  mode 0: message MLP -> agg[R,128] = mean_K;
 // mode 1: edge update -> e = LN(e + MLP).  Returns kernels launched, <0 on error.
 int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e,
-                           const float* ps, const float* pr, const int32_t* senders,
+                           const uint16_t* ps, const uint16_t* pr, const int32_t* senders,
                            const int32_t* row_base, float* partial, int R, float* agg_out);
 size_t pst_tc_partial_floats(int R, int K);
 
@@ -150,7 +150,7 @@ size_t pst_tc_partial_floats(int R, int K);
 int pst_prepare_linear_tc(pst_model* m);
 void pst_destroy_linear_tc(pst_model* m);
 int pst_launch_linear_tc(const pst_model* m, cudaStream_t st, const float* A, const float* W, float* C, int M, int N,
-                         int K, const float* bias, const float* residual, float scale, int act);
+                         int K, const float* bias, const float* residual, float scale, int act, int out_half);
 
 #define PST_CUDA_OK(expr)                                  \
   do {                                                     \
