@@ -133,11 +133,13 @@ def cpu_reference_throughput(bbs, codebook, df, seq_max, n_sample: int, seed_par
     one(sample[0])  # warm-up
     t0 = time.perf_counter()
     res = 0
+    tokens = []
     for bb in sample:
-        one(bb)
+        tokens.append(one(bb))
         res += bb.shape[0]
     dt = time.perf_counter() - t0
     desc = f"{len(sample)} of the workload's structures ({res} residues), padded to {seq_max}, batch 1, torch threads={torch.get_num_threads()}"
+    cpu_reference_throughput.last_tokens = tokens
     return res / dt, dt, desc, torch.get_num_threads()
 
 
@@ -311,9 +313,28 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(T * 4)},
             "roofline": roof,
         }
+        agreement = {}
         if world == 1 and not args.no_cpu_baseline:
             v, dt, desc, cores = cpu_reference_throughput(bbs, codebook, df, seq_max, args.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": "residues/s", "cores": cores, "kind": "port", "sample": desc}
+            # token agreement of this run's GPU tokens with the CPU oracle on the same sample (same weights)
+            gpu_tok = tokens_dev.cpu().numpy().astype(np.uint32)
+            ref = np.concatenate(cpu_reference_throughput.last_tokens)
+            got = np.concatenate([gpu_tok[tok_off[i]:tok_off[i + 1]] for i in range(len(cpu_reference_throughput.last_tokens))])
+            agreement["vs_cpu_oracle_pct"] = float((ref == got).mean() * 100)
+            agreement["vs_cpu_oracle_tokens"] = int(ref.size)
+        if world == 1 and args.precision != "fp32" and not args.no_agreement:
+            # full-batch agreement with the all-fp32 CUDA-core mode of the same library (same inputs, same weights)
+            cfg32 = TokenizerConfig.named(codebook, df, seq_max_size=seq_max, precision="fp32")
+            tok.close()
+            tok32 = StructureTokenizer(cfg32, params, device=local_rank)
+            t32 = tok32.tokenize_device(atoms_dev, None, offs_dev, toff_dev, B, R, T)
+            torch.cuda.synchronize()
+            agreement["vs_gpu_fp32_mode_pct"] = float((t32 == tokens_dev).float().mean().item() * 100)
+            agreement["vs_gpu_fp32_mode_tokens"] = int(T)
+            tok32.close()
+        if agreement:
+            line["token_agreement"] = agreement
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -330,6 +351,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="structures timed by the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-agreement", action="store_true", help="skip the full-batch fp32-mode agreement pass")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
