@@ -151,6 +151,9 @@ def run_reference(args):
     idx, n_struct, length, codebook, df, seq_max = WORKLOADS[workload]
     from pst import synthetic as syn
 
+    import torch
+
+    torch.set_num_threads(max(1, os.cpu_count() or 1))  # torchrun exports OMP_NUM_THREADS=1: use every host core
     n_sample = max(2, min(n_struct, args.cpu_sample))
     bbs = syn.make_backbones(SEED + idx, [length] * n_sample, group=n_sample)
     vals = []

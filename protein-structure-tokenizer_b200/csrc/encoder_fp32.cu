@@ -225,39 +225,65 @@ template <> __device__ __forceinline__ float to_out<float>(float v) { return v; 
 template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+template <typename OutT>
+__device__ __forceinline__ void store_pair(OutT* p, float2 v);
+template <> __device__ __forceinline__ void store_pair<float>(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+template <> __device__ __forceinline__ void store_pair<__half>(__half* p, float2 v) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y); }
+template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloat16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+
+// 128 threads = 2 receiver rows x 64 channel pairs; each thread keeps the 27 x 2 weights of its channel
+// pair in registers and does one packed FFMA2 per feature.
 template <typename OutT>
 __global__ void __launch_bounds__(128)
 edge_embed_kernel(const float* __restrict__ feat, const int32_t* __restrict__ senders,
                   const int32_t* __restrict__ row_base, const float* __restrict__ pe_table,
-                  const float* __restrict__ wf, int K, int seq_max, OutT* __restrict__ e) {
-  extern __shared__ __align__(16) float s_feat[];  // [K][28] then senders
-  int* s_send = reinterpret_cast<int*>(s_feat + K * 28);
-  const int r = blockIdx.x;
-  const int c = threadIdx.x;
-  for (int t = c; t < K * 28; t += 128) {
-    int k = t / 28, f = t - k * 28;
-    s_feat[t] = f < PST_EDGE_FEATURES ? feat[((size_t)r * K + k) * PST_EDGE_FEATURES + f] : 0.f;
+                  const float* __restrict__ wf, int K, int seq_max, int R, OutT* __restrict__ e) {
+  extern __shared__ __align__(16) float s_feat[];  // [2][K][28] then senders [2][K]
+  int* s_send = reinterpret_cast<int*>(s_feat + 2 * K * 28);
+  const int tid = threadIdx.x;
+  const int half = tid >> 6, cp = tid & 63;  // receiver within the block, channel pair
+  const int r0 = blockIdx.x * 2;
+  for (int t = tid; t < 2 * K * 28; t += 128) {
+    const int rr = t / (K * 28), u = t - rr * (K * 28);
+    const int k = u / 28, f = u - k * 28;
+    const int r = r0 + rr;
+    s_feat[t] = (f < PST_EDGE_FEATURES && r < R) ? feat[((size_t)r * K + k) * PST_EDGE_FEATURES + f] : 0.f;
   }
-  for (int t = c; t < K; t += 128) s_send[t] = senders[(size_t)r * K + t];
-  float w[28];
+  for (int t = tid; t < 2 * K; t += 128) {
+    const int rr = t / K, k = t - rr * K;
+    s_send[t] = (r0 + rr < R) ? senders[(size_t)(r0 + rr) * K + k] : 0;
+  }
+  float2 w[28];
 #pragma unroll
-  for (int f = 0; f < 28; ++f) w[f] = f < PST_EDGE_FEATURES ? wf[f * D + c] : 0.f;
+  for (int f = 0; f < 28; ++f)
+    w[f] = f < PST_EDGE_FEATURES ? *reinterpret_cast<const float2*>(wf + f * D + cp * 2) : make_float2(0.f, 0.f);
   __syncthreads();
+  const int r = r0 + half;
+  if (r >= R) return;
   const int local_r = r - row_base[r];
+  const float* sf = s_feat + half * K * 28;
+  const int* ss = s_send + half * K;
 #pragma unroll 2
   for (int k = 0; k < K; ++k) {
-    const int diff = s_send[k] - local_r + (seq_max - 1);
-    float acc = pe_table[(size_t)diff * D + c];
-    const float4* fk = reinterpret_cast<const float4*>(s_feat + k * 28);
+    const int diff = ss[k] - local_r + (seq_max - 1);
+    float2 acc = *reinterpret_cast<const float2*>(pe_table + (size_t)diff * D + cp * 2);
+    const float4* fk = reinterpret_cast<const float4*>(sf + k * 28);
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const float4 x = fk[j];
-      acc = fmaf(x.x, w[j * 4 + 0], acc);
-      acc = fmaf(x.y, w[j * 4 + 1], acc);
-      acc = fmaf(x.z, w[j * 4 + 2], acc);
-      acc = fmaf(x.w, w[j * 4 + 3], acc);
+      acc = ffma2(make_float2(x.x, x.x), w[j * 4 + 0], acc);
+      acc = ffma2(make_float2(x.y, x.y), w[j * 4 + 1], acc);
+      acc = ffma2(make_float2(x.z, x.z), w[j * 4 + 2], acc);
+      acc = ffma2(make_float2(x.w, x.w), w[j * 4 + 3], acc);
     }
-    e[((size_t)r * K + k) * D + c] = to_out<OutT>(acc);
+    store_pair<OutT>(e + ((size_t)r * K + k) * D + cp * 2, acc);
   }
 }
 
@@ -290,6 +316,17 @@ local_attention_kernel(const float* __restrict__ q, const float* __restrict__ kx
   float g = gate[(size_t)t * D + c];
   g = 1.0f / (1.0f + expf(-g));
   wa[(size_t)t * D + c] = acc * g;
+}
+
+// df == 1 shortcut of the local attention: wa = v * sigmoid(gate) (rows of v and tokens coincide)
+__global__ void gated_value_kernel(const float* __restrict__ v, const float* __restrict__ gate, float* __restrict__ wa, int n4) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 x = reinterpret_cast<const float4*>(v)[i];
+  const float4 g = reinterpret_cast<const float4*>(gate)[i];
+  x.x *= 1.0f / (1.0f + expf(-g.x)); x.y *= 1.0f / (1.0f + expf(-g.y));
+  x.z *= 1.0f / (1.0f + expf(-g.z)); x.w *= 1.0f / (1.0f + expf(-g.w));
+  reinterpret_cast<float4*>(wa)[i] = x;
 }
 
 // z[t] = (r / (||r|| + 1e-6)) . Wd + bd      one warp per token; z is [T, 8], unused columns 0
@@ -359,16 +396,18 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   node_embed_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->w.node_table, row_base, ws.h, R);
   ++L.count;
   {
-    size_t smem = (size_t)K * 28 * sizeof(float) + (size_t)K * sizeof(int);
+    size_t smem = 2 * ((size_t)K * 28 * sizeof(float) + (size_t)K * sizeof(int));
+    const int grid = (R + 1) / 2;
     if (cfg.precision == PST_PREC_FP32)
-      edge_embed_kernel<float><<<R, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
-                                                     cfg.seq_max_size, ws.e);
+      edge_embed_kernel<float><<<grid, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
+                                                        cfg.seq_max_size, R, ws.e);
     else if (cfg.precision == PST_PREC_FP16)
-      edge_embed_kernel<__half><<<R, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
-                                                      cfg.seq_max_size, reinterpret_cast<__half*>(ws.e));
+      edge_embed_kernel<__half><<<grid, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
+                                                         cfg.seq_max_size, R, reinterpret_cast<__half*>(ws.e));
     else
-      edge_embed_kernel<__nv_bfloat16><<<R, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w,
-                                                             K, cfg.seq_max_size, reinterpret_cast<__nv_bfloat16*>(ws.e));
+      edge_embed_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table,
+                                                                m->w.edge_feat_w, K, cfg.seq_max_size, R,
+                                                                reinterpret_cast<__nv_bfloat16*>(ws.e));
     ++L.count;
   }
   for (int l = 0; l < cfg.gnn_layers; ++l) {
@@ -430,14 +469,23 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     const PstBlockW& w = m->w.block[b];
     L.add_ln(ws.res, nullptr, w.qn_s, w.qn_o, ws.qn, T);
     L.add_ln(orig, nullptr, w.dn_s, w.dn_o, ws.dn, R);
-    L.gemm(ws.qn, w.wq, ws.q, T, D, D, Launcher::epi(nullptr, 0, nullptr, qscale));
     L.gemm(ws.qn, w.wg, ws.g, T, D, D, Launcher::epi(w.bg));
-    L.gemm(ws.dn, w.wk, ws.kx, R, D, D, Launcher::epi(nullptr));
     L.gemm(ws.dn, w.wv, ws.vx, R, D, D, Launcher::epi(nullptr));
-    if (T > 0) {
-      local_attention_kernel<<<T, 128, 0, st>>>(ws.q, ws.kx, ws.vx, ws.g, offsets, token_offsets, B,
-                                                cfg.downsampling_ratio, ws.wa, T);
-      ++L.count;
+    if (cfg.downsampling_ratio == 1) {
+      // each token attends exactly one residue (itself): softmax over a single logit is exactly 1.0f, so the
+      // query / key projections cannot influence the result and are skipped; out = v * sigmoid(gate).
+      if (T > 0) {
+        gated_value_kernel<<<(T * (D / 4) + 255) / 256, 256, 0, st>>>(ws.vx, ws.g, ws.wa, T * (D / 4));
+        ++L.count;
+      }
+    } else {
+      L.gemm(ws.qn, w.wq, ws.q, T, D, D, Launcher::epi(nullptr, 0, nullptr, qscale));
+      L.gemm(ws.dn, w.wk, ws.kx, R, D, D, Launcher::epi(nullptr));
+      if (T > 0) {
+        local_attention_kernel<<<T, 128, 0, st>>>(ws.q, ws.kx, ws.vx, ws.g, offsets, token_offsets, B,
+                                                  cfg.downsampling_ratio, ws.wa, T);
+        ++L.count;
+      }
     }
     L.gemm(ws.wa, w.wo, ws.res, T, D, D, Launcher::epi(w.bo, 0, ws.res));
     // resampled transition
