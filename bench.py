@@ -153,7 +153,7 @@ def run_reference(args):
 
     import torch
 
-    torch.set_num_threads(max(1, os.cpu_count() or 1))  # torchrun exports OMP_NUM_THREADS=1: use every host core
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))  # torchrun exports OMP_NUM_THREADS=1: use every core we may run on
     n_sample = max(2, min(n_struct, args.cpu_sample))
     bbs = syn.make_backbones(SEED + idx, [length] * n_sample, group=n_sample)
     vals = []
