@@ -16,7 +16,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 SOURCES = {
     "featurize.cu": ["-fmad=false"],
     "encoder_fp32.cu": [],
-    "edge_mlp_tc.cu": [],
+    "edge_mlp_tc.cu": (["-DPST_EDGE_PROFILE"] if os.environ.get("PST_EDGE_PROFILE") else []),
     "linear_tc.cu": [],
     "quantize.cu": [],
     "api.cu": [],

@@ -33,7 +33,7 @@ constexpr uint32_t kMatBytes = 128 * 128 * 2;  // one 16-bit 128x128 operand ima
 constexpr uint32_t kKBlockBytes = 128 * 128;    // 128 rows x 64 elements x 2 B
 constexpr uint32_t kSmemW = 3 * kMatBytes;
 constexpr uint32_t kSmemA = kGroups * kMatBytes;
-constexpr uint32_t kSmemVec = 2 * 128 * sizeof(float) + kGroups * 128 * 2 + 64;  // b2, b3; per-group gather table; segment bases
+constexpr uint32_t kSmemVec = 4 * 128 * sizeof(float) + 64;  // b2, b3, ln scale, ln offset; per-group segment bases
 constexpr uint32_t kSmemMisc = 64;  // mbarriers + TMEM slot
 constexpr uint32_t kSmemTotal = kSmemW + kSmemA + kSmemVec + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
@@ -258,13 +258,28 @@ __device__ __forceinline__ void store_a_chunk2(uint8_t* sA, int row, int k0, con
 // (conflict-free for both the 16-threads-per-row and the thread-per-row access); 16-bit tiles use the
 // operand image layout itself.  In the 16-threads-per-row loops row = it*8 + sub, so (row & 7) == sub
 // and every offset is (loop-invariant constant) + it * stride.
+// Optional per-phase cycle accounting (debug builds only: -DPST_EDGE_PROFILE): group 0 / thread 0 of every
+// CTA accumulates clock64() deltas per phase into g_edge_prof[mode][phase].
+#ifdef PST_EDGE_PROFILE
+__device__ unsigned long long g_edge_prof[2][16];
+#define PHASE(i)                                              \
+  do {                                                        \
+    if (tid == 0) {                                           \
+      long long _t = clock64();                               \
+      prof_acc[i] += (unsigned long long)(_t - prof_last);    \
+      prof_last = _t;                                         \
+    }                                                         \
+  } while (0)
+#else
+#define PHASE(i) do {} while (0)
+#endif
+
 template <typename T16, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sAall = smem + kSmemW;
-  float* sVec = reinterpret_cast<float*>(smem + kSmemW + kSmemA);                 // b2[128], b3[128]
-  uint16_t* sTabAll = reinterpret_cast<uint16_t*>(smem + kSmemW + kSmemA + 1024);  // [groups][128]
+  float* sVec = reinterpret_cast<float*>(smem + kSmemW + kSmemA);                 // b2, b3, ln_s, ln_o [128] each
   int* sBaseAll = reinterpret_cast<int*>(smem + kSmemW + kSmemA + 2048);          // [groups][4]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemW + kSmemA + 2048 + 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kGroups);
@@ -276,7 +291,6 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   const int wq = warp & 3;          // TMEM lane quarter this warp may access
   uint8_t* sA = sAall + g * kMatBytes;
   float* S = reinterpret_cast<float*>(sA);
-  uint16_t* sTab = sTabAll + g * 128;
   int* sBase = sBaseAll + g * 4;
   const int sub = gt >> 4, c16 = gt & 15;  // 16 threads per row, 8 rows per pass
   const uint32_t offA = (uint32_t)((c16 >> 3) * kKBlockBytes + sub * 128 + (((c16 & 7) ^ sub) << 4));  // + it*1024
@@ -292,6 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     if (tid < 128) {
       sVec[tid] = p.b2[tid];
       sVec[128 + tid] = MODE == 1 ? p.b3[tid] : 0.f;
+      sVec[256 + tid] = MODE == 1 ? p.ln_s[tid] : 0.f;
+      sVec[384 + tid] = MODE == 1 ? p.ln_o[tid] : 0.f;
     }
   }
   if (tid == 0) {
@@ -314,6 +330,25 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   const uint32_t sW_addr = smem_u32(sW);
   const uint32_t mbar_addr = smem_u32(&mbar[g]);
   uint32_t parity = 0;
+#ifdef PST_EDGE_PROFILE
+  unsigned long long prof_acc[16] = {0};
+  long long prof_last = clock64();
+#endif
+  // gather indices of the first tile: local sender index (16 bits) of rows it*8 + sub, two per register
+  uint32_t nidx[8];
+  int nbase = 0;
+  {
+    const int t0 = blockIdx.x * kGroups + g;
+    const int nrow0 = t0 * kTileM;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ra = nrow0 + (2 * i) * 8 + sub, rb = ra + 8;
+      const uint32_t lo = (t0 < p.num_tiles && ra < p.E) ? (uint32_t)__ldg(p.senders + ra) : 0u;
+      const uint32_t hi = (t0 < p.num_tiles && rb < p.E) ? (uint32_t)__ldg(p.senders + rb) : 0u;
+      nidx[i] = lo | (hi << 16);
+    }
+    if (gt < 4 && t0 < p.num_tiles) nbase = __ldg(p.row_base + min(nrow0 / p.K + gt, (p.E - 1) / p.K));
+  }
 
   for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
     const int row0 = tile * kTileM;
@@ -321,58 +356,80 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     const bool valid = er < p.E;
     const int first_recv = row0 / p.K;
     const int last_row = min(p.E - row0, kTileM);  // valid rows in this tile
-    // per-row gather indices: local sender (13 bits) | receiver segment within the tile (2 bits)
-    {
-      int t = 0;
-      if (valid) t = __ldg(p.senders + er) | ((er / p.K - first_recv) << 13);
-      sTab[gt] = (uint16_t)t;
-      if (gt < 4) sBase[gt] = __ldg(p.row_base + min(first_recv + gt, (p.E - 1) / p.K));
-    }
+    const int last_recv = (p.E - 1) / p.K;
+    // gather indices of this tile were fetched during the previous tile (nidx / nbase); publish the bases
+    if (gt < 4) sBase[gt] = nbase;
     tc_fence_before();
     group_sync(g);
     tc_fence_after();
+    PHASE(0);
     // ---- 0. accumulator <- (h.W1a)[sender] + (h.W1b + b1)[receiver] -----------------------------------
-    // One row-coalesced gather pass: the fp16 sender rows are copied into the A buffer (operand image
-    // layout); each thread then reads its own row, adds the receiver row (the same for 50 consecutive
-    // edges: a broadcast, L1-resident load) and writes the sum into its accumulator row in TMEM.
+    // One row-coalesced gather pass (16 threads x 16 B per row): sender row of the fp16 table + receiver row
+    // (the same for 50 consecutive edges), summed and written as fp16 into the A buffer in the operand image
+    // layout; each thread then reads its own row and writes it into its accumulator row in TMEM.
     {
       const uint4* ps4 = reinterpret_cast<const uint4*>(p.ps) + c16;
-#pragma unroll 8
-      for (int it = 0; it < 16; ++it) {
-        const int t = sTab[it * 8 + sub];
-        *reinterpret_cast<uint4*>(sA + offA + it * 1024) = __ldg(ps4 + (size_t)(sBase[t >> 13] + (t & 8191)) * (kD / 8));
-      }
-      if (MODE == 1 || true) {  // warm L2 with the next tile's edge rows (this group's next tile)
-        const int nt = tile + gridDim.x * kGroups;
-        if (nt < p.num_tiles) {
-          const char* nxt = reinterpret_cast<const char*>(p.e + (size_t)nt * kTileM * kD) + gt * 256;
-          if ((size_t)nt * kTileM + gt < (size_t)p.E) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
-          }
-        }
-      }
-    }
-    group_sync(g);
-    {
-      const int myseg = sTab[gt] >> 13;
-      const uint4* pr4 = reinterpret_cast<const uint4*>(p.pr + (size_t)(first_recv + myseg) * kD);
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float2 v[16];
+      const uint4* pr4 = reinterpret_cast<const uint4*>(p.pr) + c16;
+      int rem = row0 + sub - first_recv * p.K, seg = 0;  // row = it*8 + sub: (rem, seg) advance by 8 rows per pass
+      while (rem >= p.K) { rem -= p.K; ++seg; }
+      uint4 b = __ldg(pr4 + (size_t)min(first_recv + seg, last_recv) * (kD / 8));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 a = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
-          const uint4 b = __ldg(pr4 + q * 4 + j);
-          v[j * 4 + 0] = add2(Unpack<__half>::two(a.x), Unpack<__half>::two(b.x));
-          v[j * 4 + 1] = add2(Unpack<__half>::two(a.y), Unpack<__half>::two(b.y));
-          v[j * 4 + 2] = add2(Unpack<__half>::two(a.z), Unpack<__half>::two(b.z));
-          v[j * 4 + 3] = add2(Unpack<__half>::two(a.w), Unpack<__half>::two(b.w));
+      for (int it = 0; it < 16; ++it) {
+        const int t = (it & 1) ? (int)(nidx[it >> 1] >> 16) : (int)(nidx[it >> 1] & 0xffffu);
+        const uint4 a = __ldg(ps4 + (size_t)(sBase[seg] + t) * (kD / 8));
+        uint4 s;
+        {
+          const __half2 s0 = __hadd2(*reinterpret_cast<const __half2*>(&a.x), *reinterpret_cast<const __half2*>(&b.x));
+          const __half2 s1 = __hadd2(*reinterpret_cast<const __half2*>(&a.y), *reinterpret_cast<const __half2*>(&b.y));
+          const __half2 s2 = __hadd2(*reinterpret_cast<const __half2*>(&a.z), *reinterpret_cast<const __half2*>(&b.z));
+          const __half2 s3 = __hadd2(*reinterpret_cast<const __half2*>(&a.w), *reinterpret_cast<const __half2*>(&b.w));
+          s = make_uint4(*reinterpret_cast<const uint32_t*>(&s0), *reinterpret_cast<const uint32_t*>(&s1),
+                         *reinterpret_cast<const uint32_t*>(&s2), *reinterpret_cast<const uint32_t*>(&s3));
         }
-        tmem_st32v(tmem_row + q * 32, v);
+        *reinterpret_cast<uint4*>(sA + offA + it * 1024) = s;
+        rem += 8;
+        if (rem >= p.K) {  // next pass belongs to the next receiver (rows advance by 8, K >= 43: at most one step)
+          rem -= p.K;
+          ++seg;
+          b = __ldg(pr4 + (size_t)min(first_recv + seg, last_recv) * (kD / 8));
+        }
+      }
+      // fetch the next tile's gather indices (consumed at the top of the next iteration) and warm L2 with its rows
+      const int nt = tile + gridDim.x * kGroups;
+      if (nt < p.num_tiles) {
+        const int nrow0 = nt * kTileM;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ra = nrow0 + (2 * i) * 8 + sub, rb = ra + 8;
+          const uint32_t lo = ra < p.E ? (uint32_t)__ldg(p.senders + ra) : 0u;
+          const uint32_t hi = rb < p.E ? (uint32_t)__ldg(p.senders + rb) : 0u;
+          nidx[i] = lo | (hi << 16);
+        }
+        if (gt < 4) nbase = __ldg(p.row_base + min(nrow0 / p.K + gt, (p.E - 1) / p.K));
+        const char* nxt = reinterpret_cast<const char*>(p.e + (size_t)nrow0 * kD) + gt * 256;
+        if ((size_t)nrow0 + gt < (size_t)p.E) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
+        }
       }
     }
     group_sync(g);
+    PHASE(1);
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      float2 v[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 a = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
+        v[j * 4 + 0] = Unpack<__half>::two(a.x);
+        v[j * 4 + 1] = Unpack<__half>::two(a.y);
+        v[j * 4 + 2] = Unpack<__half>::two(a.z);
+        v[j * 4 + 3] = Unpack<__half>::two(a.w);
+      }
+      tmem_st32v(tmem_row + q * 32, v);
+    }
+    group_sync(g);
+    PHASE(2);
     // ---- 1. e tile (16-bit, global) -> A image: 16-byte copies, 16 threads per row, 8 rows per pass ----
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
@@ -386,11 +443,13 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
+    PHASE(3);
     // ---- 2. GEMM 1: acc += e . W1[256:384] -----------------------------------------------------------
     if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr, p.idesc, mbar_addr, /*accumulate_first=*/1u);
     mbar_wait(mbar_addr, parity);
     parity ^= 1;
     tc_fence_after();
+    PHASE(4);
     // ---- 3. epilogue 1: GELU -> A image ------------------------------------------------------------------
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
@@ -403,11 +462,13 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
+    PHASE(5);
     // ---- 4. GEMM 2 ----------------------------------------------------------------------------------
     if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + kMatBytes, p.idesc, mbar_addr, 0u);
     mbar_wait(mbar_addr, parity);
     parity ^= 1;
     tc_fence_after();
+    PHASE(6);
     if (MODE == 1) {
       // ---- 5a. epilogue 2: + b2, GELU -> A image; GEMM 3; epilogue 3: residual + LayerNorm -------------
 #pragma unroll 1
@@ -425,10 +486,12 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       fence_proxy_async();
       tc_fence_before();
       group_sync(g);
+      PHASE(7);
       if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + 2 * kMatBytes, p.idesc, mbar_addr, 0u);
       mbar_wait(mbar_addr, parity);
       parity ^= 1;
       tc_fence_after();
+      PHASE(8);
       // pass 1: x = acc + b3 + e.  The tile is re-read row-coalesced (an L2 hit) into the free A buffer,
       // in the operand image layout, so each thread finds its own row conflict-free; statistics; x -> TMEM.
       {
@@ -441,6 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         }
       }
       group_sync(g);
+      PHASE(9);
       float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
@@ -463,6 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         }
         tmem_st32v(tmem_row + q * 32, v);
       }
+      PHASE(10);
       const float mean = (sum2.x + sum2.y) * (1.0f / kD);
       const float var = fmaxf((sq2.x + sq2.y) * (1.0f / kD) - mean * mean, 0.f);
       const float inv = rsqrtf(var + 1e-5f);
@@ -476,8 +541,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4 ls = __ldg(reinterpret_cast<const float4*>(p.ln_s + q * 32) + c);
-          const float4 lo = __ldg(reinterpret_cast<const float4*>(p.ln_o + q * 32) + c);
+          const float4 ls = *reinterpret_cast<const float4*>(sVec + 256 + q * 32 + c * 4);
+          const float4 lo = *reinterpret_cast<const float4*>(sVec + 384 + q * 32 + c * 4);
           const float2 a0 = mul2(make_float2(ls.x, ls.y), inv2), a1 = mul2(make_float2(ls.z, ls.w), inv2);
           v[c * 2] = fma2(v[c * 2], a0, fma2(nmean2, a0, make_float2(lo.x, lo.y)));
           v[c * 2 + 1] = fma2(v[c * 2 + 1], a1, fma2(nmean2, a1, make_float2(lo.z, lo.w)));
@@ -485,6 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         store_a_chunk2<T16>(sA, gt, q * 32, v);
       }
       group_sync(g);
+      PHASE(11);
       {
         uint4* dst = reinterpret_cast<uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
 #pragma unroll 8
@@ -492,51 +558,71 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
           if (it * 8 + sub < last_row) dst[(size_t)it * 8 * (kD / 8)] = *reinterpret_cast<const uint4*>(sA + offA + it * 1024);
       }
       group_sync(g);
+      PHASE(12);
     } else {
       // ---- 5b. epilogue 2 (message mode): + b2, GELU, partial sums over the rows of each receiver ------
-      float* part = reinterpret_cast<float*>(sW + 2 * kMatBytes) + g * (4 * 64);  // W3 slot is free in message mode
-      const int col = gt & 63, half = gt >> 6;
+      // The activated tile is staged once, as fp16 in the operand image layout (the precision the third GEMM's
+      // operand has in update mode; the sums themselves are fp32).  Reduction: warp w owns column groups
+      // 4w..4w+3 (8 columns each), lane = (row slice 0..7) * 4 + column group; a thread walks the rows
+      // lo_s + slice, + 8, ... of each of the <= 4 receivers of the tile, then the 8 slices are combined with
+      // three shuffle steps: no shared-memory partials, one barrier.
 #pragma unroll 1
-      for (int hq = 0; hq < 2; ++hq) {
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          float2 v[16];
-          tmem_ld32v(tmem_row + hq * 64 + q * 32, v);
+      for (int q = 0; q < 4; ++q) {
+        float2 v[16];
+        tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = *reinterpret_cast<const float4*>(sVec + hq * 64 + q * 32 + j * 4);
-            float2 o0 = gelu2(add2(v[j * 2], make_float2(b.x, b.y)));
-            float2 o1 = gelu2(add2(v[j * 2 + 1], make_float2(b.z, b.w)));
-            if (!valid) o0 = o1 = make_float2(0.f, 0.f);
-            *reinterpret_cast<float4*>(S + gt * 64 + (((q * 8 + j) ^ gx) << 2)) = make_float4(o0.x, o0.y, o1.x, o1.y);
-          }
+        for (int c = 0; c < 8; ++c) {
+          const float4 b = *reinterpret_cast<const float4*>(sVec + q * 32 + c * 4);
+          v[c * 2] = gelu2(add2(v[c * 2], make_float2(b.x, b.y)));
+          v[c * 2 + 1] = gelu2(add2(v[c * 2 + 1], make_float2(b.z, b.w)));
         }
-        group_sync(g);
-        // thread = (column, row half): sums of its 64 rows split at the receiver boundaries
-        float acc[4];
+        store_a_chunk2<__half>(sA, gt, q * 32, v);
+      }
+      group_sync(g);
+      {
+        const int lane = tid & 31, slice = lane >> 2, cg = wq * 4 + (lane & 3);
+        float2 acc[4][4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          int lo = (first_recv + s) * p.K - row0, hi = lo + p.K;
-          lo = max(lo, half * 64);
-          hi = min(hi, half * 64 + 64);
-          float a = 0.f;
-          for (int r = lo; r < hi; ++r) a += S[r * 64 + ((((col >> 2) ^ (r & 7)) << 2) | (col & 3))];
-          acc[s] = a;
-        }
-        if (half == 1) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) part[s * 64 + col] = acc[s];
+          for (int c = 0; c < 4; ++c) acc[s][c] = make_float2(0.f, 0.f);
+          const int lo_u = (first_recv + s) * p.K - row0;
+          const int lo = max(lo_u, 0), hi = min(lo_u + p.K, last_row);
+          for (int r = lo + slice; r < hi; r += 8) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(sA + swz_offset(r, cg * 8));
+            acc[s][0] = add2(acc[s][0], Unpack<__half>::two(pk.x));
+            acc[s][1] = add2(acc[s][1], Unpack<__half>::two(pk.y));
+            acc[s][2] = add2(acc[s][2], Unpack<__half>::two(pk.z));
+            acc[s][3] = add2(acc[s][3], Unpack<__half>::two(pk.w));
+          }
         }
-        group_sync(g);
-        if (half == 0) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s)
-            p.partial[((size_t)tile * 4 + s) * kD + hq * 64 + col] = acc[s] + part[s * 64 + col];
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int m = 4; m <= 16; m <<= 1) {
+              acc[s][c].x += __shfl_xor_sync(0xffffffffu, acc[s][c].x, m);
+              acc[s][c].y += __shfl_xor_sync(0xffffffffu, acc[s][c].y, m);
+            }
+          }
+        if (slice == 0) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            float4* dst = reinterpret_cast<float4*>(p.partial + ((size_t)tile * 4 + s) * kD + cg * 8);
+            dst[0] = make_float4(acc[s][0].x, acc[s][0].y, acc[s][1].x, acc[s][1].y);
+            dst[1] = make_float4(acc[s][2].x, acc[s][2].y, acc[s][3].x, acc[s][3].y);
+          }
         }
-        group_sync(g);
       }
+      group_sync(g);
+      PHASE(13);
     }
   }
+#ifdef PST_EDGE_PROFILE
+  if (tid == 0)
+    for (int i = 0; i < 16; ++i) atomicAdd(&g_edge_prof[MODE][i], prof_acc[i]);
+#endif
 
   tc_fence_before();
   __syncthreads();
@@ -573,6 +659,17 @@ __global__ void build_weight_image_kernel(const float* __restrict__ w, uint16_t*
 }
 
 }  // namespace
+
+#ifdef PST_EDGE_PROFILE
+extern "C" int pst_debug_edge_profile(unsigned long long* out32, int reset) {
+  if (cudaMemcpyFromSymbol(out32, g_edge_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_edge_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int pst_prepare_tc_weights(pst_model* m) {
   const int layers = m->cfg.gnn_layers;
