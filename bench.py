@@ -37,8 +37,14 @@ WORKLOADS = {
 }
 # algorithmic work per valid residue (reference formulation, live ops, 2*MAC)
 FLOP_PER_RESIDUE = {1: 44.91e6, 2: 44.6e6, 4: 44.39e6}
-FLOP_PER_EDGE_MLP = 2 * 81920  # one 384->128->128->128 MLP on one edge (reference formulation)
-HW_FLOP_PER_EDGE_MLP = 2 * 3 * 128 * 128  # what the kernel issues after factorising the first linear
+FLOP_PER_EDGE_MLP = 2 * 81920  # one 384->128->128->128 MLP on one edge (reference formulation, SURVEY 8d)
+# what the tensor cores are actually issued per edge: the first linear is factorised (K = 128 instead of 384) and in
+# message mode the third linear is applied after the mean over K (once per residue, by linear_tc)
+HW_FLOP_MSG = 2 * 2 * 128 * 128
+HW_FLOP_UPD = 2 * 3 * 128 * 128
+# DRAM bytes per launch of the dominant kernel, from the committed capture profiles/r01_edge_mlp_tc_ncu_full.md
+# (dram__bytes_read.sum + dram__bytes_write.sum at 256 x 512 residues): message mode 1.876 GB, update mode 3.395 GB
+NCU_DRAM_BYTES = {"msg": 1.876e9, "upd": 3.395e9, "residues": 131072}
 
 
 def load_peaks():
@@ -294,9 +300,13 @@ def run_ours(args):
             peak = peaks["bf16_tflops_sustained"]
             roof = {
                 "bound": "tensor", "kernel": "edge-level MLP (message + edge-update), one launch group per MLP",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": ((prof_cnt[1] * NCU_DRAM_BYTES["msg"] + prof_cnt[2] * NCU_DRAM_BYTES["upd"]) / mlp_groups
+                            * R / NCU_DRAM_BYTES["residues"]) if args.precision != "fp32" else None,
+                "traffic_source": "ncu --set full, profiles/r01_edge_mlp_tc_ncu_full.md (per launch, scaled to this batch)",
+                "algorithmic_bytes_per_launch": E * 256 * (prof_cnt[1] * 1 + prof_cnt[2] * 2) / mlp_groups,
                 "peak_source": f"{peaks['source']} (bf16_tflops_sustained, MEASURED_PEAKS.json)",
-                "hw_flops_tflops": E * HW_FLOP_PER_EDGE_MLP / avg_s / 1e12,
+                "hw_flops_tflops": E * (prof_cnt[1] * HW_FLOP_MSG + prof_cnt[2] * HW_FLOP_UPD) / (mlp_ms * 1e-3) / 1e12,
                 "avg_launch_ms": mlp_ms / mlp_groups, "launch_groups_per_step": mlp_groups / args.steps,
                 "share_of_step": mlp_ms / ms_total,
                 "featurize_knn_ms_per_step": prof_ms[0] / max(1, prof_cnt[0]),
