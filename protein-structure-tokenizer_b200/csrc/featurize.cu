@@ -261,7 +261,16 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
   const double4 ci = cen4[row];
   Cand b0, b1;  // running 64 smallest, ascending, element e = 2*lane + r
   const int n_chunks = (L + 63) >> 6;
-  for (int c = 0; c < n_chunks; ++c) {
+  // Chunks are visited outwards from the one that holds the row itself (sequence neighbours are spatial
+  // neighbours, so the running 64-th smallest distance tightens early); a chunk none of whose distances is
+  // <= that bound cannot change the result and is skipped after the distance evaluation (warp vote).
+  const int c_home = (row - base) >> 6;
+  unsigned long long bound = 0xFFFFFFFFFFFFFFFFull;
+  for (int step = 0; step < 2 * n_chunks; ++step) {
+    // step 0 -> home, then +1, -1, +2, -2, ...
+    const int delta = (step + 1) >> 1;
+    const int c = (step & 1) ? c_home + delta : c_home - delta;
+    if (step == 0 ? false : (c < 0 || c >= n_chunks)) continue;
     Cand a0, a1;
     {
       const int j0 = c * 64 + 2 * lane;
@@ -279,8 +288,9 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
         a1.key = (unsigned long long)__double_as_longlong(sqrt((dx * dx + dy * dy) + dz * dz));
       }
     }
+    if (step > 0 && !__any_sync(0xffffffffu, a0.key <= bound || a1.key <= bound)) continue;
     bitonic_sort64(a0, a1, lane);
-    if (c == 0) {
+    if (step == 0) {
       b0 = a0;
       b1 = a1;
     } else {
@@ -290,6 +300,7 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
       if (cand_less(r1, b1)) b1 = r1;
       bitonic_stages(b0, b1, lane, 64);  // bitonic -> ascending
     }
+    bound = __shfl_sync(0xffffffffu, b1.key, 31);  // largest of the current 64 smallest
   }
   s_d[warp][2 * lane] = __longlong_as_double((long long)b0.key);
   s_d[warp][2 * lane + 1] = __longlong_as_double((long long)b1.key);
