@@ -97,6 +97,7 @@ PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T) {
   const size_t RT = (size_t)(R > T ? R : T);
   ws.status = (int32_t*)take(4 * sizeof(int32_t));
   ws.row_base = (int32_t*)take((size_t)R * sizeof(int32_t));
+  ws.redo = (int32_t*)take((size_t)R * sizeof(int32_t));
   ws.prep = (double*)take((size_t)R * PST_PREP_STRIDE * sizeof(double));
   ws.cen4 = (double*)take((size_t)R * 4 * sizeof(double));
   ws.senders = (int32_t*)take(E * sizeof(int32_t));
@@ -273,7 +274,7 @@ int pst_featurize_knn(const pst_model* m, void* stream, const float* atoms, cons
   PstWorkspace ws = pst_carve_workspace(m, workspace, total_residues, total_residues);
   PST_CUDA_OK(cudaMemsetAsync(ws.status, 0, 4 * sizeof(int32_t), st));
   m->launch_count = pst_launch_featurize(m, st, atoms, atom_mask, atoms_per_residue, offsets, num_structures,
-                                         total_residues, senders_out, edge_features_out, ws.prep, ws.cen4, ws.status);
+                                         total_residues, senders_out, edge_features_out, ws.prep, ws.cen4, ws.status, ws.redo);
   return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
 }
 
@@ -331,7 +332,7 @@ int pst_tokenize(const pst_model* m, void* stream, const float* atoms, const uin
   {
     PstSpan span(m, st, 0);
     count = pst_launch_featurize(m, st, atoms, atom_mask, atoms_per_residue, offsets, num_structures,
-                                 total_residues, ws.senders, ws.edge_feat, ws.prep, ws.cen4, ws.status);
+                                 total_residues, ws.senders, ws.edge_feat, ws.prep, ws.cen4, ws.status, ws.redo);
   }
   int n = pst_launch_encode_fp32(m, st, ws.edge_feat, ws.senders, offsets, token_offsets, num_structures,
                                  total_residues, total_tokens, ws.z, ws);

@@ -83,11 +83,12 @@ template <int kThreads>
 __global__ void __launch_bounds__(kThreads)
 knn_feature_kernel(const double* __restrict__ prep, const int32_t* __restrict__ offsets, int B, int R,
                    int K, int max_len, int32_t* __restrict__ senders, float* __restrict__ feat,
-                   int32_t* __restrict__ status) {
+                   int32_t* __restrict__ status, const int32_t* __restrict__ redo) {
   extern __shared__ unsigned long long smem_keys[];
   __shared__ int s_struct[2];
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
+  if (redo && !redo[row]) return;  // second pass: only the rows the warp kernel flagged
   if (tid == 0) {
     int lo = 0, hi = B;  // largest b with offsets[b] <= row
     while (hi - lo > 1) {
@@ -178,64 +179,68 @@ knn_feature_kernel(const double* __restrict__ prep, const int32_t* __restrict__ 
 
 // -------------------------------------------------------------------------------------------------
 // Warp-per-row k-NN: the L distances of a row are streamed in chunks of 64 (2 per lane); each chunk is
-// sorted with a register/shuffle bitonic network and merged into the running 64 smallest
-// (min against the reversed chunk gives a bitonic sequence holding the 64 smallest of the union, then
-// a 6-stage bitonic merge).  Ordering is lexicographic on (fp64 distance bits, index): exactly the
-// stable ascending argsort the reference's contract is defined by.  No block barriers.
-struct Cand {
-  unsigned long long key;
-  int idx;
-};
-__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) {
-  return (a.key < b.key) || (a.key == b.key && a.idx < b.idx);
+// sorted with a register/shuffle bitonic network and merged into the running 64 smallest (min against
+// the reversed chunk gives a bitonic sequence holding the 64 smallest of the union, then a 6-stage
+// bitonic merge).  No block barriers.
+//
+// Keys are single 64-bit words: the fp64 distance bit pattern with its 11 lowest mantissa bits replaced
+// by the candidate index (structures handled here have L <= 2048).  Two candidates whose distances agree
+// in the upper 53 bits would be ordered by index instead of by their last 11 bits, so the kernel CHECKS
+// the sorted head: if two adjacent entries among ranks 0..K+2 share the truncated distance (this also
+// covers exact ties), the row is flagged and recomputed by the exact (distance, index) block kernel
+// below.  The emitted order is therefore always the stable ascending argsort of the reference contract.
+__device__ __forceinline__ void ce_remote(unsigned long long& a, int lane_mask, bool keep_min) {
+  const unsigned long long o = __shfl_xor_sync(0xffffffffu, a, lane_mask);
+  if ((o < a) == keep_min) a = o;
 }
-__device__ __forceinline__ Cand cand_shfl_xor(const Cand& a, int mask) {
-  Cand o;
-  o.key = __shfl_xor_sync(0xffffffffu, a.key, mask);
-  o.idx = __shfl_xor_sync(0xffffffffu, a.idx, mask);
-  return o;
-}
-// compare-exchange across lanes: element index e = 2*lane + r, partner e ^ j (j >= 2), ascending iff asc
-__device__ __forceinline__ void ce_remote(Cand& a, int lane_mask, bool keep_min) {
-  const Cand o = cand_shfl_xor(a, lane_mask);
-  const bool o_less = cand_less(o, a);
-  if (o_less == keep_min) a = o;
-}
-__device__ __forceinline__ void ce_local(Cand& a0, Cand& a1, bool asc) {
-  if (cand_less(a1, a0) == asc) {
-    const Cand t = a0;
+__device__ __forceinline__ void ce_local(unsigned long long& a0, unsigned long long& a1, bool asc) {
+  if ((a1 < a0) == asc) {
+    const unsigned long long t = a0;
     a0 = a1;
     a1 = t;
   }
 }
-// stages j = k/2 .. 1 of a bitonic network on 64 elements (2 per lane); dir(e) ascending iff (e & k) == 0
-__device__ __forceinline__ void bitonic_stages(Cand& a0, Cand& a1, int lane, int k) {
+// stages j = k/2 .. 1 of a bitonic network on 64 elements (element e = 2*lane + r); ascending iff (e & k) == 0
+__device__ __forceinline__ void bitonic_stages(unsigned long long& a0, unsigned long long& a1, int lane, int k) {
   const int e0 = 2 * lane;
-  const bool asc = (e0 & k) == 0;  // bit k of e0 and e0+1 agree for k >= 2
+  const bool asc = (e0 & k) == 0;
 #pragma unroll
   for (int j = 32; j >= 2; j >>= 1) {
     if (j < k) {
-      const bool lower = (e0 & j) == 0;
-      const bool keep_min = (lower == asc);
+      const bool keep_min = (((e0 & j) == 0) == asc);
       ce_remote(a0, j >> 1, keep_min);
       ce_remote(a1, j >> 1, keep_min);
     }
   }
   ce_local(a0, a1, asc);
 }
-__device__ __forceinline__ void bitonic_sort64(Cand& a0, Cand& a1, int lane) {
+__device__ __forceinline__ void bitonic_sort64(unsigned long long& a0, unsigned long long& a1, int lane) {
 #pragma unroll
   for (int k = 2; k <= 64; k <<= 1) bitonic_stages(a0, a1, lane, k);
 }
 
+// 1.5**k, k = 0..14 (utils/protein_utils.py:266): exact in fp64
+__constant__ double c_rbf_scale[15] = {1.0, 1.5, 2.25, 3.375, 5.0625, 7.59375, 11.390625, 17.0859375, 25.62890625,
+                                      38.443359375, 57.6650390625, 86.49755859375, 129.746337890625,
+                                      194.6195068359375, 291.92926025390625};
+
 constexpr int kKnnWarps = 8;
+constexpr unsigned long long kIdxMask = 0x7FFull;  // 11 bits: L <= 2048
+
+__device__ __forceinline__ unsigned long long packed_key(const double4& ci, const double4* __restrict__ cen4, int base, int j, int L) {
+  if (j >= L) return 0xFFFFFFFFFFFFFFFFull;
+  const double4 cj = cen4[base + j];
+  const double dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(sqrt((dx * dx + dy * dy) + dz * dz));
+  return (bits & ~kIdxMask) | (unsigned long long)j;
+}
 
 __global__ void __launch_bounds__(kKnnWarps * 32)
 knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen4, const int32_t* __restrict__ offsets,
                 int B, int R, int K, int max_len, int32_t* __restrict__ senders, float* __restrict__ feat,
-                int32_t* __restrict__ status) {
-  __shared__ double s_d[kKnnWarps][64];
+                int32_t* __restrict__ status, int32_t* __restrict__ redo) {
   __shared__ int s_j[kKnnWarps][64];
+  __shared__ double s_d2[kKnnWarps][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kKnnWarps + warp;
   if (row >= R) return;
@@ -259,85 +264,79 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
     return;
   }
   const double4 ci = cen4[row];
-  Cand b0, b1;  // running 64 smallest, ascending, element e = 2*lane + r
+  unsigned long long b0 = 0, b1 = 0;  // running 64 smallest keys, ascending, element e = 2*lane + r
   const int n_chunks = (L + 63) >> 6;
-  // Chunks are visited outwards from the one that holds the row itself (sequence neighbours are spatial
-  // neighbours, so the running 64-th smallest distance tightens early); a chunk none of whose distances is
-  // <= that bound cannot change the result and is skipped after the distance evaluation (warp vote).
+  // Chunks are visited outwards from the one that holds the row itself; a chunk none of whose keys is below
+  // the current 64-th smallest cannot change the result and is skipped after the distance evaluation.
   const int c_home = (row - base) >> 6;
   unsigned long long bound = 0xFFFFFFFFFFFFFFFFull;
   for (int step = 0; step < 2 * n_chunks; ++step) {
-    // step 0 -> home, then +1, -1, +2, -2, ...
     const int delta = (step + 1) >> 1;
     const int c = (step & 1) ? c_home + delta : c_home - delta;
-    if (step == 0 ? false : (c < 0 || c >= n_chunks)) continue;
-    Cand a0, a1;
-    {
-      const int j0 = c * 64 + 2 * lane;
-      a0.idx = j0;
-      a1.idx = j0 + 1;
-      a0.key = a1.key = 0xFFFFFFFFFFFFFFFFull;
-      if (j0 < L) {
-        const double4 cj = cen4[base + j0];
-        const double dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z;
-        a0.key = (unsigned long long)__double_as_longlong(sqrt((dx * dx + dy * dy) + dz * dz));
-      }
-      if (j0 + 1 < L) {
-        const double4 cj = cen4[base + j0 + 1];
-        const double dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z;
-        a1.key = (unsigned long long)__double_as_longlong(sqrt((dx * dx + dy * dy) + dz * dz));
-      }
-    }
-    if (step > 0 && !__any_sync(0xffffffffu, a0.key <= bound || a1.key <= bound)) continue;
+    if (step > 0 && (c < 0 || c >= n_chunks)) continue;
+    const int j0 = c * 64 + 2 * lane;
+    unsigned long long a0 = packed_key(ci, cen4, base, j0, L);
+    unsigned long long a1 = packed_key(ci, cen4, base, j0 + 1, L);
+    if (step > 0 && !__any_sync(0xffffffffu, a0 < bound || a1 < bound)) continue;
     bitonic_sort64(a0, a1, lane);
     if (step == 0) {
       b0 = a0;
       b1 = a1;
     } else {
       // reversed chunk: element e <- element 63 - e  (lane 31 - lane, registers swapped)
-      const Cand r0 = cand_shfl_xor(a1, 31), r1 = cand_shfl_xor(a0, 31);
-      if (cand_less(r0, b0)) b0 = r0;
-      if (cand_less(r1, b1)) b1 = r1;
+      const unsigned long long r0 = __shfl_xor_sync(0xffffffffu, a1, 31), r1 = __shfl_xor_sync(0xffffffffu, a0, 31);
+      b0 = r0 < b0 ? r0 : b0;
+      b1 = r1 < b1 ? r1 : b1;
       bitonic_stages(b0, b1, lane, 64);  // bitonic -> ascending
     }
-    bound = __shfl_sync(0xffffffffu, b1.key, 31);  // largest of the current 64 smallest
+    bound = __shfl_sync(0xffffffffu, b1, 31);  // largest of the current 64 smallest
   }
-  s_d[warp][2 * lane] = __longlong_as_double((long long)b0.key);
-  s_d[warp][2 * lane + 1] = __longlong_as_double((long long)b1.key);
-  s_j[warp][2 * lane] = b0.idx;
-  s_j[warp][2 * lane + 1] = b1.idx;
+  // exactness check on the sorted head (ranks 0 .. K+2): equal truncated distances -> exact recompute
+  {
+    const unsigned long long nxt = __shfl_down_sync(0xffffffffu, b0, 1);  // element 2*lane + 2
+    bool clash = (2 * lane + 1 <= K + 2) && ((b0 >> 11) == (b1 >> 11)) && (b1 != 0xFFFFFFFFFFFFFFFFull);
+    clash = clash || ((2 * lane + 2 <= K + 2) && lane < 31 && ((b1 >> 11) == (nxt >> 11)) && (nxt != 0xFFFFFFFFFFFFFFFFull));
+    if (__any_sync(0xffffffffu, clash)) {
+      if (lane == 0) redo[row] = 1;
+      return;
+    }
+  }
+  s_j[warp][2 * lane] = (int)(b0 & kIdxMask);
+  s_j[warp][2 * lane + 1] = (int)(b1 & kIdxMask);
   __syncwarp();
   const int first = (L == K) ? 0 : 1;  // protein_utils.py:385-389
   for (int e = lane; e < K; e += 32) senders[(size_t)row * K + e] = s_j[warp][first + e];
   if (!feat) return;
 
+  // ---- features: squared distances once per edge, then the 750 RBF items and the 600 orientation items as two
+  // divergence-free loops (item -> lane mapping keeps consecutive lanes on consecutive output floats)
   const double* pi = prep + (size_t)row * PST_PREP_STRIDE;
-  const double ca_x = pi[3], ca_y = pi[4], ca_z = pi[5];
+  for (int e = lane; e < K; e += 32) {
+    const double4 cj = cen4[base + s_j[warp][first + e]];
+    const double dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z;
+    const double d = sqrt((dx * dx + dy * dy) + dz * dz);  // the reference squares the rounded distance again
+    s_d2[warp][e] = d * d;
+  }
+  __syncwarp();
   float* out = feat + (size_t)row * K * PST_EDGE_FEATURES;
-  for (int t = lane; t < K * PST_EDGE_FEATURES; t += 32) {
-    const int e = t / PST_EDGE_FEATURES;
-    const int f = t - e * PST_EDGE_FEATURES;
-    double val;
-    if (f < 15) {
-      const double d = s_d[warp][first + e];
-      double scale = 1.0;
-      for (int q = 0; q < f; ++q) scale = scale * 1.5;  // 1.5**f, exact in fp64
-      val = exp(-(d * d) / scale);
+  for (int t = lane; t < K * 15; t += 32) {
+    const int e = t / 15, f = t - e * 15;
+    out[e * PST_EDGE_FEATURES + f] = (float)exp(-s_d2[warp][e] / c_rbf_scale[f]);
+  }
+  const double ca_x = pi[3], ca_y = pi[4], ca_z = pi[5];
+  for (int t = lane; t < K * 12; t += 32) {
+    const int e = t / 12, c = t - e * 12;
+    const int g = c / 3, r = c - 3 * g;  // g: 0:p 1:q 2:k 3:t ; r: basis row 0:n 1:u 2:v
+    const double* pj = prep + (size_t)(base + s_j[warp][first + e]) * PST_PREP_STRIDE;
+    double vx, vy, vz;
+    if (g == 0) {
+      vx = pj[3] - ca_x; vy = pj[4] - ca_y; vz = pj[5] - ca_z;
     } else {
-      const int g = (f - 15) / 3;      // 0:p 1:q 2:k 3:t
-      const int r = (f - 15) - 3 * g;  // basis row: 0:n 1:u 2:v
-      const double* pj = prep + (size_t)(base + s_j[warp][first + e]) * PST_PREP_STRIDE;
-      double vx, vy, vz;
-      if (g == 0) {
-        vx = pj[3] - ca_x; vy = pj[4] - ca_y; vz = pj[5] - ca_z;
-      } else {
-        const double* s = pj + 3 + 3 * g;
-        vx = s[0]; vy = s[1]; vz = s[2];
-      }
-      const double* b = pi + 6 + 3 * r;
-      val = b[0] * vx + b[1] * vy + b[2] * vz;
+      const double* sv = pj + 3 + 3 * g;
+      vx = sv[0]; vy = sv[1]; vz = sv[2];
     }
-    out[t] = (float)val;
+    const double* b = pi + 6 + 3 * r;
+    out[e * PST_EDGE_FEATURES + 15 + c] = (float)(b[0] * vx + b[1] * vy + b[2] * vz);
   }
 }
 
@@ -345,23 +344,26 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
 
 int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms,
                          const uint8_t* mask, int apr, const int32_t* offsets, int B, int R,
-                         int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status) {
+                         int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status, int32_t* redo) {
   if (R <= 0) return 0;
   prep_kernel<<<(R + 127) / 128, 128, 0, st>>>(atoms, mask, apr, R, prep, reinterpret_cast<double4*>(cen4));
-  if (m->cfg.num_neighbor <= 62) {
-    knn_warp_kernel<<<(R + kKnnWarps - 1) / kKnnWarps, kKnnWarps * 32, 0, st>>>(
-        prep, reinterpret_cast<const double4*>(cen4), offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len, senders,
-        edge_feat, status);
-    return 2;
-  }
-  // K = 63, 64: the warp kernel keeps only 64 candidates (K + 1 needed); use the block-sort kernel
   int n_pad = 64;
   while (n_pad < m->cfg.max_len) n_pad <<= 1;
-  size_t smem = (size_t)n_pad * (sizeof(unsigned long long) + sizeof(int));
+  const size_t smem = (size_t)n_pad * (sizeof(unsigned long long) + sizeof(int));
   constexpr int kThreads = 256;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(knn_feature_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  knn_feature_kernel<kThreads><<<R, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor,
-                                                         m->cfg.max_len, senders, edge_feat, status);
+  if (m->cfg.num_neighbor <= 60 && m->cfg.max_len <= 2048) {
+    cudaMemsetAsync(redo, 0, (size_t)R * sizeof(int32_t), st);
+    knn_warp_kernel<<<(R + kKnnWarps - 1) / kKnnWarps, kKnnWarps * 32, 0, st>>>(
+        prep, reinterpret_cast<const double4*>(cen4), offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len, senders,
+        edge_feat, status, redo);
+    // exact recompute of the (normally zero) rows flagged above
+    knn_feature_kernel<kThreads><<<R, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,
+                                                           senders, edge_feat, status, redo);
+    return 3;
+  }
+  knn_feature_kernel<kThreads><<<R, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,
+                                                         senders, edge_feat, status, nullptr);
   return 2;
 }

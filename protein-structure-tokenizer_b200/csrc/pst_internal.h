@@ -94,6 +94,7 @@ size_t pst_fill_weight_pointers(const pst_config& cfg, const float* base, PstWei
 struct PstWorkspace {
   int32_t* status;       // [4]
   int32_t* row_base;     // [R]
+  int32_t* redo;         // [R] rows the packed-key k-NN kernel hands to the exact kernel
   double* prep;          // [R,16]
   double* cen4;          // [R,4] centroid (x,y,z,0): compact copy for the k-NN scan
   int32_t* senders;      // [E]
@@ -125,7 +126,8 @@ PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T_up
 // ---- kernel launchers (each returns the number of kernels enqueued) --------------
 int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms,
                          const uint8_t* mask, int apr, const int32_t* offsets, int B, int R,
-                         int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status);
+                         int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status,
+                         int32_t* redo);
 
 int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edge_feat,
                            const int32_t* senders, const int32_t* offsets,

@@ -103,3 +103,28 @@ def test_atom37_and_backbone4_layouts_agree(tok):
     s4, f4, _ = _run(tok, [bb])
     s37, f37, _ = _run(tok, [pos], [gt.astype(np.uint8)])
     assert np.array_equal(s4, s37) and np.array_equal(f4, f37)
+
+
+def test_exact_distance_ties_follow_stable_argsort(tok):
+    """Residues on a regular lattice: many exactly equal distances.  The packed-key k-NN kernel must detect them
+    and hand those rows to the exact (distance, index) kernel; the result is the stable argsort of the reference
+    contract."""
+    from oracle import featurize as fz
+
+    g = np.stack(np.meshgrid(np.arange(5), np.arange(5), np.arange(4), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    ca = g * 4.0  # 100 residues on a 4 A lattice
+    bb = np.stack([ca + np.float32([-1.2, 0.6, 0.1]), ca, ca + np.float32([1.1, 0.9, -0.2]), ca + np.float32([1.6, 2.0, 0.3])], axis=1)
+    bb = np.round(bb, 3).astype(np.float32)
+    s, f, offs = _run(tok, [bb])
+    assert tok.read_status() == 0
+    pos = np.zeros((100, 37, 3), np.float32)
+    gt = np.zeros((100, 37), bool)
+    for src, dst in enumerate((0, 1, 2, 4)):
+        pos[:, dst] = bb[:, src]
+        gt[:, dst] = True
+    o = fz.featurize(pos, gt, gt, 50)
+    assert fz.has_rank_ties(fz.pairwise_distance(o["centroid"]), 50)  # the input really has ties
+    assert np.array_equal(s.astype(np.int64), o["senders"])
+    u = ulp_diff(f, o["edge_features"].astype(np.float32))
+    tiny = np.abs(o["edge_features"].astype(np.float32)) < 1e-30
+    assert (u[~tiny] <= 1).all()
