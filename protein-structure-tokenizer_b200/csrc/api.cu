@@ -167,6 +167,8 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   m->launch_count = 0;
   m->tc_dev = nullptr;
   m->linear_tc = nullptr;
+  m->embed_img_dev = nullptr;
+  m->table16_dev = nullptr;
   m->prof_on = false;
   m->prof_n = 0;
   for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i) m->prof_ev[i] = nullptr;
@@ -211,6 +213,8 @@ void pst_model_destroy(pst_model* m) {
   if (m->blob_dev) cudaFree(m->blob_dev);
   if (m->tc_dev) cudaFree(m->tc_dev);
   pst_destroy_linear_tc(m);
+  if (m->embed_img_dev) cudaFree(m->embed_img_dev);
+  if (m->table16_dev) cudaFree(m->table16_dev);
   for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i)
     if (m->prof_ev[i]) cudaEventDestroy(m->prof_ev[i]);
   delete m;

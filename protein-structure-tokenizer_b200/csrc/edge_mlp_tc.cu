@@ -631,6 +631,181 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Input edge embedding on the tensor cores (reference: structure_tokenizer/model/structure_encoder.py:94-105):
+//   e0 = PE_edge(s - r) . W[0:128] + b  (a constant table row, folded at weight-pack time)  +  f27 . W[128:155]
+// Per 128-edge tile: the 27 features are read as one contiguous coalesced block, split into fp16 hi/lo
+// operand images (K padded to 32), multiplied by the hi/lo images of W[128:155] with three tcgen05.mma per
+// k-step (hi.hi + hi.lo + lo.hi: fp32-level accuracy); meanwhile the fp16 table rows are gathered
+// row-coalesced into the (then free) A buffer; the epilogue adds them to the accumulator row, packs the
+// 16-bit edge state in place and the tile is copied out row-coalesced.  Same 4-group persistent structure
+// as the edge MLP kernel.
+constexpr uint32_t kEmbSmemW = 2 * 16384;  // W hi / lo images, [128 n x 64 k] (k < 32 used)
+constexpr uint32_t kEmbSmemTotal = kEmbSmemW + kSmemA + kGroups * 256 + 64;
+
+struct EmbedParams {
+  const uint16_t* w_img;     // hi image (16 KB) then lo image (16 KB)
+  const __half* table;       // [2*seq_max-1, 128] fp16
+  const float* feat;         // [E, 27]
+  const int32_t* senders;    // [E]
+  const int32_t* row_base;   // [R]
+  uint16_t* e;               // [E, 128] out
+  int E, K, num_tiles, seq_max;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ uint32_t swz_k64(uint32_t row, uint32_t kk) {  // element (row, kk < 64) of a [128 x 64] image
+  return row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1));
+}
+
+template <typename T16>
+__global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sAall = smem + kEmbSmemW;
+  uint16_t* sTabAll = reinterpret_cast<uint16_t*>(smem + kEmbSmemW + kSmemA);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kEmbSmemW + kSmemA + kGroups * 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kGroups);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = warp >> 2, gt = tid & 127, wq = warp & 3;
+  uint8_t* sA = sAall + g * kMatBytes;
+  uint16_t* sTab = sTabAll + g * 128;
+  const int sub = gt >> 4, c16 = gt & 15;
+  const uint32_t offA = (uint32_t)((c16 >> 3) * kKBlockBytes + sub * 128 + (((c16 & 7) ^ sub) << 4));
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
+    uint4* dst = reinterpret_cast<uint4*>(sW);
+    for (int i = tid; i < (int)(kEmbSmemW / 16); i += kThreads) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc = tmem_base + (uint32_t)(g * 128);
+  const uint32_t tmem_row = tmem_acc + ((uint32_t)(wq * 32) << 16);
+  const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), mbar_addr = smem_u32(&mbar[g]);
+  uint32_t parity = 0;
+
+  for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
+    const int row0 = tile * kTileM;
+    const int er = row0 + gt;
+    const int last_row = min(p.E - row0, kTileM);
+    // table row of this thread's edge: sender - receiver (local indices) + seq_max - 1
+    {
+      int t = 0;
+      if (er < p.E) {
+        const int recv = er / p.K;
+        t = __ldg(p.senders + er) - (recv - __ldg(p.row_base + recv)) + (p.seq_max - 1);
+      }
+      sTab[gt] = (uint16_t)t;
+    }
+    // ---- features -> fp16 hi / lo operand images (A_hi at K block 0, A_lo at K block 1 of the buffer) ----
+    {
+      const float* f0 = p.feat + (size_t)row0 * PST_EDGE_FEATURES;
+      const int n_el = last_row * PST_EDGE_FEATURES;
+#pragma unroll 9
+      for (int i = 0; i < PST_EDGE_FEATURES; ++i) {
+        const int idx = gt + i * 128;
+        const float x = idx < n_el ? __ldg(f0 + idx) : 0.f;
+        const int r = idx / PST_EDGE_FEATURES, kk = idx - r * PST_EDGE_FEATURES;
+        const __half hi = __float2half_rn(x);
+        const __half lo = __float2half_rn(x - __half2float(hi));
+        const uint32_t off = swz_k64(r, kk);
+        *reinterpret_cast<__half*>(sA + off) = hi;
+        *reinterpret_cast<__half*>(sA + kKBlockBytes + off) = lo;
+      }
+      // zero the K padding 27..31 of this thread's own row (the matching weight rows are zero, but 0 * garbage
+      // must not be NaN)
+#pragma unroll
+      for (int kk = PST_EDGE_FEATURES; kk < 32; ++kk) {
+        const uint32_t off = swz_k64(gt, kk);
+        *reinterpret_cast<uint16_t*>(sA + off) = 0;
+        *reinterpret_cast<uint16_t*>(sA + kKBlockBytes + off) = 0;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    group_sync(g);
+    if (gt == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {  // K = 32 = 2 x UMMA_K
+        const uint32_t o = j * 32;
+        umma_f16(tmem_acc, make_smem_desc(sA_addr + o), make_smem_desc(sW_addr + o), p.idesc, j > 0 ? 1u : 0u);
+        umma_f16(tmem_acc, make_smem_desc(sA_addr + o), make_smem_desc(sW_addr + 16384 + o), p.idesc, 1u);
+        umma_f16(tmem_acc, make_smem_desc(sA_addr + kKBlockBytes + o), make_smem_desc(sW_addr + o), p.idesc, 1u);
+      }
+      umma_commit(mbar_addr);
+    }
+    mbar_wait(mbar_addr, parity);
+    parity ^= 1;
+    tc_fence_after();
+    // ---- table rows (fp16) gathered row-coalesced into the now free buffer, operand image layout --------
+    {
+      const uint4* tb = reinterpret_cast<const uint4*>(p.table) + c16;
+#pragma unroll 8
+      for (int it = 0; it < 16; ++it)
+        *reinterpret_cast<uint4*>(sA + offA + it * 1024) = __ldg(tb + (size_t)sTab[it * 8 + sub] * (kD / 8));
+    }
+    group_sync(g);
+    // ---- epilogue: acc + table row -> 16-bit edge state, in place (each thread only touches its own row) ----
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      float2 v[16];
+      tmem_ld32v(tmem_row + q * 32, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
+        v[j * 4 + 0] = add2(v[j * 4 + 0], Unpack<__half>::two(pk.x));
+        v[j * 4 + 1] = add2(v[j * 4 + 1], Unpack<__half>::two(pk.y));
+        v[j * 4 + 2] = add2(v[j * 4 + 2], Unpack<__half>::two(pk.z));
+        v[j * 4 + 3] = add2(v[j * 4 + 3], Unpack<__half>::two(pk.w));
+      }
+      store_a_chunk2<T16>(sA, gt, q * 32, v);
+    }
+    tc_fence_before();
+    group_sync(g);
+    {
+      uint4* dst = reinterpret_cast<uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
+#pragma unroll 8
+      for (int it = 0; it < 16; ++it)
+        if (it * 8 + sub < last_row) dst[(size_t)it * 8 * (kD / 8)] = *reinterpret_cast<const uint4*>(sA + offA + it * 1024);
+    }
+    group_sync(g);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// W[128:155] (fp32 [32 (27 used), 128]) -> hi / lo fp16 images [128 n x 64 k]; table fp32 -> fp16
+__global__ void build_embed_images_kernel(const float* __restrict__ wf, uint16_t* __restrict__ img) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * 64) return;
+  const int n = idx >> 6, kk = idx & 63;
+  const float x = kk < PST_EDGE_FEATURES ? wf[kk * kD + n] : 0.f;
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  img[swz_k64(n, kk) >> 1] = *reinterpret_cast<const uint16_t*>(&hi);
+  img[(16384 + swz_k64(n, kk)) >> 1] = *reinterpret_cast<const uint16_t*>(&lo);
+}
+__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
 // tbar[r] = (sum of the partial row sums that cover receiver r) / K
 __global__ void combine_partials_kernel(const float* __restrict__ partial, int K, int R, float* __restrict__ tbar) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -689,6 +864,16 @@ int pst_prepare_tc_weights(pst_model* m) {
           build_weight_image_kernel<__nv_bfloat16><<<64, 256>>>(src[t][j], dst);
       }
   }
+  {
+    const int n_table = (2 * m->cfg.seq_max_size - 1) * kD;
+    if (cudaMalloc(&m->embed_img_dev, 2 * 16384) != cudaSuccess) return PST_ERR_CUDA;
+    if (cudaMalloc(&m->table16_dev, (size_t)n_table * sizeof(uint16_t)) != cudaSuccess) return PST_ERR_CUDA;
+    build_embed_images_kernel<<<32, 256>>>(m->w.edge_feat_w, m->embed_img_dev);
+    to_half_kernel<<<(n_table + 255) / 256, 256>>>(m->w.edge_pe_table, reinterpret_cast<__half*>(m->table16_dev), n_table);
+    if (cudaFuncSetAttribute(edge_embed_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemTotal) != cudaSuccess ||
+        cudaFuncSetAttribute(edge_embed_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemTotal) != cudaSuccess)
+      return PST_ERR_CUDA;
+  }
   if (cudaGetLastError() != cudaSuccess) return PST_ERR_CUDA;
   cudaError_t e1 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   cudaError_t e2 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
@@ -741,5 +926,28 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   }
   if (half) edge_mlp_tc_kernel<__half, 1><<<grid, kThreads, kSmemTotal, st>>>(p);
   else edge_mlp_tc_kernel<__nv_bfloat16, 1><<<grid, kThreads, kSmemTotal, st>>>(p);
+  return 1;
+}
+
+int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* feat, const int32_t* senders,
+                             const int32_t* row_base, int R, uint16_t* e) {
+  EmbedParams p{};
+  p.w_img = m->embed_img_dev;
+  p.table = reinterpret_cast<const __half*>(m->table16_dev);
+  p.feat = feat;
+  p.senders = senders;
+  p.row_base = row_base;
+  p.e = e;
+  p.K = m->cfg.num_neighbor;
+  p.E = R * p.K;
+  p.num_tiles = (p.E + kTileM - 1) / kTileM;
+  p.seq_max = m->cfg.seq_max_size;
+  p.idesc = (1u << 4) | ((uint32_t)(kD >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);  // fp16 x fp16 -> fp32
+  if (p.num_tiles == 0) return 0;
+  int grid = m->num_sms;
+  const int need = (p.num_tiles + kGroups - 1) / kGroups;
+  if (grid > need) grid = need;
+  if (m->cfg.precision == PST_PREC_FP16) edge_embed_tc_kernel<__half><<<grid, kThreads, kEmbSmemTotal, st>>>(p);
+  else edge_embed_tc_kernel<__nv_bfloat16><<<grid, kThreads, kEmbSmemTotal, st>>>(p);
   return 1;
 }

@@ -401,13 +401,10 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     if (cfg.precision == PST_PREC_FP32)
       edge_embed_kernel<float><<<grid, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
                                                         cfg.seq_max_size, R, ws.e);
-    else if (cfg.precision == PST_PREC_FP16)
-      edge_embed_kernel<__half><<<grid, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
-                                                         cfg.seq_max_size, R, reinterpret_cast<__half*>(ws.e));
-    else
-      edge_embed_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table,
-                                                                m->w.edge_feat_w, K, cfg.seq_max_size, R,
-                                                                reinterpret_cast<__nv_bfloat16*>(ws.e));
+    else {
+      int n = pst_launch_edge_embed_tc(m, st, edge_feat, senders, row_base, R, reinterpret_cast<uint16_t*>(ws.e));
+      if (n < 0) return n;
+    }
     ++L.count;
   }
   for (int l = 0; l < cfg.gnn_layers; ++l) {

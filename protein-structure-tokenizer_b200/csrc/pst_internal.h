@@ -63,6 +63,8 @@ struct pst_model {
   PstWeights w;
   uint16_t* tc_dev;
   PstTcWeights tc;
+  uint16_t* embed_img_dev;   // hi/lo fp16 images of W_edge[128:155] (tensor-core input embedding)
+  uint16_t* table16_dev;     // fp16 copy of edge_pe_table
   PstLinearRegistry* linear_tc;  // split-fp16 operand images of the node-level weights (tensor-core modes)
   // FSQ constants (model/quantize.py:175-181), fp32
   float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
@@ -147,6 +149,8 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
                            const uint16_t* ps, const uint16_t* pr, const int32_t* senders,
                            const int32_t* row_base, float* partial, int R, float* agg_out);
 size_t pst_tc_partial_floats(int R, int K);
+int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* feat, const int32_t* senders,
+                             const int32_t* row_base, int R, uint16_t* e);
 
 // node-level linears on tensor cores (linear_tc.cu)
 int pst_prepare_linear_tc(pst_model* m);
