@@ -121,10 +121,34 @@ def init_params(cfg: TokenizerConfig, seed: int = 0, flavour: str = "ref") -> Di
     return p
 
 
+def canonical_name(name: str) -> str:
+    """Haiku module path -> the name used here: the "~" / "~method" components Haiku inserts for
+    modules built in __init__ / in a method other than __call__ are dropped, e.g.
+    `vq3_d/~/structure_encoder/~/graph_neural_network/~/mpnn_layer/node_mlp_0/~/linear_0/w` ->
+    `vq3_d/structure_encoder/graph_neural_network/mpnn_layer/node_mlp_0/linear_0/w`
+    (the full list of the reference's names is pinned in tests/golden/model_ref_param_names.json)."""
+    return "/".join(p for p in name.replace("//", "/").split("/") if p and not p.startswith("~"))
+
+
+def from_haiku(tree) -> Dict[str, np.ndarray]:
+    """A Haiku parameter tree ({module_name: {param: array}}, or a flat {"module/param": array} dict,
+    e.g. a released checkpoint after scripts/inference_runner.py:236-248) -> flat dict keyed by
+    canonical names.  Parameters of the decoder side are carried along untouched; `pack_weights`
+    only looks up the encode-path names, by suffix."""
+    flat: Dict[str, np.ndarray] = {}
+    for k, v in tree.items():
+        if isinstance(v, dict):
+            for n, a in v.items():
+                flat[canonical_name(f"{k}/{n}")] = np.asarray(a)
+        else:
+            flat[canonical_name(k)] = np.asarray(v)
+    return flat
+
+
 def _find(params: Dict[str, np.ndarray], suffix: str) -> np.ndarray:
     if suffix in params:
         return np.asarray(params[suffix], np.float32)
-    hits = [k for k in params if k.endswith("/" + suffix)]
+    hits = [k for k in params if canonical_name(k).endswith("/" + suffix)]
     if len(hits) != 1:
         raise KeyError(f"parameter '{suffix}': {len(hits)} matches")
     return np.asarray(params[hits[0]], np.float32)
