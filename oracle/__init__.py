@@ -17,9 +17,15 @@ Parity pinning status
   bundled CASP14 structures; outputs of the reference functions are committed
   as golden vectors under ``tests/golden/`` (generator:
   ``tests/golden/make_golden.py``).
-* Model forward (Haiku/JAX): PARITY UNPINNED.  The reference ships no tests
-  or golden vectors for the model, and jax/haiku are not installable here, so
-  the fp32 forward in ``oracle/model.py`` follows the reference source
-  line-by-line (citations in each function) but has never been compared with
-  a real JAX run.  Golden vectors for the model are outputs of this oracle.
+* Model forward (Haiku/JAX): PINNED AGAINST THE REFERENCE'S SOURCE, not against
+  XLA.  ``tests/golden/make_golden_model.py`` executes the reference's own
+  ``Vq3D.encode_and_quantize`` (files under /root/reference, unmodified) over
+  NumPy stand-ins for jax / haiku (``tests/golden/refshim.py``: JAX's x64-off
+  dtype rules, Haiku 0.0.10 module naming, layer_stack's creator/getter hooks)
+  for four released configs on CASP14 structures and commits tokens, bounded
+  latents, pre-projection embeddings and the Haiku parameter names under
+  ``tests/golden/model_ref_*``.  ``oracle/model.py`` reproduces them to <= 4e-6
+  with identical tokens (``tests/test_golden_model.py``).  What remains
+  unpinned is XLA:CPU's fp32 arithmetic itself (summation order, last-ulp
+  tanh/exp/sin/cos/pow): jax and haiku are not installable in this image.
 """

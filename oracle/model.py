@@ -1,8 +1,15 @@
 """Oracle (TEST INFRASTRUCTURE): torch-CPU fp32 restatement of the reference's
 device forward `Vq3D.encode_and_quantize` (tokenize path only).  See
-``oracle/__init__.py`` for who may import this.  PARITY UNPINNED against a real
-JAX/Haiku run (neither is installable in this image); every function cites the
+``oracle/__init__.py`` for who may import this.  Every function cites the
 reference lines it follows (paths relative to structure_tokenizer/).
+
+PINNED against the reference's own model source: tests/golden/make_golden_model.py
+executes `Vq3D.encode_and_quantize` (the reference's files, unmodified) over NumPy
+stand-ins for jax / haiku (tests/golden/refshim.py) on CASP14 structures for four
+released configs; this restatement reproduces those outputs to <= 4e-6 on the bounded
+latents with identical tokens (tests/test_golden_model.py).  NOT pinned: XLA's own
+fp32 arithmetic (a real JAX run is impossible here: neither jax nor haiku is
+installable) - summation order and the last ulp of tanh/exp/sin/cos/pow.
 
   positional encodings   model/positional_encoding_layer.py:49-150
   input embeddings       model/structure_encoder.py:55-123
