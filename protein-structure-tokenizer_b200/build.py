@@ -18,6 +18,7 @@ SOURCES = {
     "encoder_fp32.cu": [],
     "edge_mlp_tc.cu": (["-DPST_EDGE_PROFILE"] if os.environ.get("PST_EDGE_PROFILE") else []),
     "linear_tc.cu": [],
+    "node_chain_tc.cu": [],
     "quantize.cu": [],
     "api.cu": [],
 }

@@ -167,6 +167,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   m->launch_count = 0;
   m->tc_dev = nullptr;
   m->linear_tc = nullptr;
+  m->node_chain = nullptr;
   m->embed_img_dev = nullptr;
   m->table16_dev = nullptr;
   m->prof_on = false;
@@ -200,6 +201,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   if (cfg->precision != PST_PREC_FP32) {
     int rc = pst_prepare_tc_weights(m);
     if (rc == PST_OK) rc = pst_prepare_linear_tc(m);
+    if (rc == PST_OK) rc = pst_prepare_node_chain(m);
     if (rc != PST_OK) { pst_model_destroy(m); return rc; }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) { pst_model_destroy(m); return PST_ERR_CUDA; }
@@ -212,6 +214,7 @@ void pst_model_destroy(pst_model* m) {
   cudaSetDevice(m->device);
   if (m->blob_dev) cudaFree(m->blob_dev);
   if (m->tc_dev) cudaFree(m->tc_dev);
+  pst_destroy_node_chain(m);
   pst_destroy_linear_tc(m);
   if (m->embed_img_dev) cudaFree(m->embed_img_dev);
   if (m->table16_dev) cudaFree(m->table16_dev);

@@ -407,22 +407,47 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     }
     ++L.count;
   }
-  for (int l = 0; l < cfg.gnn_layers; ++l) {
-    const PstLayerW& w = m->w.layer[l];
-    // message MLP, first linear factorised: [h_s|h_r|e].W1 = (h.W1[0:128])[s] + (h.W1[128:256])[r] + e.W1[256:384]
-    // (tensor-core modes keep the two gathered addend tables in fp16: measured harmless for the tokens)
-    L.gemm(ws.h, w.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr), tc);
-    L.gemm(ws.h, w.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.msg_b1), tc);
-    PstSpan* span = new PstSpan(m, st, 1);
-    if (tc) {
-      // tensor-core path returns the per-receiver mean of the 2nd hidden layer; the 3rd linear
-      // commutes with that mean (no activation follows it): agg = mean_K(T2) . W3 + b3
-      int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), reinterpret_cast<const uint16_t*>(ws.ps),
-                                     reinterpret_cast<const uint16_t*>(ws.pr), senders, row_base, ws.partial, R, ws.tmp);
+  if (tc) {
+    // Tensor-core modes: edge-level kernels (edge_mlp_tc.cu) alternate with ONE fused node-level kernel per layer
+    // (node_chain_tc.cu).  The gathered addend tables (fp16) ping-pong: (ps, pr) feed the message MLPs,
+    // (ps2, pr2) the edge-update MLPs; the node kernel of layer l writes both pairs for what follows it.
+    uint16_t* ps = reinterpret_cast<uint16_t*>(ws.ps);
+    uint16_t* pr = reinterpret_cast<uint16_t*>(ws.pr);
+    uint16_t* ps2 = reinterpret_cast<uint16_t*>(ws.agg);
+    uint16_t* pr2 = reinterpret_cast<uint16_t*>(ws.u);
+    const PstLayerW& w0 = m->w.layer[0];
+    L.gemm(ws.h, w0.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr), 1);
+    L.gemm(ws.h, w0.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w0.msg_b1), 1);
+    for (int l = 0; l < cfg.gnn_layers; ++l) {
+      {
+        // message MLP: returns the per-receiver mean of the 2nd hidden layer; the 3rd linear commutes with
+        // that mean (no activation follows it) and is applied by the node kernel
+        PstSpan span(m, st, 1);
+        int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, senders, row_base, ws.partial, R, ws.tmp);
+        if (n < 0) return n;
+        L.count += n;
+      }
+      {
+        PstSpan span(m, st, 3);
+        int n = pst_launch_node_update(m, st, l, ws.tmp, ws.h, R, ps2, pr2, ps, pr);
+        if (n < 0) return n;
+        L.count += n;
+      }
+      if (l == cfg.gnn_layers - 1) break;  // the last layer's edge update is never read (model.py:385)
+      PstSpan span(m, st, 2);
+      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), ps2, pr2, senders, row_base, ws.partial, R, nullptr);
       if (n < 0) return n;
       L.count += n;
-      L.gemm(ws.tmp, w.msg_w3, ws.agg, R, D, D, Launcher::epi(w.msg_b3));
-    } else {
+    }
+  } else
+  for (int l = 0; l < cfg.gnn_layers; ++l) {
+    const PstLayerW& w = m->w.layer[l];
+    // fp32 mode (all CUDA cores): first linear factorised,
+    // [h_s|h_r|e].W1 = (h.W1[0:128])[s] + (h.W1[128:256])[r] + e.W1[256:384]
+    L.gemm(ws.h, w.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr));
+    L.gemm(ws.h, w.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.msg_b1));
+    {
+      PstSpan span(m, st, 1);
       GemmEpi g = Launcher::epi(nullptr, 1);
       g.gather_s = ws.ps; g.gather_r = ws.pr; g.senders = senders; g.row_base = row_base; g.knn = K;
       L.gemm(ws.e, w.msg_w1 + 2 * D * D, ws.t1, E, D, D, g);
@@ -431,22 +456,16 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       segment_mean_kernel<<<(R + 7) / 8, 256, 0, st>>>(ws.t1, K, ws.agg, R);
       ++L.count;
     }
-    delete span;
     L.add_ln(ws.h, ws.agg, w.ln0_s, w.ln0_o, ws.h, R);
     // feed-forward 128 -> 512 -> 128
     L.gemm(ws.h, w.ffn_w1, ws.u, R, PST_FFN, D, Launcher::epi(w.ffn_b1, 1));
     L.gemm(ws.u, w.ffn_w2, ws.tmp, R, D, PST_FFN, Launcher::epi(w.ffn_b2));
     L.add_ln(ws.h, ws.tmp, w.ln1_s, w.ln1_o, ws.h, R);
     if (l == cfg.gnn_layers - 1) break;  // the last layer's edge update is never read (model.py:385)
-    L.gemm(ws.h, w.edge_w1, ws.ps, R, D, D, Launcher::epi(nullptr), tc);
-    L.gemm(ws.h, w.edge_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.edge_b1), tc);
-    span = new PstSpan(m, st, 2);
-    if (tc) {
-      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), reinterpret_cast<const uint16_t*>(ws.ps),
-                                     reinterpret_cast<const uint16_t*>(ws.pr), senders, row_base, ws.partial, R, nullptr);
-      if (n < 0) return n;
-      L.count += n;
-    } else {
+    L.gemm(ws.h, w.edge_w1, ws.ps, R, D, D, Launcher::epi(nullptr));
+    L.gemm(ws.h, w.edge_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w.edge_b1));
+    {
+      PstSpan span(m, st, 2);
       GemmEpi g = Launcher::epi(nullptr, 1);
       g.gather_s = ws.ps; g.gather_r = ws.pr; g.senders = senders; g.row_base = row_base; g.knn = K;
       L.gemm(ws.e, w.edge_w1 + 2 * D * D, ws.t1, E, D, D, g);
@@ -454,7 +473,6 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       L.gemm(ws.t2, w.edge_w3, ws.t1, E, D, D, Launcher::epi(w.edge_b3));
       L.add_ln(ws.e, ws.t1, w.ln2_s, w.ln2_o, ws.e, E);
     }
-    delete span;
   }
 
   // ---- resampler (CrossAttentionScaler, 3 blocks) -------------------------------------------

@@ -269,6 +269,13 @@ int pst_prepare_linear_tc(pst_model* m) {
   return PST_OK;
 }
 
+const uint8_t* pst_linear_tc_image(const pst_model* m, const float* W, int K, int N) {
+  if (!m->linear_tc) return nullptr;
+  for (const auto& x : m->linear_tc->entries)
+    if (x.w == W && x.K == K && x.N == N) return reinterpret_cast<const uint8_t*>(x.img);
+  return nullptr;
+}
+
 void pst_destroy_linear_tc(pst_model* m) {
   if (!m->linear_tc) return;
   for (auto& e : m->linear_tc->entries) cudaFree(e.img);

@@ -1,0 +1,522 @@
+// Fused node-level chains on the tensor cores (tcgen05 + TMEM), tensor-core precision modes only.
+//
+// Everything the encoder does once per residue between two edge-level kernels is row-local (every op maps
+// row r of [R,128] to row r), so a whole chain runs in ONE persistent kernel per 128-row tile instead of a
+// launch per linear / LayerNorm with the [R,128] intermediates bouncing through HBM:
+//
+//  node_update_kernel  (reference: structure_tokenizer/model/gnn_layers.py:364-419, per MPNN layer)
+//      agg = tbar.W3 + b3                       (tbar = per-receiver mean of the message MLP's 2nd hidden layer)
+//      h   = MaskedLayerNorm0(h + agg)          (:379-382)
+//      h   = MaskedLayerNorm1(h + MLP_{128->512->128}(h))   (:385-399; the 512-wide hidden is chunked 4 x 128
+//                                                 and never leaves the SM)
+//      out_o = fp16(h.Wout_o + b_o)             the four gathered addend tables the next two edge-level
+//                                                 kernels need: edge MLP of this layer (:402-419) and message
+//                                                 MLP of the next (:344-361), first linear factorised
+//
+//  resampler_df1_kernel  (reference: model/modules.py:438-636, model/model.py:148-174,414-418,
+//                         model/quantize.py:175-209; downsampling_ratio == 1 only)
+//      the 3 CrossAttentionScaler blocks + spherical norm + down_proj + FSQ.  With df = 1 token t attends
+//      residue t alone (softmax over one logit == 1), so the block is row-local: res += (v * sigmoid(gate)).Wo + bo,
+//      res += Transition(res), orig += Transition(orig).
+//
+// Numerics: as linear_tc.cu - every fp32 operand is split x = hi + lo (two fp16) and each product is evaluated as
+// hi.hi + hi.lo + lo.hi with fp32 accumulation in TMEM; LayerNorm / GELU / sigmoid / FSQ in fp32 registers.
+//
+// Structure: 1 CTA / SM, 4 epilogue warps (thread = row: the TMEM 32x32b layout) + 1 producer warp.
+// Shared memory: two activation image sets (hi/lo, 2 K-blocks: 64 KB each) + a 3-slot ring of 32 KB weight
+// half-units (hi+lo images of one 64-row K block of a 128-column weight slice) streamed from L2 by
+// cp.async.bulk on full/empty mbarriers; tcgen05.commit releases a slot.  The per-row state that must survive a
+// GEMM (h after LN0, res / orig of the resampler) lives in spare TMEM columns, not in registers.
+#include <cuda_fp16.h>
+
+#include <vector>
+
+#include "pst_internal.h"
+
+namespace {
+
+constexpr int D = PST_D;
+constexpr uint32_t kImgBlk = 16384;        // [128 x 64] fp16 K-major SWIZZLE_128B image
+constexpr uint32_t kSlotBytes = 2 * kImgBlk;  // weight half-unit: hi image, lo image of one K block
+constexpr uint32_t kSetBytes = 2 * kSlotBytes;  // activation image set: [kb][hi, lo]
+constexpr int kSlots = 3;
+constexpr uint32_t kOffX = 0, kOffU = kSetBytes, kOffW = 2 * kSetBytes;
+constexpr uint32_t kOffBar = kOffW + kSlots * kSlotBytes;
+constexpr uint32_t kSmemBytes = kOffBar + 128;
+constexpr int kEpiThreads = 128, kThreads = 160;
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+
+__host__ __device__ __forceinline__ uint32_t swz64(uint32_t row, uint32_t k) {
+  return row * 128 + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(c)); }
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// tanh to ~1e-7 absolute: 1 - 2 / (exp(2u) + 1)   (exp overflow -> +inf -> 1, underflow -> 0 -> -1)
+__device__ __forceinline__ float tanh_fast(float u) { return 1.0f - __fdividef(2.0f, __expf(2.0f * u) + 1.0f); }
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanh_fast(u));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// 32 consecutive K-elements [k0, k0+32) of `row`, fp32 -> hi / lo fp16 images of an activation image set
+__device__ __forceinline__ void split_store(uint8_t* set, int row, int k0, const float (&v)[32]) {
+  uint8_t* base = set + (k0 >> 6) * kSlotBytes;
+  const int kk0 = k0 & 63;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[c * 8 + 2 * j], b = v[c * 8 + 2 * j + 1];
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 f = __half22float2(h);
+      const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const uint32_t off = swz64(row, kk0 + c * 8);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + kImgBlk + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// state of the weight ring as seen by the MMA-issuing thread / the producer thread
+struct Ring {
+  uint32_t full, empty, wbase;  // smem addresses: full[kSlots], empty[kSlots] mbarriers, slot 0
+  uint32_t n;                   // half-units consumed / produced so far
+};
+
+// one 128 x 128 x 128 product (split precision): A image set x the next two half-units of the ring -> acc
+__device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tmem_acc, uint32_t accumulate, uint32_t idesc,
+                                           uint32_t done_bar) {
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {
+    const uint32_t slot = r.n % kSlots, par = (r.n / kSlots) & 1;
+    mbar_wait(r.full + slot * 8, par);
+    tc_after();
+    const uint32_t a_hi = a_set + kb * kSlotBytes, a_lo = a_hi + kImgBlk;
+    const uint32_t w_hi = r.wbase + slot * kSlotBytes, w_lo = w_hi + kImgBlk;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t o = j * 32;
+      umma(tmem_acc, make_desc(a_hi + o), make_desc(w_hi + o), idesc, (kb | j) ? 1u : accumulate);
+      umma(tmem_acc, make_desc(a_hi + o), make_desc(w_lo + o), idesc, 1u);
+      umma(tmem_acc, make_desc(a_lo + o), make_desc(w_hi + o), idesc, 1u);
+    }
+    umma_commit(r.empty + slot * 8);
+    ++r.n;
+  }
+  umma_commit(done_bar);
+}
+
+__device__ __forceinline__ void producer_loop(Ring r, const uint8_t* const* sched, int n_sched, int my_tiles) {
+  for (int t = 0; t < my_tiles; ++t)
+    for (int i = 0; i < n_sched; ++i) {
+      const uint32_t slot = r.n % kSlots;
+      if (r.n >= kSlots) mbar_wait(r.empty + slot * 8, ((r.n / kSlots) - 1) & 1);
+      mbar_expect_tx(r.full + slot * 8, kSlotBytes);
+      bulk_g2s(r.wbase + slot * kSlotBytes, sched[i], kSlotBytes, r.full + slot * 8);
+      ++r.n;
+    }
+}
+
+// LayerNorm of a 128-float row held as 4 x 32 registers: biased variance of the centred row, eps 1e-5
+// (gnn_layers.py:108-120,162-164; hk.LayerNorm is the same formula)
+__device__ __forceinline__ void row_stats(const float (&x)[4][32], float& mean, float& inv) {
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += x[q][j];
+  mean = s * (1.0f / D);
+  float v = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = x[q][j] - mean;
+      v = fmaf(d, d, v);
+    }
+  inv = rsqrtf(v * (1.0f / D) + 1e-5f);
+}
+
+struct Setup {
+  uint8_t* smem;
+  uint32_t tmem_base;
+  uint32_t bar_done[2];
+  Ring ring;
+};
+
+__device__ __forceinline__ Setup chain_setup(uint8_t* smem, int tid, int warp) {
+  Setup s;
+  s.smem = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);  // full[3], empty[3], done[2], tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_before();
+  __syncthreads();
+  tc_after();
+  s.tmem_base = *tmem_slot;
+  s.ring.full = smem_u32(&bars[0]);
+  s.ring.empty = smem_u32(&bars[3]);
+  s.ring.wbase = smem_u32(smem + kOffW);
+  s.ring.n = 0;
+  s.bar_done[0] = smem_u32(&bars[6]);
+  s.bar_done[1] = smem_u32(&bars[7]);
+  return s;
+}
+
+__device__ __forceinline__ void chain_teardown(const Setup& s, int warp) {
+  tc_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "r"(512u) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct NodeUpdateParams {
+  const float* tbar;  // [R,128]
+  float* h;           // [R,128] in / out
+  const float *b3, *ln0_s, *ln0_o, *ffn_b1, *ffn_b2, *ln1_s, *ln1_o;
+  const uint8_t* const* sched;
+  int n_sched, n_out;
+  const float* out_bias[4];
+  __half* out[4];
+  int R, num_tiles;
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdateParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  Setup S = chain_setup(smem, tid, warp);
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (warp == 4) {
+    if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
+    __syncwarp();
+    chain_teardown(S, warp);
+    return;
+  }
+  uint8_t* X = smem + kOffX;
+  uint8_t* U = smem + kOffU;
+  const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t t_acc0 = S.tmem_base + 0, t_h1 = S.tmem_base + 128, t_acc1 = S.tmem_base + 256, t_acc2 = S.tmem_base + 384;
+  Ring ring = S.ring;
+  uint32_t n_issued = 0, n_waited = 0;
+  // every thread counts the groups; thread 0 issues them.  Group i commits to done[i & 1].
+  auto issue = [&](uint32_t a_set, uint32_t acc, uint32_t accumulate) {
+    if (tid == 0) issue_unit(ring, a_set, acc, accumulate, p.idesc, S.bar_done[n_issued & 1]);
+    ++n_issued;
+  };
+  auto wait_next = [&]() {
+    mbar_wait(S.bar_done[n_waited & 1], (n_waited >> 1) & 1);
+    ++n_waited;
+    tc_after();
+  };
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int row = tile * 128 + tid;
+    const bool valid = row < p.R;
+    // ---- 1. tbar row -> X images ----------------------------------------------------------------------
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.tbar + (size_t)row * D);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = valid ? __ldg(src + q * 8 + j) : make_float4(0, 0, 0, 0);
+          v[j * 4] = t.x; v[j * 4 + 1] = t.y; v[j * 4 + 2] = t.z; v[j * 4 + 3] = t.w;
+        }
+        split_store(X, tid, q * 32, v);
+      }
+    }
+    fence_async();
+    tc_before();
+    epi_sync();
+    issue(X_addr, t_acc0, 0u);
+    wait_next();
+    // ---- 2. h1 = LN0(h + tbar.W3 + b3) -> TMEM (fp32) + X images ---------------------------------------------
+    {
+      float x[4][32];
+      const float4* hsrc = reinterpret_cast<const float4*>(p.h + (size_t)row * D);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        tmem_ld32(t_acc0 + lane_off + q * 32, x[q]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 hh = valid ? hsrc[q * 8 + j] : make_float4(0, 0, 0, 0);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.b3) + q * 8 + j);
+          x[q][j * 4] += hh.x + b.x; x[q][j * 4 + 1] += hh.y + b.y; x[q][j * 4 + 2] += hh.z + b.z; x[q][j * 4 + 3] += hh.w + b.w;
+        }
+      }
+      float mean, inv;
+      row_stats(x, mean, inv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          x[q][j] = (__ldg(p.ln0_s + q * 32 + j) * inv) * (x[q][j] - mean) + __ldg(p.ln0_o + q * 32 + j);
+        tmem_st32(t_h1 + lane_off + q * 32, x[q]);
+        split_store(X, tid, q * 32, x[q]);
+      }
+    }
+    fence_async();
+    tc_before();
+    epi_sync();
+    // ---- 3. FFN 128 -> 512 -> 128, hidden chunked 4 x 128 -----------------------------------------------
+    issue(X_addr, t_acc1, 0u);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      wait_next();  // h1 . F1[:, c]  (and, in order, everything issued before it: U is free)
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float v[32];
+        tmem_ld32(t_acc1 + lane_off + q * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j] + __ldg(p.ffn_b1 + c * 128 + q * 32 + j));
+        split_store(U, tid, q * 32, v);
+      }
+      fence_async();
+      tc_before();
+      epi_sync();
+      issue(U_addr, t_acc2, c > 0 ? 1u : 0u);
+      if (c < 3) issue(X_addr, t_acc1, 0u);
+      wait_next();  // u_c . F2[c, :] accumulated
+    }
+    // ---- 4. h2 = LN1(h1 + ffn + b2) -> global h, X images ----------------------------------------------
+    {
+      float x[4][32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float h1[32];
+        tmem_ld32(t_acc2 + lane_off + q * 32, x[q]);
+        tmem_ld32(t_h1 + lane_off + q * 32, h1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[q][j] += h1[j] + __ldg(p.ffn_b2 + q * 32 + j);
+      }
+      float mean, inv;
+      row_stats(x, mean, inv);
+      float4* hdst = reinterpret_cast<float4*>(p.h + (size_t)row * D);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          x[q][j] = (__ldg(p.ln1_s + q * 32 + j) * inv) * (x[q][j] - mean) + __ldg(p.ln1_o + q * 32 + j);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hdst[q * 8 + j] = make_float4(x[q][j * 4], x[q][j * 4 + 1], x[q][j * 4 + 2], x[q][j * 4 + 3]);
+        }
+        if (p.n_out > 0) split_store(X, tid, q * 32, x[q]);
+      }
+    }
+    if (p.n_out > 0) {
+      fence_async();
+      tc_before();
+      epi_sync();
+      // ---- 5. the gathered addend tables of the next edge-level kernels: fp16(h2 . Wout_o + b_o) ---------------
+      issue(X_addr, t_acc0, 0u);
+#pragma unroll 1
+      for (int o = 0; o < p.n_out; ++o) {
+        if (o + 1 < p.n_out) issue(X_addr, ((o + 1) & 1) ? t_acc1 : t_acc0, 0u);
+        wait_next();
+        const uint32_t acc = (o & 1) ? t_acc1 : t_acc0;
+        const float* bias = p.out_bias[o];
+        uint4* dst = reinterpret_cast<uint4*>(p.out[o] + (size_t)row * D);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          float v[32];
+          tmem_ld32(acc + lane_off + q * 32, v);
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + q * 32 + j);
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __half2 a = __floats2half2_rn(v[j * 8], v[j * 8 + 1]), b = __floats2half2_rn(v[j * 8 + 2], v[j * 8 + 3]);
+              const __half2 c2 = __floats2half2_rn(v[j * 8 + 4], v[j * 8 + 5]), d = __floats2half2_rn(v[j * 8 + 6], v[j * 8 + 7]);
+              dst[q * 4 + j] = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                                          *reinterpret_cast<const uint32_t*>(&c2), *reinterpret_cast<const uint32_t*>(&d));
+            }
+          }
+        }
+        tc_before();
+        epi_sync();  // the accumulator just read is overwritten by the group issued at the top of the next pass
+      }
+    } else {
+      tc_before();
+      epi_sync();
+    }
+  }
+  chain_teardown(S, warp);
+}
+
+struct Entry {
+  const float* w;
+  int K, N;
+  const uint8_t* img;
+};
+
+}  // namespace
+
+// linear_tc.cu: image of a registered weight ([K/64][N/128][hi,lo][16 KB]) or null
+const uint8_t* pst_linear_tc_image(const pst_model* m, const float* W, int K, int N);
+
+struct PstNodeChain {
+  const uint8_t** sched_dev = nullptr;  // all schedules, concatenated
+  int layer_off[PST_MAX_LAYERS], layer_n[PST_MAX_LAYERS], layer_nout[PST_MAX_LAYERS];
+};
+
+int pst_prepare_node_chain(pst_model* m) {
+  m->node_chain = new PstNodeChain();
+  PstNodeChain& C = *m->node_chain;
+  std::vector<const uint8_t*> all;
+  auto half_unit = [&](const float* W, int K, int N, int kb, int nc) -> const uint8_t* {
+    const uint8_t* img = pst_linear_tc_image(m, W, K, N);
+    if (!img) return nullptr;
+    return img + ((size_t)(kb * (N / 128) + nc) * 2) * kImgBlk;
+  };
+  bool ok = true;
+  auto push_unit = [&](const float* W, int K, int N, int kchunk, int nc) {  // 128(K) x 128(N) unit = 2 half-units
+    for (int kb = 0; kb < 2; ++kb) {
+      const uint8_t* p = half_unit(W, K, N, kchunk * 2 + kb, nc);
+      ok = ok && p;
+      all.push_back(p);
+    }
+  };
+  const int L = m->cfg.gnn_layers;
+  for (int l = 0; l < L; ++l) {
+    const PstLayerW& w = m->w.layer[l];
+    C.layer_off[l] = (int)all.size();
+    push_unit(w.msg_w3, D, D, 0, 0);
+    for (int c = 0; c < 4; ++c) {
+      push_unit(w.ffn_w1, D, PST_FFN, 0, c);
+      push_unit(w.ffn_w2, PST_FFN, D, c, 0);
+    }
+    C.layer_nout[l] = 0;
+    if (l < L - 1) {
+      const PstLayerW& nx = m->w.layer[l + 1];
+      push_unit(w.edge_w1, D, D, 0, 0);
+      push_unit(w.edge_w1 + D * D, D, D, 0, 0);
+      push_unit(nx.msg_w1, D, D, 0, 0);
+      push_unit(nx.msg_w1 + D * D, D, D, 0, 0);
+      C.layer_nout[l] = 4;
+    }
+    C.layer_n[l] = (int)all.size() - C.layer_off[l];
+  }
+  if (!ok) return PST_ERR_BAD_ARGUMENT;
+  if (cudaMalloc(&C.sched_dev, all.size() * sizeof(void*)) != cudaSuccess) return PST_ERR_CUDA;
+  if (cudaMemcpy(C.sched_dev, all.data(), all.size() * sizeof(void*), cudaMemcpyHostToDevice) != cudaSuccess) return PST_ERR_CUDA;
+  if (cudaFuncSetAttribute(node_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+    return PST_ERR_CUDA;
+  return PST_OK;
+}
+
+void pst_destroy_node_chain(pst_model* m) {
+  if (!m->node_chain) return;
+  if (m->node_chain->sched_dev) cudaFree(m->node_chain->sched_dev);
+  delete m->node_chain;
+  m->node_chain = nullptr;
+}
+
+// h <- node update of MPNN layer `layer` (see the header); for layer < last also the four fp16 addend tables:
+// out_edge_s/r for this layer's edge MLP, out_msg_s/r for the next layer's message MLP.
+int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* tbar, float* h, int R,
+                           uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r) {
+  if (!m->node_chain || R <= 0) return 0;
+  const PstNodeChain& C = *m->node_chain;
+  const PstLayerW& w = m->w.layer[layer];
+  NodeUpdateParams p{};
+  p.tbar = tbar; p.h = h;
+  p.b3 = w.msg_b3; p.ln0_s = w.ln0_s; p.ln0_o = w.ln0_o; p.ffn_b1 = w.ffn_b1; p.ffn_b2 = w.ffn_b2; p.ln1_s = w.ln1_s; p.ln1_o = w.ln1_o;
+  p.sched = C.sched_dev + C.layer_off[layer];
+  p.n_sched = C.layer_n[layer];
+  p.n_out = C.layer_nout[layer];
+  if (p.n_out) {
+    const PstLayerW& nx = m->w.layer[layer + 1];
+    p.out[0] = reinterpret_cast<__half*>(out_edge_s); p.out_bias[0] = nullptr;
+    p.out[1] = reinterpret_cast<__half*>(out_edge_r); p.out_bias[1] = w.edge_b1;
+    p.out[2] = reinterpret_cast<__half*>(out_msg_s);  p.out_bias[2] = nullptr;
+    p.out[3] = reinterpret_cast<__half*>(out_msg_r);  p.out_bias[3] = nx.msg_b1;
+  }
+  p.R = R;
+  p.num_tiles = (R + 127) / 128;
+  p.idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  int grid = m->num_sms < p.num_tiles ? m->num_sms : p.num_tiles;
+  node_update_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
+  return 1;
+}

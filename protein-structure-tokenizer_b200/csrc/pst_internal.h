@@ -53,6 +53,7 @@ struct PstTcWeights {
 };
 
 struct PstLinearRegistry;
+struct PstNodeChain;
 
 struct pst_model {
   pst_config cfg;
@@ -66,6 +67,7 @@ struct pst_model {
   uint16_t* embed_img_dev;   // hi/lo fp16 images of W_edge[128:155] (tensor-core input embedding)
   uint16_t* table16_dev;     // fp16 copy of edge_pe_table
   PstLinearRegistry* linear_tc;  // split-fp16 operand images of the node-level weights (tensor-core modes)
+  PstNodeChain* node_chain;      // weight streaming schedules of the fused node-level kernels (node_chain_tc.cu)
   // FSQ constants (model/quantize.py:175-181), fp32
   float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
   int32_t basis[PST_C8], half_width[PST_C8];
@@ -157,6 +159,13 @@ int pst_prepare_linear_tc(pst_model* m);
 void pst_destroy_linear_tc(pst_model* m);
 int pst_launch_linear_tc(const pst_model* m, cudaStream_t st, const float* A, const float* W, float* C, int M, int N,
                          int K, const float* bias, const float* residual, float scale, int act, int out_half);
+
+// fused node-level chains (node_chain_tc.cu); prepare after pst_prepare_linear_tc
+const uint8_t* pst_linear_tc_image(const pst_model* m, const float* W, int K, int N);
+int pst_prepare_node_chain(pst_model* m);
+void pst_destroy_node_chain(pst_model* m);
+int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* tbar, float* h, int R,
+                           uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r);
 
 #define PST_CUDA_OK(expr)                                  \
   do {                                                     \
