@@ -476,6 +476,13 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   }
 
   // ---- resampler (CrossAttentionScaler, 3 blocks) -------------------------------------------
+  if (tc && cfg.downsampling_ratio == 1) {
+    // df = 1: token t attends residue t alone, the three blocks + head are row-local: one fused kernel
+    PstSpan span(m, st, 3);
+    int n = pst_launch_resampler_df1(m, st, ws.h, row_base, R, z_out);
+    if (n < 0) return n;
+    return L.count + n;
+  }
   token_embed_kernel<<<(T + 7) / 8, 256, 0, st>>>(m->w.token_table, token_offsets, B, ws.res, T);
   ++L.count;
   const float* orig = ws.h;

@@ -42,8 +42,8 @@ constexpr uint32_t kSetBytes = 2 * kSlotBytes;  // activation image set: [kb][hi
 constexpr int kSlots = 3;
 constexpr uint32_t kOffX = 0, kOffU = kSetBytes, kOffW = 2 * kSetBytes;
 constexpr uint32_t kOffBar = kOffW + kSlots * kSlotBytes;
-constexpr uint32_t kSmemBytes = kOffBar + 128;
-constexpr int kEpiThreads = 128, kThreads = 160;
+constexpr uint32_t kSmemBytes = kOffBar + 128 + 2 * 2 * 128 * 4;  // barriers + TMEM slot, row-statistics exchange
+constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 32;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 
 __host__ __device__ __forceinline__ uint32_t swz64(uint32_t row, uint32_t k) {
@@ -67,7 +67,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(mbar)
                : "memory");
 }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -186,24 +186,75 @@ __device__ __forceinline__ void producer_loop(Ring r, const uint8_t* const* sche
     }
 }
 
-// LayerNorm of a 128-float row held as 4 x 32 registers: biased variance of the centred row, eps 1e-5
-// (gnn_layers.py:108-120,162-164; hk.LayerNorm is the same formula)
-__device__ __forceinline__ void row_stats(const float (&x)[4][32], float& mean, float& inv) {
+// ---- epilogue thread layout ----------------------------------------------------------------------------------
+// 256 epilogue threads: row = tid & 127 (TMEM lane; the lane quarter a warp may touch is warp & 3), half = tid >> 7
+// selects the 64 columns [64*half, 64*half + 64) of the row (= K block `half` of an activation image set).  Two
+// warps per SM sub-partition hide each other's latencies; row statistics are exchanged through shared memory.
+struct Epi {
+  int tid, row, half;
+  uint32_t lane_off;  // TMEM lane field of this thread's warp
+  float* red;         // [2 stages][2 halves][128 rows]
+};
+
+// LayerNorm over the full 128-wide row (biased variance of the centred row, eps 1e-5: gnn_layers.py:108-120,162-164;
+// hk.LayerNorm is the same formula); x = this thread's 64 columns
+__device__ __forceinline__ void layer_norm_row(const Epi& e, float (&x)[2][32], const float* __restrict__ scale,
+                                               const float* __restrict__ offset) {
   float s = 0.f;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 2; ++q)
 #pragma unroll
     for (int j = 0; j < 32; ++j) s += x[q][j];
-  mean = s * (1.0f / D);
+  e.red[e.half * 128 + e.row] = s;
+  epi_sync();
+  const float mean = (e.red[e.row] + e.red[128 + e.row]) * (1.0f / D);
   float v = 0.f;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 2; ++q)
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float d = x[q][j] - mean;
       v = fmaf(d, d, v);
     }
-  inv = rsqrtf(v * (1.0f / D) + 1e-5f);
+  e.red[256 + e.half * 128 + e.row] = v;
+  epi_sync();
+  const float inv = rsqrtf((e.red[256 + e.row] + e.red[256 + 128 + e.row]) * (1.0f / D) + 1e-5f);
+  const float* sc = scale + e.half * 64;
+  const float* of = offset + e.half * 64;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[q][j] = (__ldg(sc + q * 32 + j) * inv) * (x[q][j] - mean) + __ldg(of + q * 32 + j);
+}
+
+__device__ __forceinline__ void tmem_ld_half(const Epi& e, uint32_t region, float (&x)[2][32]) {
+  tmem_ld32(region + e.lane_off + e.half * 64, x[0]);
+  tmem_ld32(region + e.lane_off + e.half * 64 + 32, x[1]);
+}
+__device__ __forceinline__ void tmem_st_half(const Epi& e, uint32_t region, const float (&x)[2][32]) {
+  tmem_st32(region + e.lane_off + e.half * 64, x[0]);
+  tmem_st32(region + e.lane_off + e.half * 64 + 32, x[1]);
+}
+__device__ __forceinline__ void split_store_half(const Epi& e, uint8_t* set, const float (&x)[2][32]) {
+  split_store(set, e.row, e.half * 64, x[0]);
+  split_store(set, e.row, e.half * 64 + 32, x[1]);
+}
+__device__ __forceinline__ void load_row_half(const Epi& e, const float* row_ptr, bool valid, float (&x)[2][32]) {
+  const float4* src = reinterpret_cast<const float4*>(row_ptr + e.half * 64);
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = valid ? src[q * 8 + j] : make_float4(0, 0, 0, 0);
+      x[q][j * 4] = t.x; x[q][j * 4 + 1] = t.y; x[q][j * 4 + 2] = t.z; x[q][j * 4 + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void add_bias_half(const Epi& e, float (&x)[2][32], const float* __restrict__ bias) {
+  const float* b = bias + e.half * 64;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[q][j] += __ldg(b + q * 32 + j);
 }
 
 struct Setup {
@@ -211,6 +262,7 @@ struct Setup {
   uint32_t tmem_base;
   uint32_t bar_done[2];
   Ring ring;
+  float* red;
 };
 
 __device__ __forceinline__ Setup chain_setup(uint8_t* smem, int tid, int warp) {
@@ -236,6 +288,7 @@ __device__ __forceinline__ Setup chain_setup(uint8_t* smem, int tid, int warp) {
   s.ring.n = 0;
   s.bar_done[0] = smem_u32(&bars[6]);
   s.bar_done[1] = smem_u32(&bars[7]);
+  s.red = reinterpret_cast<float*>(smem + kOffBar + 128);
   return s;
 }
 
@@ -243,6 +296,59 @@ __device__ __forceinline__ void chain_teardown(const Setup& s, int warp) {
   tc_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "r"(512u) : "memory");
+}
+
+// MMA groups: every epilogue thread counts them, thread 0 issues.  Group i commits to done[i & 1] and the threads
+// wait for the groups in issue order, so each barrier has at most one unobserved completion (at most two groups
+// are ever in flight).
+struct Groups {
+  Ring ring;
+  uint32_t bar_done[2];
+  uint32_t idesc;
+  uint32_t n_issued = 0, n_waited = 0;
+  int tid;
+  __device__ __forceinline__ void issue(uint32_t a_set, uint32_t acc, uint32_t accumulate) {
+    if (tid == 0) issue_unit(ring, a_set, acc, accumulate, idesc, bar_done[n_issued & 1]);
+    ++n_issued;
+  }
+  __device__ __forceinline__ void wait_next() {
+    mbar_wait(bar_done[n_waited & 1], (n_waited >> 1) & 1);
+    ++n_waited;
+    tc_after();
+  }
+};
+// images written by the epilogue threads become visible to the tensor core; accumulators read by them may be reused
+__device__ __forceinline__ void publish() {
+  fence_async();
+  tc_before();
+  epi_sync();
+}
+
+// y = act(X . W1[:, c] + b1[c]) . W2[c, :] accumulated over `chunks` 128-wide chunks of the hidden layer.
+// X: image set of the input (already published); U: scratch image set; result in acc_out (waited for on return).
+template <int ACT>  // 1 gelu(tanh), 2 relu
+__device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_addr, uint8_t* U, uint32_t U_addr,
+                                            uint32_t acc_hidden, uint32_t acc_out, int chunks, const float* __restrict__ b1) {
+  G.issue(X_addr, acc_hidden, 0u);
+#pragma unroll 1
+  for (int c = 0; c < chunks; ++c) {
+    G.wait_next();  // X . W1[:, c]   (groups complete in order: U is free as well)
+    float v[2][32];
+    tmem_ld_half(e, acc_hidden, v);
+    const float* b = b1 + c * 128 + e.half * 64;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float t = v[q][j] + __ldg(b + q * 32 + j);
+        v[q][j] = ACT == 1 ? gelu_tanh(t) : fmaxf(t, 0.f);
+      }
+    split_store_half(e, U, v);
+    publish();
+    G.issue(U_addr, acc_out, c > 0 ? 1u : 0u);
+    if (c + 1 < chunks) G.issue(X_addr, acc_hidden, 0u);
+    G.wait_next();  // u_c . W2[c, :]
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -263,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  if (warp == 4) {
+  if (warp == kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
     __syncwarp();
     chain_teardown(S, warp);
@@ -272,147 +378,78 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
   uint8_t* X = smem + kOffX;
   uint8_t* U = smem + kOffU;
   const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
   const uint32_t t_acc0 = S.tmem_base + 0, t_h1 = S.tmem_base + 128, t_acc1 = S.tmem_base + 256, t_acc2 = S.tmem_base + 384;
-  Ring ring = S.ring;
-  uint32_t n_issued = 0, n_waited = 0;
-  // every thread counts the groups; thread 0 issues them.  Group i commits to done[i & 1].
-  auto issue = [&](uint32_t a_set, uint32_t acc, uint32_t accumulate) {
-    if (tid == 0) issue_unit(ring, a_set, acc, accumulate, p.idesc, S.bar_done[n_issued & 1]);
-    ++n_issued;
-  };
-  auto wait_next = [&]() {
-    mbar_wait(S.bar_done[n_waited & 1], (n_waited >> 1) & 1);
-    ++n_waited;
-    tc_after();
-  };
+  Groups G{S.ring, {S.bar_done[0], S.bar_done[1]}, p.idesc, 0, 0, tid};
 
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-    const int row = tile * 128 + tid;
+    const int row = tile * 128 + e.row;
     const bool valid = row < p.R;
-    // ---- 1. tbar row -> X images ----------------------------------------------------------------------
+    float x[2][32];
+    // ---- 1. agg = tbar . W3 -------------------------------------------------------------------------------
+    load_row_half(e, p.tbar + (size_t)row * D, valid, x);
+    split_store_half(e, X, x);
+    publish();
+    G.issue(X_addr, t_acc0, 0u);
+    G.wait_next();
+    // ---- 2. h1 = LN0(h + agg + b3) -> TMEM (fp32) + X images ---------------------------------------------------
     {
-      const float4* src = reinterpret_cast<const float4*>(p.tbar + (size_t)row * D);
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float v[32];
+      float hh[2][32];
+      tmem_ld_half(e, t_acc0, x);
+      load_row_half(e, p.h + (size_t)row * D, valid, hh);
+      const float* b = p.b3 + e.half * 64;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = valid ? __ldg(src + q * 8 + j) : make_float4(0, 0, 0, 0);
-          v[j * 4] = t.x; v[j * 4 + 1] = t.y; v[j * 4 + 2] = t.z; v[j * 4 + 3] = t.w;
-        }
-        split_store(X, tid, q * 32, v);
-      }
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[q][j] += hh[q][j] + __ldg(b + q * 32 + j);
     }
-    fence_async();
-    tc_before();
-    epi_sync();
-    issue(X_addr, t_acc0, 0u);
-    wait_next();
-    // ---- 2. h1 = LN0(h + tbar.W3 + b3) -> TMEM (fp32) + X images ---------------------------------------------
+    layer_norm_row(e, x, p.ln0_s, p.ln0_o);
+    tmem_st_half(e, t_h1, x);
+    split_store_half(e, X, x);
+    publish();
+    // ---- 3. FFN 128 -> 512 -> 128 (gnn_layers.py:385-394), hidden chunked 4 x 128 ---------------------------------
+    chunked_mlp<1>(G, e, X_addr, U, U_addr, t_acc1, t_acc2, 4, p.ffn_b1);
+    // ---- 4. h2 = LN1(h1 + ffn + b2) -> global h, X images ------------------------------------------------------
     {
-      float x[4][32];
-      const float4* hsrc = reinterpret_cast<const float4*>(p.h + (size_t)row * D);
+      float h1[2][32];
+      tmem_ld_half(e, t_acc2, x);
+      tmem_ld_half(e, t_h1, h1);
+      const float* b = p.ffn_b2 + e.half * 64;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        tmem_ld32(t_acc0 + lane_off + q * 32, x[q]);
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 hh = valid ? hsrc[q * 8 + j] : make_float4(0, 0, 0, 0);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.b3) + q * 8 + j);
-          x[q][j * 4] += hh.x + b.x; x[q][j * 4 + 1] += hh.y + b.y; x[q][j * 4 + 2] += hh.z + b.z; x[q][j * 4 + 3] += hh.w + b.w;
-        }
-      }
-      float mean, inv;
-      row_stats(x, mean, inv);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          x[q][j] = (__ldg(p.ln0_s + q * 32 + j) * inv) * (x[q][j] - mean) + __ldg(p.ln0_o + q * 32 + j);
-        tmem_st32(t_h1 + lane_off + q * 32, x[q]);
-        split_store(X, tid, q * 32, x[q]);
-      }
+        for (int j = 0; j < 32; ++j) x[q][j] += h1[q][j] + __ldg(b + q * 32 + j);
     }
-    fence_async();
-    tc_before();
-    epi_sync();
-    // ---- 3. FFN 128 -> 512 -> 128, hidden chunked 4 x 128 -----------------------------------------------
-    issue(X_addr, t_acc1, 0u);
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      wait_next();  // h1 . F1[:, c]  (and, in order, everything issued before it: U is free)
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float v[32];
-        tmem_ld32(t_acc1 + lane_off + q * 32, v);
+    layer_norm_row(e, x, p.ln1_s, p.ln1_o);
+    if (valid) {
+      float4* hdst = reinterpret_cast<float4*>(p.h + (size_t)row * D + e.half * 64);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j] + __ldg(p.ffn_b1 + c * 128 + q * 32 + j));
-        split_store(U, tid, q * 32, v);
-      }
-      fence_async();
-      tc_before();
-      epi_sync();
-      issue(U_addr, t_acc2, c > 0 ? 1u : 0u);
-      if (c < 3) issue(X_addr, t_acc1, 0u);
-      wait_next();  // u_c . F2[c, :] accumulated
-    }
-    // ---- 4. h2 = LN1(h1 + ffn + b2) -> global h, X images ----------------------------------------------
-    {
-      float x[4][32];
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float h1[32];
-        tmem_ld32(t_acc2 + lane_off + q * 32, x[q]);
-        tmem_ld32(t_h1 + lane_off + q * 32, h1);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[q][j] += h1[j] + __ldg(p.ffn_b2 + q * 32 + j);
-      }
-      float mean, inv;
-      row_stats(x, mean, inv);
-      float4* hdst = reinterpret_cast<float4*>(p.h + (size_t)row * D);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          x[q][j] = (__ldg(p.ln1_s + q * 32 + j) * inv) * (x[q][j] - mean) + __ldg(p.ln1_o + q * 32 + j);
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) hdst[q * 8 + j] = make_float4(x[q][j * 4], x[q][j * 4 + 1], x[q][j * 4 + 2], x[q][j * 4 + 3]);
-        }
-        if (p.n_out > 0) split_store(X, tid, q * 32, x[q]);
-      }
+        for (int j = 0; j < 8; ++j) hdst[q * 8 + j] = make_float4(x[q][j * 4], x[q][j * 4 + 1], x[q][j * 4 + 2], x[q][j * 4 + 3]);
     }
     if (p.n_out > 0) {
-      fence_async();
-      tc_before();
-      epi_sync();
+      split_store_half(e, X, x);
+      publish();
       // ---- 5. the gathered addend tables of the next edge-level kernels: fp16(h2 . Wout_o + b_o) ---------------
-      issue(X_addr, t_acc0, 0u);
+      G.issue(X_addr, t_acc0, 0u);
 #pragma unroll 1
       for (int o = 0; o < p.n_out; ++o) {
-        if (o + 1 < p.n_out) issue(X_addr, ((o + 1) & 1) ? t_acc1 : t_acc0, 0u);
-        wait_next();
-        const uint32_t acc = (o & 1) ? t_acc1 : t_acc0;
-        const float* bias = p.out_bias[o];
-        uint4* dst = reinterpret_cast<uint4*>(p.out[o] + (size_t)row * D);
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          float v[32];
-          tmem_ld32(acc + lane_off + q * 32, v);
-          if (bias) {
+        if (o + 1 < p.n_out) G.issue(X_addr, ((o + 1) & 1) ? t_acc1 : t_acc0, 0u);
+        G.wait_next();
+        tmem_ld_half(e, (o & 1) ? t_acc1 : t_acc0, x);
+        if (p.out_bias[o]) add_bias_half(e, x, p.out_bias[o]);
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out[o] + (size_t)row * D + e.half * 64);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + q * 32 + j);
-          }
-          if (valid) {
+          for (int q = 0; q < 2; ++q)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const __half2 a = __floats2half2_rn(v[j * 8], v[j * 8 + 1]), b = __floats2half2_rn(v[j * 8 + 2], v[j * 8 + 3]);
-              const __half2 c2 = __floats2half2_rn(v[j * 8 + 4], v[j * 8 + 5]), d = __floats2half2_rn(v[j * 8 + 6], v[j * 8 + 7]);
+              const __half2 a = __floats2half2_rn(x[q][j * 8], x[q][j * 8 + 1]), b = __floats2half2_rn(x[q][j * 8 + 2], x[q][j * 8 + 3]);
+              const __half2 c2 = __floats2half2_rn(x[q][j * 8 + 4], x[q][j * 8 + 5]), d = __floats2half2_rn(x[q][j * 8 + 6], x[q][j * 8 + 7]);
               dst[q * 4 + j] = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
                                           *reinterpret_cast<const uint32_t*>(&c2), *reinterpret_cast<const uint32_t*>(&d));
             }
-          }
         }
         tc_before();
         epi_sync();  // the accumulator just read is overwritten by the group issued at the top of the next pass
@@ -420,6 +457,178 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
     } else {
       tc_before();
       epi_sync();
+    }
+  }
+  chain_teardown(S, warp);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct ResamplerBlockP {
+  const float *qn_s, *qn_o, *dn_s, *dn_o, *bg, *bo;
+  const float *rt_ln_s, *rt_ln_o, *rt_b1, *rt_b2;
+  const float *ot_ln_s, *ot_ln_o, *ot_b1, *ot_b2;
+};
+struct ResamplerParams {
+  const float* h;            // [R,128] node features after the GNN ("original" track input)
+  const float* token_table;  // [max_out_len,128] PE of the token index (modules.py:486-500)
+  const int32_t* row_base;   // [R] first row of the structure a row belongs to (df = 1: token index == row)
+  float* z;                  // [R,8] pre-quantisation latents, unused columns 0
+  ResamplerBlockP blk[PST_MAX_BLOCKS];
+  int num_blocks;
+  const float* down_w;       // [128,8]
+  const float* down_b;       // [8]
+  int C;
+  const uint8_t* const* sched;
+  int n_sched;
+  int R, num_tiles;
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  Setup S = chain_setup(smem, tid, warp);
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (warp == kEpiThreads / 32) {
+    if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
+    __syncwarp();
+    chain_teardown(S, warp);
+    return;
+  }
+  uint8_t* X = smem + kOffX;
+  uint8_t* U = smem + kOffU;
+  const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
+  Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
+  const uint32_t t_res = S.tmem_base + 0, t_orig = S.tmem_base + 128, t_accA = S.tmem_base + 256, t_accB = S.tmem_base + 384;
+  Groups G{S.ring, {S.bar_done[0], S.bar_done[1]}, p.idesc, 0, 0, tid};
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int row = tile * 128 + e.row;
+    const bool valid = row < p.R;
+    float x[2][32];
+    {
+      const int local = valid ? row - __ldg(p.row_base + row) : 0;
+      load_row_half(e, p.token_table + (size_t)local * D, valid, x);
+      tmem_st_half(e, t_res, x);
+      float y[2][32];
+      load_row_half(e, p.h + (size_t)row * D, valid, y);
+      tmem_st_half(e, t_orig, y);
+    }
+#pragma unroll 1
+    for (int b = 0; b < p.num_blocks; ++b) {
+      const ResamplerBlockP& w = p.blk[b];
+      // ---- cross attention, df = 1 (modules.py:303-380,407-424): res += (v * sigmoid(gate)) . Wo + bo ------------
+      tmem_ld_half(e, t_res, x);
+      layer_norm_row(e, x, w.qn_s, w.qn_o);
+      split_store_half(e, X, x);
+      tmem_ld_half(e, t_orig, x);
+      layer_norm_row(e, x, w.dn_s, w.dn_o);
+      split_store_half(e, U, x);
+      publish();
+      G.issue(X_addr, t_accA, 0u);  // gate = LNq(res) . Wg
+      G.issue(U_addr, t_accB, 0u);  // v    = LNd(orig) . Wv
+      G.wait_next();
+      G.wait_next();
+      {
+        float g[2][32];
+        tmem_ld_half(e, t_accA, g);
+        tmem_ld_half(e, t_accB, x);
+        const float* bg = w.bg + e.half * 64;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[q][j] *= sigmoid_f(g[q][j] + __ldg(bg + q * 32 + j));
+      }
+      split_store_half(e, X, x);
+      publish();
+      G.issue(X_addr, t_accA, 0u);
+      G.wait_next();
+      {
+        float r[2][32];
+        tmem_ld_half(e, t_accA, x);
+        tmem_ld_half(e, t_res, r);
+        const float* bo = w.bo + e.half * 64;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + __ldg(bo + q * 32 + j);
+      }
+      tmem_st_half(e, t_res, x);
+      // ---- resampled transition (modules.py:227-252): res += W2 . relu(W1 . LN(res) + b1) + b2 -----------------------
+      layer_norm_row(e, x, w.rt_ln_s, w.rt_ln_o);
+      split_store_half(e, X, x);
+      publish();
+      chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, 2, w.rt_b1);
+      {
+        float r[2][32];
+        tmem_ld_half(e, t_accB, x);
+        tmem_ld_half(e, t_res, r);
+        const float* b2 = w.rt_b2 + e.half * 64;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + __ldg(b2 + q * 32 + j);
+      }
+      tmem_st_half(e, t_res, x);
+      // ---- original transition; its result is never read after the last block (modules.py:624-629) ---------------
+      if (b < p.num_blocks - 1) {
+        tmem_ld_half(e, t_orig, x);
+        layer_norm_row(e, x, w.ot_ln_s, w.ot_ln_o);
+        split_store_half(e, X, x);
+        publish();
+        chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, 2, w.ot_b1);
+        float r[2][32];
+        tmem_ld_half(e, t_accB, x);
+        tmem_ld_half(e, t_orig, r);
+        const float* b2 = w.ot_b2 + e.half * 64;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + __ldg(b2 + q * 32 + j);
+        tmem_st_half(e, t_orig, x);
+      }
+    }
+    // ---- head (model.py:169-174,148-164): z = (res / (||res|| + 1e-6)) . Wd + bd -------------------------------------
+    {
+      tmem_ld_half(e, t_res, x);
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ss = fmaf(x[q][j], x[q][j], ss);
+      e.red[e.half * 128 + e.row] = ss;
+      epi_sync();
+      const float d = sqrtf(e.red[e.row] + e.red[128 + e.row]) + 1e-6f;
+      float zc[PST_C8];
+#pragma unroll
+      for (int c = 0; c < PST_C8; ++c) zc[c] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const float r = x[q][j] / d;
+          const float4* wr = reinterpret_cast<const float4*>(p.down_w + (size_t)(e.half * 64 + q * 32 + j) * PST_C8);
+          const float4 w0 = __ldg(wr), w1 = __ldg(wr + 1);
+          zc[0] = fmaf(r, w0.x, zc[0]); zc[1] = fmaf(r, w0.y, zc[1]); zc[2] = fmaf(r, w0.z, zc[2]); zc[3] = fmaf(r, w0.w, zc[3]);
+          zc[4] = fmaf(r, w1.x, zc[4]); zc[5] = fmaf(r, w1.y, zc[5]); zc[6] = fmaf(r, w1.z, zc[6]); zc[7] = fmaf(r, w1.w, zc[7]);
+        }
+      float* zs = reinterpret_cast<float*>(U);  // U is free: [128 rows][8]
+      if (e.half == 1) {
+        *reinterpret_cast<float4*>(zs + e.row * 8) = make_float4(zc[0], zc[1], zc[2], zc[3]);
+        *reinterpret_cast<float4*>(zs + e.row * 8 + 4) = make_float4(zc[4], zc[5], zc[6], zc[7]);
+      }
+      epi_sync();
+      if (e.half == 0 && valid) {
+        const float4 a = *reinterpret_cast<const float4*>(zs + e.row * 8), b = *reinterpret_cast<const float4*>(zs + e.row * 8 + 4);
+        float o[PST_C8] = {zc[0] + a.x, zc[1] + a.y, zc[2] + a.z, zc[3] + a.w, zc[4] + b.x, zc[5] + b.y, zc[6] + b.z, zc[7] + b.w};
+#pragma unroll
+        for (int c = 0; c < PST_C8; ++c) o[c] = c < p.C ? o[c] + __ldg(p.down_b + c) : 0.f;
+        float4* zd = reinterpret_cast<float4*>(p.z + (size_t)row * PST_C8);
+        zd[0] = make_float4(o[0], o[1], o[2], o[3]);
+        zd[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      tc_before();
+      epi_sync();  // zs (in U) and the TMEM state are rewritten by the next tile
     }
   }
   chain_teardown(S, warp);
@@ -439,6 +648,7 @@ const uint8_t* pst_linear_tc_image(const pst_model* m, const float* W, int K, in
 struct PstNodeChain {
   const uint8_t** sched_dev = nullptr;  // all schedules, concatenated
   int layer_off[PST_MAX_LAYERS], layer_n[PST_MAX_LAYERS], layer_nout[PST_MAX_LAYERS];
+  int resampler_off = 0, resampler_n = 0;
 };
 
 int pst_prepare_node_chain(pst_model* m) {
@@ -478,10 +688,29 @@ int pst_prepare_node_chain(pst_model* m) {
     }
     C.layer_n[l] = (int)all.size() - C.layer_off[l];
   }
+  // resampler (df = 1): per block gate, value, output, resampled transition (2 chunks), original transition
+  C.resampler_off = (int)all.size();
+  for (int b = 0; b < m->cfg.num_blocks; ++b) {
+    const PstBlockW& w = m->w.block[b];
+    push_unit(w.wg, D, D, 0, 0);
+    push_unit(w.wv, D, D, 0, 0);
+    push_unit(w.wo, D, D, 0, 0);
+    for (int c = 0; c < 2; ++c) {
+      push_unit(w.rt_w1, D, PST_TRANS, 0, c);
+      push_unit(w.rt_w2, PST_TRANS, D, c, 0);
+    }
+    if (b < m->cfg.num_blocks - 1)
+      for (int c = 0; c < 2; ++c) {
+        push_unit(w.ot_w1, D, PST_TRANS, 0, c);
+        push_unit(w.ot_w2, PST_TRANS, D, c, 0);
+      }
+  }
+  C.resampler_n = (int)all.size() - C.resampler_off;
   if (!ok) return PST_ERR_BAD_ARGUMENT;
   if (cudaMalloc(&C.sched_dev, all.size() * sizeof(void*)) != cudaSuccess) return PST_ERR_CUDA;
   if (cudaMemcpy(C.sched_dev, all.data(), all.size() * sizeof(void*), cudaMemcpyHostToDevice) != cudaSuccess) return PST_ERR_CUDA;
-  if (cudaFuncSetAttribute(node_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+  if (cudaFuncSetAttribute(node_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(resampler_df1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
     return PST_ERR_CUDA;
   return PST_OK;
 }
@@ -518,5 +747,28 @@ int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const
   p.idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   int grid = m->num_sms < p.num_tiles ? m->num_sms : p.num_tiles;
   node_update_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
+  return 1;
+}
+
+// z <- the whole resampler + head for downsampling_ratio == 1 (token t == residue t); h = node features after the GNN
+int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z) {
+  if (!m->node_chain || R <= 0 || m->cfg.downsampling_ratio != 1) return 0;
+  const PstNodeChain& C = *m->node_chain;
+  ResamplerParams p{};
+  p.h = h; p.token_table = m->w.token_table; p.row_base = row_base; p.z = z;
+  p.num_blocks = m->cfg.num_blocks;
+  for (int b = 0; b < p.num_blocks; ++b) {
+    const PstBlockW& w = m->w.block[b];
+    p.blk[b] = ResamplerBlockP{w.qn_s, w.qn_o, w.dn_s, w.dn_o, w.bg, w.bo, w.rt_ln_s, w.rt_ln_o, w.rt_b1, w.rt_b2,
+                               w.ot_ln_s, w.ot_ln_o, w.ot_b1, w.ot_b2};
+  }
+  p.down_w = m->w.down_w; p.down_b = m->w.down_b; p.C = m->cfg.num_levels;
+  p.sched = C.sched_dev + C.resampler_off;
+  p.n_sched = C.resampler_n;
+  p.R = R;
+  p.num_tiles = (R + 127) / 128;
+  p.idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  int grid = m->num_sms < p.num_tiles ? m->num_sms : p.num_tiles;
+  resampler_df1_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
   return 1;
 }

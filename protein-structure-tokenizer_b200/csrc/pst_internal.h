@@ -166,6 +166,7 @@ int pst_prepare_node_chain(pst_model* m);
 void pst_destroy_node_chain(pst_model* m);
 int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* tbar, float* h, int R,
                            uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r);
+int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z);
 
 #define PST_CUDA_OK(expr)                                  \
   do {                                                     \
