@@ -307,8 +307,12 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": E * 256 * (prof_cnt[1] * 1 + prof_cnt[2] * 2) / mlp_groups,
                 "peak_source": f"{peaks['source']} (bf16_tflops_sustained, MEASURED_PEAKS.json)",
                 "hw_flops_tflops": E * (prof_cnt[1] * HW_FLOP_MSG + prof_cnt[2] * HW_FLOP_UPD) / (mlp_ms * 1e-3) / 1e12,
-                "avg_launch_ms": mlp_ms / mlp_groups, "launch_groups_per_step": mlp_groups / args.steps,
-                "share_of_step": mlp_ms / ms_total,
+                "avg_launch_ms": mlp_ms / mlp_groups,
+                # the span recorder has a fixed capacity: per-step figures come from the per-kind averages and the
+                # known launch structure (3 message + 2 edge-update MLPs per step), not from raw span counts
+                "launch_groups_per_step": 2 * cfg.gnn_layers - 1,
+                "share_of_step": (prof_ms[1] / max(1, prof_cnt[1]) * cfg.gnn_layers
+                                  + prof_ms[2] / max(1, prof_cnt[2]) * (cfg.gnn_layers - 1)) / ms_step,
                 "featurize_knn_ms_per_step": prof_ms[0] / max(1, prof_cnt[0]),
                 "end_to_end_frac": value / world * FLOP_PER_RESIDUE.get(df, 44.91e6) / 1e12 / peak,
             }

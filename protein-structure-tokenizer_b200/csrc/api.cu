@@ -106,6 +106,7 @@ PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T) {
   ws.t1 = (float*)take(fp32 ? E * D * sizeof(float) : 0);
   ws.t2 = (float*)take(fp32 ? E * D * sizeof(float) : 0);
   ws.partial = (float*)take(fp32 ? 0 : pst_tc_partial_floats(R, (int)K) * sizeof(float));
+  ws.senders_abs = (int32_t*)take(fp32 ? 0 : E * sizeof(int32_t));
   ws.h = (float*)take((size_t)R * D * sizeof(float));
   ws.agg = (float*)take((size_t)R * D * sizeof(float));
   ws.ps = (float*)take((size_t)R * D * sizeof(float));

@@ -47,13 +47,14 @@ struct EdgeMlpParams {
   uint16_t* e;              // [E,128] 16-bit edge state (read; rewritten in update mode)
   const __half* ps;         // [R,128] fp16  (h.W1[0:128])
   const __half* pr;         // [R,128] fp16  (h.W1[128:256] + b1)
-  const int32_t* senders;   // [E] local indices
+  const int32_t* senders;   // [E] ABSOLUTE sender rows (row_base[receiver] + local index, abs_senders_kernel)
   const int32_t* row_base;  // [R]
   float* partial;           // message mode: [num_tiles][4][128] partial row sums of the 2nd hidden layer
   int E;
   int K;
   int num_tiles;
   uint32_t idesc;
+  uint32_t idesc_sum;       // message mode: fp16 MN-major A x K-major B, M = 128, N = 16 (row sums)
 };
 
 // byte offset of element (row, k) inside a 128x128 16-bit K-major SWIZZLE_128B operand image
@@ -90,6 +91,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   // K-major, SWIZZLE_128B, 8-row atoms of 1024 B: SBO = 1024, LBO unused, version 1 (Blackwell)
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// The same [128 x 128] 16-bit image read as an MN-major operand (M/N = the image's 128 K-elements, K = its rows):
+// 64 MN-elements (128 B) contiguous, the next 64 at LBO = 16 KB (the image's second K block), 8 K-rows per 1024 B
+// atom (SBO); canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(kKBlockBytes >> 4) << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
@@ -234,6 +248,10 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
   return fma2(hx, t, hx);
 }
 
+__device__ __forceinline__ uint32_t hadd2u(uint32_t a, uint32_t b) {
+  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ void tmem_ld32v(uint32_t taddr, float2 (&v)[16]) { tmem_ld32(taddr, *reinterpret_cast<float (*)[32]>(&v)); }
 __device__ __forceinline__ void tmem_st32v(uint32_t taddr, const float2 (&v)[16]) { tmem_st32(taddr, *reinterpret_cast<const float (*)[32]>(&v)); }
 
@@ -290,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   const int gt = tid & 127;         // thread within the group == accumulator row
   const int wq = warp & 3;          // TMEM lane quarter this warp may access
   uint8_t* sA = sAall + g * kMatBytes;
+  uint8_t* sSel = sW + 2 * kMatBytes + g * 4096;  // message mode only: the W3 slot is not loaded
   float* S = reinterpret_cast<float*>(sA);
   int* sBase = sBaseAll + g * 4;
   const int sub = gt >> 4, c16 = gt & 15;  // 16 threads per row, 8 rows per pass
@@ -303,6 +322,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     uint4* dst = reinterpret_cast<uint4*>(sW);
     const int n16 = (MODE == 0 ? 2 : 3) * (int)(kMatBytes / 16);
     for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
+    if (MODE == 0) {
+      uint4* z = reinterpret_cast<uint4*>(sW + 2 * kMatBytes);
+      for (int i = tid; i < (int)(kGroups * 4096 / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
     if (tid < 128) {
       sVec[tid] = p.b2[tid];
       sVec[128 + tid] = MODE == 1 ? p.b3[tid] : 0.f;
@@ -334,20 +357,21 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   unsigned long long prof_acc[16] = {0};
   long long prof_last = clock64();
 #endif
-  // gather indices of the first tile: local sender index (16 bits) of rows it*8 + sub, two per register
+  // gather indices of the first tile: sender row minus the base row of the tile's first receiver's structure
+  // (16 bits: a tile spans at most two structures), rows it*8 + sub, two per register
   uint32_t nidx[8];
   int nbase = 0;
   {
     const int t0 = blockIdx.x * kGroups + g;
     const int nrow0 = t0 * kTileM;
+    if (t0 < p.num_tiles) nbase = __ldg(p.row_base + min(nrow0 / p.K, (p.E - 1) / p.K));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int ra = nrow0 + (2 * i) * 8 + sub, rb = ra + 8;
-      const uint32_t lo = (t0 < p.num_tiles && ra < p.E) ? (uint32_t)__ldg(p.senders + ra) : 0u;
-      const uint32_t hi = (t0 < p.num_tiles && rb < p.E) ? (uint32_t)__ldg(p.senders + rb) : 0u;
+      const uint32_t lo = (t0 < p.num_tiles && ra < p.E) ? (uint32_t)(__ldg(p.senders + ra) - nbase) : 0u;
+      const uint32_t hi = (t0 < p.num_tiles && rb < p.E) ? (uint32_t)(__ldg(p.senders + rb) - nbase) : 0u;
       nidx[i] = lo | (hi << 16);
     }
-    if (gt < 4 && t0 < p.num_tiles) nbase = __ldg(p.row_base + min(nrow0 / p.K + gt, (p.E - 1) / p.K));
   }
 
   for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
@@ -357,8 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     const int first_recv = row0 / p.K;
     const int last_row = min(p.E - row0, kTileM);  // valid rows in this tile
     const int last_recv = (p.E - 1) / p.K;
-    // gather indices of this tile were fetched during the previous tile (nidx / nbase); publish the bases
-    if (gt < 4) sBase[gt] = nbase;
+    // gather indices of this tile were fetched during the previous tile (nidx, relative to row nbase)
     tc_fence_before();
     group_sync(g);
     tc_fence_after();
@@ -368,44 +391,38 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     // (the same for 50 consecutive edges), summed and written as fp16 into the A buffer in the operand image
     // layout; each thread then reads its own row and writes it into its accumulator row in TMEM.
     {
-      const uint4* ps4 = reinterpret_cast<const uint4*>(p.ps) + c16;
-      const uint4* pr4 = reinterpret_cast<const uint4*>(p.pr) + c16;
-      int rem = row0 + sub - first_recv * p.K, seg = 0;  // row = it*8 + sub: (rem, seg) advance by 8 rows per pass
-      while (rem >= p.K) { rem -= p.K; ++seg; }
-      uint4 b = __ldg(pr4 + (size_t)min(first_recv + seg, last_recv) * (kD / 8));
+      // All 8 loads of a batch are issued before anything is consumed: two L2 round trips per tile (a
+      // loop-carried load -> store form makes ptxas serialise one round trip per row).
+      {  // warm L1 with this thread's receiver row (read in the preload pass below)
+        const char* prr = reinterpret_cast<const char*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(prr));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(prr + 128));
+      }
+      const uint4* psb = reinterpret_cast<const uint4*>(p.ps) + (size_t)nbase * (kD / 8) + c16;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int t = (it & 1) ? (int)(nidx[it >> 1] >> 16) : (int)(nidx[it >> 1] & 0xffffu);
-        const uint4 a = __ldg(ps4 + (size_t)(sBase[seg] + t) * (kD / 8));
-        uint4 s;
-        {
-          const __half2 s0 = __hadd2(*reinterpret_cast<const __half2*>(&a.x), *reinterpret_cast<const __half2*>(&b.x));
-          const __half2 s1 = __hadd2(*reinterpret_cast<const __half2*>(&a.y), *reinterpret_cast<const __half2*>(&b.y));
-          const __half2 s2 = __hadd2(*reinterpret_cast<const __half2*>(&a.z), *reinterpret_cast<const __half2*>(&b.z));
-          const __half2 s3 = __hadd2(*reinterpret_cast<const __half2*>(&a.w), *reinterpret_cast<const __half2*>(&b.w));
-          s = make_uint4(*reinterpret_cast<const uint32_t*>(&s0), *reinterpret_cast<const uint32_t*>(&s1),
-                         *reinterpret_cast<const uint32_t*>(&s2), *reinterpret_cast<const uint32_t*>(&s3));
+      for (int hb = 0; hb < 2; ++hb) {
+        uint4 a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int it = hb * 8 + i;
+          const uint32_t d = (it & 1) ? (nidx[it >> 1] >> 16) : (nidx[it >> 1] & 0xffffu);
+          a[i] = __ldg(psb + (size_t)d * (kD / 8));
         }
-        *reinterpret_cast<uint4*>(sA + offA + it * 1024) = s;
-        rem += 8;
-        if (rem >= p.K) {  // next pass belongs to the next receiver (rows advance by 8, K >= 43: at most one step)
-          rem -= p.K;
-          ++seg;
-          b = __ldg(pr4 + (size_t)min(first_recv + seg, last_recv) * (kD / 8));
-        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sA + offA + (hb * 8 + i) * 1024) = a[i];
       }
       // fetch the next tile's gather indices (consumed at the top of the next iteration) and warm L2 with its rows
       const int nt = tile + gridDim.x * kGroups;
       if (nt < p.num_tiles) {
         const int nrow0 = nt * kTileM;
+        nbase = __ldg(p.row_base + min(nrow0 / p.K, last_recv));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int ra = nrow0 + (2 * i) * 8 + sub, rb = ra + 8;
-          const uint32_t lo = ra < p.E ? (uint32_t)__ldg(p.senders + ra) : 0u;
-          const uint32_t hi = rb < p.E ? (uint32_t)__ldg(p.senders + rb) : 0u;
+          const uint32_t lo = ra < p.E ? (uint32_t)(__ldg(p.senders + ra) - nbase) : 0u;
+          const uint32_t hi = rb < p.E ? (uint32_t)(__ldg(p.senders + rb) - nbase) : 0u;
           nidx[i] = lo | (hi << 16);
         }
-        if (gt < 4) nbase = __ldg(p.row_base + min(nrow0 / p.K + gt, (p.E - 1) / p.K));
         const char* nxt = reinterpret_cast<const char*>(p.e + (size_t)nrow0 * kD) + gt * 256;
         if ((size_t)nrow0 + gt < (size_t)p.E) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
@@ -415,18 +432,23 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     }
     group_sync(g);
     PHASE(1);
+    {
+      // + the receiver's row (the same for K consecutive edges: L1 hits, at most two distinct rows per warp)
+      const uint4* prr = reinterpret_cast<const uint4*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
 #pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      float2 v[16];
+      for (int q = 0; q < 4; ++q) {
+        float2 v[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 a = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
-        v[j * 4 + 0] = Unpack<__half>::two(a.x);
-        v[j * 4 + 1] = Unpack<__half>::two(a.y);
-        v[j * 4 + 2] = Unpack<__half>::two(a.z);
-        v[j * 4 + 3] = Unpack<__half>::two(a.w);
+        for (int j = 0; j < 4; ++j) {
+          const uint4 a = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
+          const uint4 b = __ldg(prr + q * 4 + j);
+          v[j * 4 + 0] = Unpack<__half>::two(hadd2u(a.x, b.x));
+          v[j * 4 + 1] = Unpack<__half>::two(hadd2u(a.y, b.y));
+          v[j * 4 + 2] = Unpack<__half>::two(hadd2u(a.z, b.z));
+          v[j * 4 + 3] = Unpack<__half>::two(hadd2u(a.w, b.w));
+        }
+        tmem_st32v(tmem_row + q * 32, v);
       }
-      tmem_st32v(tmem_row + q * 32, v);
     }
     group_sync(g);
     PHASE(2);
@@ -561,11 +583,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       PHASE(12);
     } else {
       // ---- 5b. epilogue 2 (message mode): + b2, GELU, partial sums over the rows of each receiver ------
-      // The activated tile is staged once, as fp16 in the operand image layout (the precision the third GEMM's
-      // operand has in update mode; the sums themselves are fp32).  Reduction: warp w owns column groups
-      // 4w..4w+3 (8 columns each), lane = (row slice 0..7) * 4 + column group; a thread walks the rows
-      // lo_s + slice, + 8, ... of each of the <= 4 receivers of the tile, then the 8 slices are combined with
-      // three shuffle steps: no shared-memory partials, one barrier.
+      // The activated tile is staged as fp16 in the operand image layout (the precision the third GEMM's operand
+      // has in update mode).  The per-receiver row sums are one more tensor-core product: the staged tile, read
+      // as an MN-major A operand (M = the 128 channels, K = the 128 edge rows: the same bytes, transposed by the
+      // descriptor), times a 0/1 selection matrix Sel^T [N = 16 (4 used) x K = 128 rows] built per tile, gives
+      // D[channel, receiver] in fp32 in 16 TMEM columns; thread = channel reads its 4 sums.
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         float2 v[16];
@@ -578,42 +600,40 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         }
         store_a_chunk2<__half>(sA, gt, q * 32, v);
       }
-      group_sync(g);
       {
-        const int lane = tid & 31, slice = lane >> 2, cg = wq * 4 + (lane & 3);
-        float2 acc[4][4];
+        // Sel^T[s][r] for r = gt: K block r >> 6, row s (128 B each), 16-byte chunk ((r & 63) >> 3) ^ s
+        uint8_t* sel = sSel + (gt >> 6) * 2048 + ((gt & 7) << 1);
+        const int kc = (gt & 63) >> 3;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[s][c] = make_float2(0.f, 0.f);
-          const int lo_u = (first_recv + s) * p.K - row0;
-          const int lo = max(lo_u, 0), hi = min(lo_u + p.K, last_row);
-          for (int r = lo + slice; r < hi; r += 8) {
-            const uint4 pk = *reinterpret_cast<const uint4*>(sA + swz_offset(r, cg * 8));
-            acc[s][0] = add2(acc[s][0], Unpack<__half>::two(pk.x));
-            acc[s][1] = add2(acc[s][1], Unpack<__half>::two(pk.y));
-            acc[s][2] = add2(acc[s][2], Unpack<__half>::two(pk.z));
-            acc[s][3] = add2(acc[s][3], Unpack<__half>::two(pk.w));
-          }
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int lo_u = (first_recv + s4) * p.K - row0;
+          const bool in = gt >= lo_u && gt < lo_u + p.K && gt < last_row;
+          *reinterpret_cast<uint16_t*>(sel + s4 * 128 + ((kc ^ s4) << 4)) = in ? (uint16_t)0x3C00 : (uint16_t)0;
         }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      group_sync(g);
+      if (gt == 0) {
+        tc_fence_after();
+        const uint32_t sel_addr = smem_u32(sSel);
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int m = 4; m <= 16; m <<= 1) {
-              acc[s][c].x += __shfl_xor_sync(0xffffffffu, acc[s][c].x, m);
-              acc[s][c].y += __shfl_xor_sync(0xffffffffu, acc[s][c].y, m);
-            }
-          }
-        if (slice == 0) {
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            float4* dst = reinterpret_cast<float4*>(p.partial + ((size_t)tile * 4 + s) * kD + cg * 8);
-            dst[0] = make_float4(acc[s][0].x, acc[s][0].y, acc[s][1].x, acc[s][1].y);
-            dst[1] = make_float4(acc[s][2].x, acc[s][2].y, acc[s][3].x, acc[s][3].y);
-          }
+        for (int j = 0; j < 8; ++j) {  // 16 edge rows per step: two 8-row atoms of the image (SBO = 1024)
+          umma_f16(tmem_acc, make_smem_desc_mn(sA_addr + j * 2048), make_smem_desc(sel_addr + (j >> 2) * 2048 + (j & 3) * 32),
+                   p.idesc_sum, j > 0 ? 1u : 0u);
         }
+        umma_commit(mbar_addr);
+      }
+      mbar_wait(mbar_addr, parity);
+      parity ^= 1;
+      tc_fence_after();
+      {
+        float r0, r1, r2, r3;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3) : "r"(tmem_row) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* dst = p.partial + (size_t)tile * 4 * kD + gt;
+        dst[0] = r0; dst[kD] = r1; dst[2 * kD] = r2; dst[3 * kD] = r3;
       }
       group_sync(g);
       PHASE(13);
@@ -806,6 +826,14 @@ __global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict
   if (i < n) dst[i] = __float2half_rn(src[i]);
 }
 
+// senders_abs[e] = row_base[receiver(e)] + senders[e]: absolute row of the sender (the k-NN indices are local to
+// their structure, gnn_layers.py:344-351 indexes node_inp[senders] per structure)
+__global__ void abs_senders_kernel(const int32_t* __restrict__ senders, const int32_t* __restrict__ row_base, int K, int E,
+                                   int32_t* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) out[e] = __ldg(row_base + e / K) + __ldg(senders + e);
+}
+
 // tbar[r] = (sum of the partial row sums that cover receiver r) / K
 __global__ void combine_partials_kernel(const float* __restrict__ partial, int K, int R, float* __restrict__ tbar) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -912,6 +940,8 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   p.num_tiles = (p.E + kTileM - 1) / kTileM;
   const uint32_t fmt = m->cfg.precision == PST_PREC_FP16 ? 0u : 1u;  // F16 / BF16
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kD >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  // row sums: fp16 x fp16 -> fp32, A MN-major (bit 15), M = 128 channels, N = 16 receivers slots
+  p.idesc_sum = (1u << 4) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(kD >> 4) << 24);
   if (p.num_tiles == 0) return 0;
   if (K < 43) return PST_ERR_UNSUPPORTED_CONFIG;  // a 128-row tile must touch at most 4 receivers
   int grid = m->num_sms;
@@ -949,5 +979,13 @@ int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* f
   if (grid > need) grid = need;
   if (m->cfg.precision == PST_PREC_FP16) edge_embed_tc_kernel<__half><<<grid, kThreads, kEmbSmemTotal, st>>>(p);
   else edge_embed_tc_kernel<__nv_bfloat16><<<grid, kThreads, kEmbSmemTotal, st>>>(p);
+  return 1;
+}
+
+int pst_launch_abs_senders(const pst_model* m, cudaStream_t st, const int32_t* senders, const int32_t* row_base, int R,
+                           int32_t* senders_abs) {
+  const int K = m->cfg.num_neighbor, E = R * K;
+  if (E <= 0) return 0;
+  abs_senders_kernel<<<(E + 255) / 256, 256, 0, st>>>(senders, row_base, K, E, senders_abs);
   return 1;
 }

@@ -415,6 +415,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     uint16_t* pr = reinterpret_cast<uint16_t*>(ws.pr);
     uint16_t* ps2 = reinterpret_cast<uint16_t*>(ws.agg);
     uint16_t* pr2 = reinterpret_cast<uint16_t*>(ws.u);
+    L.count += pst_launch_abs_senders(m, st, senders, row_base, R, ws.senders_abs);
     const PstLayerW& w0 = m->w.layer[0];
     L.gemm(ws.h, w0.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr), 1);
     L.gemm(ws.h, w0.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w0.msg_b1), 1);
@@ -423,7 +424,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
         // message MLP: returns the per-receiver mean of the 2nd hidden layer; the 3rd linear commutes with
         // that mean (no activation follows it) and is applied by the node kernel
         PstSpan span(m, st, 1);
-        int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, senders, row_base, ws.partial, R, ws.tmp);
+        int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, ws.senders_abs, row_base, ws.partial, R, ws.tmp);
         if (n < 0) return n;
         L.count += n;
       }
@@ -435,7 +436,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       }
       if (l == cfg.gnn_layers - 1) break;  // the last layer's edge update is never read (model.py:385)
       PstSpan span(m, st, 2);
-      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), ps2, pr2, senders, row_base, ws.partial, R, nullptr);
+      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), ps2, pr2, ws.senders_abs, row_base, ws.partial, R, nullptr);
       if (n < 0) return n;
       L.count += n;
     }

@@ -14,7 +14,7 @@
 #define PST_C8 PST_MAX_LEVELS
 #define PST_FEAT_PAD 32   // 27 edge features padded to 32 GEMM rows
 #define PST_PREP_STRIDE 16 // doubles per residue in the prep record
-#define PST_PROF_MAX_SPANS 64
+#define PST_PROF_MAX_SPANS 512
 #define PST_PROF_KINDS 4   // 0 featurise+knn, 1 message MLP, 2 edge-update MLP, 3 rest of the encoder
 
 // ---- prepared weight blob (fp32), see pst/weights.py for the packer ----------
@@ -107,6 +107,7 @@ struct PstWorkspace {
   float* t1;             // [E,128]   (fp32 mode only)
   float* t2;             // [E,128]   (fp32 mode only)
   float* partial;        // [tiles,4,128] (tensor-core modes only)
+  int32_t* senders_abs;  // [E] absolute sender rows (tensor-core modes only)
   float* h;              // [R,128]
   float* agg;            // [R,128]
   float* ps;             // [R,128]
@@ -146,11 +147,14 @@ int pst_launch_indexes_to_codes(const pst_model* m, cudaStream_t st, const int32
                                 float* codes);
 
 // tensor-core edge MLP (edge_mlp_tc.cu).  mode 0: message MLP -> agg[R,128] = mean_K;
-// mode 1: edge update -> e = LN(e + MLP).  Returns kernels launched, <0 on error.
+// mode 1: edge update -> e = LN(e + MLP).  `senders` are ABSOLUTE rows (pst_launch_abs_senders).
+// Returns kernels launched, <0 on error.
 int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e,
                            const uint16_t* ps, const uint16_t* pr, const int32_t* senders,
                            const int32_t* row_base, float* partial, int R, float* agg_out);
 size_t pst_tc_partial_floats(int R, int K);
+int pst_launch_abs_senders(const pst_model* m, cudaStream_t st, const int32_t* senders, const int32_t* row_base, int R,
+                           int32_t* senders_abs);
 int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* feat, const int32_t* senders,
                              const int32_t* row_base, int R, uint16_t* e);
 
