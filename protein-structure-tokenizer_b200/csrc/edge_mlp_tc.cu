@@ -399,17 +399,15 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         asm volatile("prefetch.global.L1 [%0];" ::"l"(prr + 128));
       }
       const uint4* psb = reinterpret_cast<const uint4*>(p.ps) + (size_t)nbase * (kD / 8) + c16;
+      {
+        uint4 a[16];
 #pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
-        uint4 a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int it = hb * 8 + i;
+        for (int it = 0; it < 16; ++it) {
           const uint32_t d = (it & 1) ? (nidx[it >> 1] >> 16) : (nidx[it >> 1] & 0xffffu);
-          a[i] = __ldg(psb + (size_t)d * (kD / 8));
+          a[it] = __ldg(psb + (size_t)d * (kD / 8));
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sA + offA + (hb * 8 + i) * 1024) = a[i];
+        for (int it = 0; it < 16; ++it) *reinterpret_cast<uint4*>(sA + offA + it * 1024) = a[it];
       }
       // fetch the next tile's gather indices (consumed at the top of the next iteration) and warm L2 with its rows
       const int nt = tile + gridDim.x * kGroups;
@@ -455,12 +453,14 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     // ---- 1. e tile (16-bit, global) -> A image: 16-byte copies, 16 threads per row, 8 rows per pass ----
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
-#pragma unroll 8
+      uint4 x[16];
+#pragma unroll
       for (int it = 0; it < 16; ++it) {
-        uint4 x = make_uint4(0, 0, 0, 0);
-        if (it * 8 + sub < last_row) x = src[(size_t)it * 8 * (kD / 8)];
-        *reinterpret_cast<uint4*>(sA + offA + it * 1024) = x;
+        x[it] = make_uint4(0, 0, 0, 0);
+        if (it * 8 + sub < last_row) x[it] = src[(size_t)it * 8 * (kD / 8)];
       }
+#pragma unroll
+      for (int it = 0; it < 16; ++it) *reinterpret_cast<uint4*>(sA + offA + it * 1024) = x[it];
     }
     fence_proxy_async();
     tc_fence_before();
@@ -518,12 +518,14 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       // in the operand image layout, so each thread finds its own row conflict-free; statistics; x -> TMEM.
       {
         const uint4* src = reinterpret_cast<const uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
-#pragma unroll 8
+        uint4 x[16];
+#pragma unroll
         for (int it = 0; it < 16; ++it) {
-          uint4 x = make_uint4(0, 0, 0, 0);
-          if (it * 8 + sub < last_row) x = src[(size_t)it * 8 * (kD / 8)];
-          *reinterpret_cast<uint4*>(sA + offA + it * 1024) = x;
+          x[it] = make_uint4(0, 0, 0, 0);
+          if (it * 8 + sub < last_row) x[it] = src[(size_t)it * 8 * (kD / 8)];
         }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) *reinterpret_cast<uint4*>(sA + offA + it * 1024) = x[it];
       }
       group_sync(g);
       PHASE(9);
