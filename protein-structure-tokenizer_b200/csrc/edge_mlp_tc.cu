@@ -390,37 +390,50 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     // One row-coalesced gather pass (16 threads x 16 B per row): sender row of the fp16 table + receiver row
     // (the same for 50 consecutive edges), summed and written as fp16 into the A buffer in the operand image
     // layout; each thread then reads its own row and writes it into its accumulator row in TMEM.
+    int raw[16];
     {
-      // All 8 loads of a batch are issued before anything is consumed: two L2 round trips per tile (a
-      // loop-carried load -> store form makes ptxas serialise one round trip per row).
-      {  // warm L1 with this thread's receiver row (read in the preload pass below)
-        const char* prr = reinterpret_cast<const char*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(prr));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(prr + 128));
-      }
+      // Every load of the pass is issued before its batch is consumed (a loop-carried load -> store form makes
+      // ptxas serialise one L2 round trip per row).  Order: the 16 sender rows; the next tile's sender indices
+      // (raw, packed only after the stores so that their latency hides behind the row loads); stores; this
+      // thread's receiver row for the preload pass, issued before the barrier so that it lands while waiting.
       const uint4* psb = reinterpret_cast<const uint4*>(p.ps) + (size_t)nbase * (kD / 8) + c16;
-      {
-        uint4 a[16];
+      uint4 a[16];
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const uint32_t d = (it & 1) ? (nidx[it >> 1] >> 16) : (nidx[it >> 1] & 0xffffu);
-          a[it] = __ldg(psb + (size_t)d * (kD / 8));
-        }
-#pragma unroll
-        for (int it = 0; it < 16; ++it) *reinterpret_cast<uint4*>(sA + offA + it * 1024) = a[it];
+      for (int it = 0; it < 16; ++it) {
+        const uint32_t d = (it & 1) ? (nidx[it >> 1] >> 16) : (nidx[it >> 1] & 0xffffu);
+        a[it] = __ldg(psb + (size_t)d * (kD / 8));
       }
-      // fetch the next tile's gather indices (consumed at the top of the next iteration) and warm L2 with its rows
+      const int nt = tile + gridDim.x * kGroups;
+      const int nrow0 = nt * kTileM;
+      if (nt < p.num_tiles) {
+        nbase = __ldg(p.row_base + min(nrow0 / p.K, last_recv));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int ra = nrow0 + i * 8 + sub;
+          raw[i] = __ldg(p.senders + min(ra, p.E - 1));
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 16; ++it) *reinterpret_cast<uint4*>(sA + offA + it * 1024) = a[it];
+    }
+    uint4 prow[16];
+    {
+      const uint4* prr = reinterpret_cast<const uint4*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) prow[j] = __ldg(prr + j);
+    }
+    {
       const int nt = tile + gridDim.x * kGroups;
       if (nt < p.num_tiles) {
         const int nrow0 = nt * kTileM;
-        nbase = __ldg(p.row_base + min(nrow0 / p.K, last_recv));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int ra = nrow0 + (2 * i) * 8 + sub, rb = ra + 8;
-          const uint32_t lo = ra < p.E ? (uint32_t)(__ldg(p.senders + ra) - nbase) : 0u;
-          const uint32_t hi = rb < p.E ? (uint32_t)(__ldg(p.senders + rb) - nbase) : 0u;
+          const uint32_t lo = ra < p.E ? (uint32_t)(raw[2 * i] - nbase) : 0u;
+          const uint32_t hi = rb < p.E ? (uint32_t)(raw[2 * i + 1] - nbase) : 0u;
           nidx[i] = lo | (hi << 16);
         }
+        // warm L2 with the next tile's rows
         const char* nxt = reinterpret_cast<const char*>(p.e + (size_t)nrow0 * kD) + gt * 256;
         if ((size_t)nrow0 + gt < (size_t)p.E) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
@@ -431,15 +444,14 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     group_sync(g);
     PHASE(1);
     {
-      // + the receiver's row (the same for K consecutive edges: L1 hits, at most two distinct rows per warp)
-      const uint4* prr = reinterpret_cast<const uint4*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
-#pragma unroll 1
+      // accumulator row <- sender row (staged) + receiver row (the same for K consecutive edges)
+#pragma unroll
       for (int q = 0; q < 4; ++q) {
         float2 v[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 a = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
-          const uint4 b = __ldg(prr + q * 4 + j);
+          const uint4 b = prow[q * 4 + j];
           v[j * 4 + 0] = Unpack<__half>::two(hadd2u(a.x, b.x));
           v[j * 4 + 1] = Unpack<__half>::two(hadd2u(a.y, b.y));
           v[j * 4 + 2] = Unpack<__half>::two(hadd2u(a.z, b.z));
