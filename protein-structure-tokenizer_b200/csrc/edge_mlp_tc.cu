@@ -18,6 +18,7 @@
 // epilogue2 -> [MMA3 -> epilogue3 (residual + LayerNorm)]   serially, and the four groups interleave
 // on the SM so one group's MMA overlaps the others' epilogues.  In the 32x32b TMEM load layout each
 // thread owns one accumulator row (= one edge), so the LayerNorm and the gathers are thread-local.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -34,7 +35,7 @@ constexpr uint32_t kKBlockBytes = 128 * 128;    // 128 rows x 64 elements x 2 B
 constexpr uint32_t kSmemW = 3 * kMatBytes;
 constexpr uint32_t kSmemA = kGroups * kMatBytes;
 constexpr uint32_t kSmemVec = 4 * 128 * sizeof(float) + 64;  // b2, b3, ln scale, ln offset; per-group segment bases
-constexpr uint32_t kSmemMisc = 64;  // mbarriers + TMEM slot
+constexpr uint32_t kSmemMisc = 128;  // MMA mbarriers, TMA mbarriers, TMEM slot
 constexpr uint32_t kSmemTotal = kSmemW + kSmemA + kSmemVec + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 
@@ -82,6 +83,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// ---- TMA (cp.async.bulk.tensor): the 128 x 128 16-bit edge-state tile moves between HBM and the A buffer as two
+// [128 rows x 64 columns] SWIZZLE_128B boxes, which is exactly the K-major operand image layout.  The copies run
+// on the async proxy: no LDG / STS / LDS / STG wavefronts on the L1 data pipe that bounds this kernel.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_tile_load(uint32_t sA_addr, const CUtensorMap* map, int row0, uint32_t mbar) {
+  mbar_expect_tx(mbar, kMatBytes);
+  tma_load_2d(sA_addr, map, 0, row0, mbar);
+  tma_load_2d(sA_addr + kKBlockBytes, map, 64, row0, mbar);
+}
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -293,14 +318,15 @@ __device__ unsigned long long g_edge_prof[2][16];
 #endif
 
 template <typename T16, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams p) {
+__global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams p, const __grid_constant__ CUtensorMap tmap_e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sAall = smem + kSmemW;
   float* sVec = reinterpret_cast<float*>(smem + kSmemW + kSmemA);                 // b2, b3, ln_s, ln_o [128] each
   int* sBaseAll = reinterpret_cast<int*>(smem + kSmemW + kSmemA + 2048);          // [groups][4]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemW + kSmemA + 2048 + 64);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kGroups);
+  uint64_t* tbar = mbar + kGroups;  // per group: completion of the TMA loads of the edge-state tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbar + kGroups);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -335,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   }
   if (tid == 0) {
     for (int i = 0; i < kGroups; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+    for (int i = 0; i < kGroups; ++i) mbar_init(smem_u32(&tbar[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -352,7 +379,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   const uint32_t sA_addr = smem_u32(sA);
   const uint32_t sW_addr = smem_u32(sW);
   const uint32_t mbar_addr = smem_u32(&mbar[g]);
-  uint32_t parity = 0;
+  const uint32_t tbar_addr = smem_u32(&tbar[g]);
+  uint32_t parity = 0, tparity = 0;
 #ifdef PST_EDGE_PROFILE
   unsigned long long prof_acc[16] = {0};
   long long prof_last = clock64();
@@ -413,14 +441,26 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
           raw[i] = __ldg(p.senders + min(ra, p.E - 1));
         }
       }
+      // + the receiver's row: a tile touches at most 4 receivers (K >= 43), this thread needs 16 B of each.
+      // Shared-memory / L1 data-pipe traffic is what bounds this kernel (ncu: l1tex data-pipe wavefronts 53-70 %
+      // of peak), so the row is NOT re-read per edge row: 4 small loads per thread, selected by row position.
+      uint4 brow[4];
+      {
+        const uint4* pr4 = reinterpret_cast<const uint4*>(p.pr) + c16;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) *reinterpret_cast<uint4*>(sA + offA + it * 1024) = a[it];
-    }
-    uint4 prow[16];
-    {
-      const uint4* prr = reinterpret_cast<const uint4*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
+        for (int s4 = 0; s4 < 4; ++s4) brow[s4] = __ldg(pr4 + (size_t)min(first_recv + s4, last_recv) * (kD / 8));
+      }
+      const int t1 = (first_recv + 1) * p.K - row0, t2 = t1 + p.K, t3 = t2 + p.K;  // first tile row of receiver 1, 2, 3
 #pragma unroll
-      for (int j = 0; j < 16; ++j) prow[j] = __ldg(prr + j);
+      for (int it = 0; it < 16; ++it) {
+        const int row = it * 8 + sub;
+        uint4 bb = brow[0];
+        if (row >= t1) bb = brow[1];
+        if (row >= t2) bb = brow[2];
+        if (row >= t3) bb = brow[3];
+        *reinterpret_cast<uint4*>(sA + offA + it * 1024) =
+            make_uint4(hadd2u(a[it].x, bb.x), hadd2u(a[it].y, bb.y), hadd2u(a[it].z, bb.z), hadd2u(a[it].w, bb.w));
+      }
     }
     {
       const int nt = tile + gridDim.x * kGroups;
@@ -433,53 +473,42 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
           const uint32_t hi = rb < p.E ? (uint32_t)(raw[2 * i + 1] - nbase) : 0u;
           nidx[i] = lo | (hi << 16);
         }
-        // warm L2 with the next tile's rows
-        const char* nxt = reinterpret_cast<const char*>(p.e + (size_t)nrow0 * kD) + gt * 256;
-        if ((size_t)nrow0 + gt < (size_t)p.E) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
+        if (gt == 0) {  // warm L2 with the next tile's rows
+          tma_prefetch_2d(&tmap_e, 0, nrow0);
+          tma_prefetch_2d(&tmap_e, 64, nrow0);
         }
       }
     }
     group_sync(g);
     PHASE(1);
     {
-      // accumulator row <- sender row (staged) + receiver row (the same for K consecutive edges)
-#pragma unroll
+      // accumulator row <- staged addend row
+#pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         float2 v[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 a = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
-          const uint4 b = prow[q * 4 + j];
-          v[j * 4 + 0] = Unpack<__half>::two(hadd2u(a.x, b.x));
-          v[j * 4 + 1] = Unpack<__half>::two(hadd2u(a.y, b.y));
-          v[j * 4 + 2] = Unpack<__half>::two(hadd2u(a.z, b.z));
-          v[j * 4 + 3] = Unpack<__half>::two(hadd2u(a.w, b.w));
+          v[j * 4 + 0] = Unpack<__half>::two(a.x);
+          v[j * 4 + 1] = Unpack<__half>::two(a.y);
+          v[j * 4 + 2] = Unpack<__half>::two(a.z);
+          v[j * 4 + 3] = Unpack<__half>::two(a.w);
         }
         tmem_st32v(tmem_row + q * 32, v);
       }
     }
-    group_sync(g);
-    PHASE(2);
-    // ---- 1. e tile (16-bit, global) -> A image: 16-byte copies, 16 threads per row, 8 rows per pass ----
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
-      uint4 x[16];
-#pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        x[it] = make_uint4(0, 0, 0, 0);
-        if (it * 8 + sub < last_row) x[it] = src[(size_t)it * 8 * (kD / 8)];
-      }
-#pragma unroll
-      for (int it = 0; it < 16; ++it) *reinterpret_cast<uint4*>(sA + offA + it * 1024) = x[it];
-    }
-    fence_proxy_async();
     tc_fence_before();
     group_sync(g);
+    PHASE(2);
+    // ---- 1. e tile (16-bit, global) -> A image by TMA (rows beyond E are zero-filled); 2. GEMM 1: acc += e . W1[256:384].
+    // Only the issuing thread waits for the copy: the others go straight to the GEMM's barrier.
+    if (gt == 0) {
+      tma_tile_load(sA_addr, &tmap_e, row0, tbar_addr);
+      mbar_wait(tbar_addr, tparity);
+      issue_gemm(tmem_acc, sA_addr, sW_addr, p.idesc, mbar_addr, /*accumulate_first=*/1u);
+    }
+    tparity ^= 1;
     PHASE(3);
-    // ---- 2. GEMM 1: acc += e . W1[256:384] -----------------------------------------------------------
-    if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr, p.idesc, mbar_addr, /*accumulate_first=*/1u);
     mbar_wait(mbar_addr, parity);
     parity ^= 1;
     tc_fence_after();
@@ -526,20 +555,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       parity ^= 1;
       tc_fence_after();
       PHASE(8);
-      // pass 1: x = acc + b3 + e.  The tile is re-read row-coalesced (an L2 hit) into the free A buffer,
-      // in the operand image layout, so each thread finds its own row conflict-free; statistics; x -> TMEM.
-      {
-        const uint4* src = reinterpret_cast<const uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
-        uint4 x[16];
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          x[it] = make_uint4(0, 0, 0, 0);
-          if (it * 8 + sub < last_row) x[it] = src[(size_t)it * 8 * (kD / 8)];
-        }
-#pragma unroll
-        for (int it = 0; it < 16; ++it) *reinterpret_cast<uint4*>(sA + offA + it * 1024) = x[it];
-      }
-      group_sync(g);
+      // pass 1: x = acc + b3 + e.  The tile is re-read (an L2 hit) by TMA into the free A buffer, in the operand
+      // image layout, so each thread finds its own row conflict-free; statistics; x -> TMEM.
+      if (gt == 0) tma_tile_load(sA_addr, &tmap_e, row0, tbar_addr);
+      mbar_wait(tbar_addr, tparity);
+      tparity ^= 1;
       PHASE(9);
       float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll 1
@@ -585,15 +605,15 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         }
         store_a_chunk2<T16>(sA, gt, q * 32, v);
       }
+      fence_proxy_async();
       group_sync(g);
       PHASE(11);
-      {
-        uint4* dst = reinterpret_cast<uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
-#pragma unroll 8
-        for (int it = 0; it < 16; ++it)
-          if (it * 8 + sub < last_row) dst[(size_t)it * 8 * (kD / 8)] = *reinterpret_cast<const uint4*>(sA + offA + it * 1024);
+      if (gt == 0) {  // TMA store of the new edge state (rows beyond E are clipped); the buffer is reused afterwards
+        tma_store_2d(&tmap_e, 0, row0, sA_addr);
+        tma_store_2d(&tmap_e, 64, row0, sA_addr + kKBlockBytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
-      group_sync(g);
       PHASE(12);
     } else {
       // ---- 5b. epilogue 2 (message mode): + b2, GELU, partial sums over the rows of each receiver ------
@@ -657,6 +677,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   if (tid == 0)
     for (int i = 0; i < 16; ++i) atomicAdd(&g_edge_prof[MODE][i], prof_acc[i]);
 #endif
+  if (MODE == 1 && gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the TMA stores have landed
 
   tc_fence_before();
   __syncthreads();
@@ -930,6 +951,30 @@ size_t pst_tc_partial_floats(int R, int K) {
   return tiles * 4 * kD;
 }
 
+// Tensor map of the 16-bit edge state [E, 128]: boxes of [128 rows x 64 columns], SWIZZLE_128B (= one K block of
+// the operand image).  cuTensorMapEncodeTiled is a driver entry point; it is fetched through the runtime so that
+// the library does not link libcuda.
+typedef CUresult (*PstEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_edge_state_map(const uint16_t* e, int E, CUtensorMap* out) {
+  static PstEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return PST_ERR_CUDA;
+    fn = reinterpret_cast<PstEncodeTiledFn>(sym);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)E};
+  const cuuint64_t strides[1] = {(cuuint64_t)kD * sizeof(uint16_t)};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)kTileM};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t*>(e), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? PST_OK : PST_ERR_CUDA;
+}
+
 // mode 0: writes tbar (mean over K of the 2nd hidden layer) into agg_out[R,128]; the caller applies W3, b3.
 // mode 1: e <- LN(e + MLP).
 int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e, const uint16_t* ps,
@@ -958,18 +1003,20 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   p.idesc_sum = (1u << 4) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(kD >> 4) << 24);
   if (p.num_tiles == 0) return 0;
   if (K < 43) return PST_ERR_UNSUPPORTED_CONFIG;  // a 128-row tile must touch at most 4 receivers
+  CUtensorMap tmap;
+  if (int rc = make_edge_state_map(e, p.E, &tmap)) return rc;
+  const bool half = m->cfg.precision == PST_PREC_FP16;
   int grid = m->num_sms;
   const int need = (p.num_tiles + kGroups - 1) / kGroups;
   if (grid > need) grid = need;
-  const bool half = m->cfg.precision == PST_PREC_FP16;
   if (mode == 0) {
-    if (half) edge_mlp_tc_kernel<__half, 0><<<grid, kThreads, kSmemTotal, st>>>(p);
-    else edge_mlp_tc_kernel<__nv_bfloat16, 0><<<grid, kThreads, kSmemTotal, st>>>(p);
+    if (half) edge_mlp_tc_kernel<__half, 0><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
+    else edge_mlp_tc_kernel<__nv_bfloat16, 0><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
     combine_partials_kernel<<<(R + 7) / 8, 256, 0, st>>>(partial, K, R, agg_out);
     return 2;
   }
-  if (half) edge_mlp_tc_kernel<__half, 1><<<grid, kThreads, kSmemTotal, st>>>(p);
-  else edge_mlp_tc_kernel<__nv_bfloat16, 1><<<grid, kThreads, kSmemTotal, st>>>(p);
+  if (half) edge_mlp_tc_kernel<__half, 1><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
+  else edge_mlp_tc_kernel<__nv_bfloat16, 1><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
   return 1;
 }
 
