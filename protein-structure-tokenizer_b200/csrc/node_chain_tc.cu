@@ -40,6 +40,7 @@ constexpr uint32_t kImgBlk = 16384;        // [128 x 64] fp16 K-major SWIZZLE_12
 constexpr uint32_t kSlotBytes = 2 * kImgBlk;  // weight half-unit: hi image, lo image of one K block
 constexpr uint32_t kSetBytes = 2 * kSlotBytes;  // activation image set: [kb][hi, lo]
 constexpr int kSlots = 3;
+constexpr int kCluster = 2;  // CTAs per cluster: each weight half-unit is fetched from L2 once per cluster and multicast
 constexpr uint32_t kOffX = 0, kOffU = kSetBytes, kOffW = 2 * kSetBytes;
 constexpr uint32_t kOffBar = kOffW + kSlots * kSlotBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 128 + 2 * 2 * 128 * 4;  // barriers + TMEM slot, row-statistics exchange
@@ -67,6 +68,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(mbar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(mbar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -84,6 +100,11 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, ui
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
       "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in every CTA of the cluster
+__device__ __forceinline__ void umma_commit_mc(uint32_t mbar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
@@ -169,19 +190,27 @@ __device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tme
       umma(tmem_acc, make_desc(a_hi + o), make_desc(w_lo + o), idesc, 1u);
       umma(tmem_acc, make_desc(a_lo + o), make_desc(w_hi + o), idesc, 1u);
     }
-    umma_commit(r.empty + slot * 8);
+    umma_commit_mc(r.empty + slot * 8, (uint16_t)((1u << kCluster) - 1));  // the slot is refilled for the whole cluster
     ++r.n;
   }
   umma_commit(done_bar);
 }
 
+// Weight streaming, cluster-cooperative: every CTA of the cluster runs the same schedule in lock step.  For each
+// half-unit (32 KB) CTA `rank` fetches its 1/kCluster slice from L2 and multicasts it into the same ring slot of
+// every CTA; each CTA's full barrier therefore collects kCluster slices.  A slot is refilled only when every CTA has
+// released it: the empty barriers count kCluster arrivals (multicast tcgen05.commit).  Without this, all 148 SMs
+// pull the same 64 KB per 128 x 128 product from a few L2 slices, which bounds the kernel.
 __device__ __forceinline__ void producer_loop(Ring r, const uint8_t* const* sched, int n_sched, int my_tiles) {
+  const uint32_t rank = cluster_ctarank();
+  constexpr uint32_t kSlice = kSlotBytes / kCluster;
   for (int t = 0; t < my_tiles; ++t)
     for (int i = 0; i < n_sched; ++i) {
       const uint32_t slot = r.n % kSlots;
       if (r.n >= kSlots) mbar_wait(r.empty + slot * 8, ((r.n / kSlots) - 1) & 1);
       mbar_expect_tx(r.full + slot * 8, kSlotBytes);
-      bulk_g2s(r.wbase + slot * kSlotBytes, sched[i], kSlotBytes, r.full + slot * 8);
+      bulk_g2s_mc(r.wbase + slot * kSlotBytes + rank * kSlice, sched[i] + rank * kSlice, kSlice, r.full + slot * 8,
+                  (uint16_t)((1u << kCluster) - 1));
       ++r.n;
     }
 }
@@ -260,7 +289,7 @@ __device__ __forceinline__ void add_bias_half(const Epi& e, float (&x)[2][32], c
 struct Setup {
   uint8_t* smem;
   uint32_t tmem_base;
-  uint32_t bar_done[2];
+  uint32_t bar_done[4];
   Ring ring;
   float* red;
 };
@@ -268,10 +297,10 @@ struct Setup {
 __device__ __forceinline__ Setup chain_setup(uint8_t* smem, int tid, int warp) {
   Setup s;
   s.smem = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);  // full[3], empty[3], done[2], tmem slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);  // full[3], empty[3], done[4], tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   if (tid == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < 10; ++i) mbar_init(smem_u32(&bars[i]), (i >= 3 && i < 6) ? kCluster : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -280,14 +309,14 @@ __device__ __forceinline__ Setup chain_setup(uint8_t* smem, int tid, int warp) {
   }
   tc_before();
   __syncthreads();
+  cluster_sync();  // every CTA's barriers exist before a peer multicasts into them
   tc_after();
   s.tmem_base = *tmem_slot;
   s.ring.full = smem_u32(&bars[0]);
   s.ring.empty = smem_u32(&bars[3]);
   s.ring.wbase = smem_u32(smem + kOffW);
   s.ring.n = 0;
-  s.bar_done[0] = smem_u32(&bars[6]);
-  s.bar_done[1] = smem_u32(&bars[7]);
+  for (int i = 0; i < 4; ++i) s.bar_done[i] = smem_u32(&bars[6 + i]);
   s.red = reinterpret_cast<float*>(smem + kOffBar + 128);
   return s;
 }
@@ -295,24 +324,25 @@ __device__ __forceinline__ Setup chain_setup(uint8_t* smem, int tid, int warp) {
 __device__ __forceinline__ void chain_teardown(const Setup& s, int warp) {
   tc_before();
   __syncthreads();
+  cluster_sync();  // no CTA leaves while a peer may still multicast into its shared memory / barriers
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "r"(512u) : "memory");
 }
 
-// MMA groups: every epilogue thread counts them, thread 0 issues.  Group i commits to done[i & 1] and the threads
-// wait for the groups in issue order, so each barrier has at most one unobserved completion (at most two groups
-// are ever in flight).
+// MMA groups: every epilogue thread counts them, thread 0 issues.  Group i commits to done[i & 3] and the threads
+// wait for the groups in issue order, so each barrier has at most one unobserved completion as long as no more than
+// four groups are in flight.
 struct Groups {
   Ring ring;
-  uint32_t bar_done[2];
+  uint32_t bar_done[4];
   uint32_t idesc;
   uint32_t n_issued = 0, n_waited = 0;
   int tid;
   __device__ __forceinline__ void issue(uint32_t a_set, uint32_t acc, uint32_t accumulate) {
-    if (tid == 0) issue_unit(ring, a_set, acc, accumulate, idesc, bar_done[n_issued & 1]);
+    if (tid == 0) issue_unit(ring, a_set, acc, accumulate, idesc, bar_done[n_issued & 3]);
     ++n_issued;
   }
   __device__ __forceinline__ void wait_next() {
-    mbar_wait(bar_done[n_waited & 1], (n_waited >> 1) & 1);
+    mbar_wait(bar_done[n_waited & 3], (n_waited >> 2) & 1);
     ++n_waited;
     tc_after();
   }
@@ -325,30 +355,47 @@ __device__ __forceinline__ void publish() {
 }
 
 // y = act(X . W1[:, c] + b1[c]) . W2[c, :] accumulated over `chunks` 128-wide chunks of the hidden layer.
-// X: image set of the input (already published); U: scratch image set; result in acc_out (waited for on return).
+// X: image set of the input (already published); U: scratch image set; accH[2]: two hidden accumulators.
+// Software pipeline: the first-layer products run two chunks ahead into alternating accumulators, and the
+// activation of chunk c is computed in registers while the tensor core still reads U for chunk c - 1; only the
+// store into U waits for it.  Issue order F1(0) F1(1) F2(0) F1(2) F2(1) ... == wait order.  Result in acc_out
+// (complete on return).  NOTE the schedule of weight half-units must list the units in this issue order.
 template <int ACT>  // 1 gelu(tanh), 2 relu
 __device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_addr, uint8_t* U, uint32_t U_addr,
-                                            uint32_t acc_hidden, uint32_t acc_out, int chunks, const float* __restrict__ b1) {
-  G.issue(X_addr, acc_hidden, 0u);
+                                            uint32_t accH0, uint32_t accH1, uint32_t acc_out, int chunks,
+                                            const float* __restrict__ b1) {
+  G.issue(X_addr, accH0, 0u);
+  if (chunks > 1) G.issue(X_addr, accH1, 0u);
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
-    G.wait_next();  // X . W1[:, c]   (groups complete in order: U is free as well)
+    float bv[2][32];
+    {
+      const float* b = b1 + c * 128 + e.half * 64;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(b + q * 32) + j);
+          bv[q][j * 4] = t.x; bv[q][j * 4 + 1] = t.y; bv[q][j * 4 + 2] = t.z; bv[q][j * 4 + 3] = t.w;
+        }
+    }
+    G.wait_next();  // X . W1[:, c]
     float v[2][32];
-    tmem_ld_half(e, acc_hidden, v);
-    const float* b = b1 + c * 128 + e.half * 64;
+    tmem_ld_half(e, (c & 1) ? accH1 : accH0, v);
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float t = v[q][j] + __ldg(b + q * 32 + j);
+        const float t = v[q][j] + bv[q][j];
         v[q][j] = ACT == 1 ? gelu_tanh(t) : fmaxf(t, 0.f);
       }
+    if (c > 0) G.wait_next();  // u_{c-1} . W2[c-1, :] has read U
     split_store_half(e, U, v);
     publish();
     G.issue(U_addr, acc_out, c > 0 ? 1u : 0u);
-    if (c + 1 < chunks) G.issue(X_addr, acc_hidden, 0u);
-    G.wait_next();  // u_c . W2[c, :]
+    if (c + 2 < chunks) G.issue(X_addr, (c & 1) ? accH1 : accH0, 0u);
   }
+  G.wait_next();  // last second-layer product
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -368,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
   if (warp == kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
     __syncwarp();
@@ -380,9 +427,9 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
   const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
   Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
   const uint32_t t_acc0 = S.tmem_base + 0, t_h1 = S.tmem_base + 128, t_acc1 = S.tmem_base + 256, t_acc2 = S.tmem_base + 384;
-  Groups G{S.ring, {S.bar_done[0], S.bar_done[1]}, p.idesc, 0, 0, tid};
+  Groups G{S.ring, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, p.idesc, 0, 0, tid};
 
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+  for (int ti = 0, tile = blockIdx.x; ti < my_tiles; ++ti, tile += gridDim.x) {  // tiles past the end: all rows invalid
     const int row = tile * 128 + e.row;
     const bool valid = row < p.R;
     float x[2][32];
@@ -408,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
     split_store_half(e, X, x);
     publish();
     // ---- 3. FFN 128 -> 512 -> 128 (gnn_layers.py:385-394), hidden chunked 4 x 128 ---------------------------------
-    chunked_mlp<1>(G, e, X_addr, U, U_addr, t_acc1, t_acc2, 4, p.ffn_b1);
+    chunked_mlp<1>(G, e, X_addr, U, U_addr, t_acc1, t_acc0, t_acc2, 4, p.ffn_b1);
     // ---- 4. h2 = LN1(h1 + ffn + b2) -> global h, X images ------------------------------------------------------
     {
       float h1[2][32];
@@ -488,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
   if (warp == kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
     __syncwarp();
@@ -500,9 +547,9 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
   const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
   Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
   const uint32_t t_res = S.tmem_base + 0, t_orig = S.tmem_base + 128, t_accA = S.tmem_base + 256, t_accB = S.tmem_base + 384;
-  Groups G{S.ring, {S.bar_done[0], S.bar_done[1]}, p.idesc, 0, 0, tid};
+  Groups G{S.ring, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, p.idesc, 0, 0, tid};
 
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+  for (int ti = 0, tile = blockIdx.x; ti < my_tiles; ++ti, tile += gridDim.x) {  // tiles past the end: all rows invalid
     const int row = tile * 128 + e.row;
     const bool valid = row < p.R;
     float x[2][32];
@@ -558,10 +605,10 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
       layer_norm_row(e, x, w.rt_ln_s, w.rt_ln_o);
       split_store_half(e, X, x);
       publish();
-      chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, 2, w.rt_b1);
+      chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accA, 2, w.rt_b1);  // 2 chunks: the output reuses accA
       {
         float r[2][32];
-        tmem_ld_half(e, t_accB, x);
+        tmem_ld_half(e, t_accA, x);
         tmem_ld_half(e, t_res, r);
         const float* b2 = w.rt_b2 + e.half * 64;
 #pragma unroll
@@ -576,9 +623,9 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
         layer_norm_row(e, x, w.ot_ln_s, w.ot_ln_o);
         split_store_half(e, X, x);
         publish();
-        chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, 2, w.ot_b1);
+        chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accA, 2, w.ot_b1);
         float r[2][32];
-        tmem_ld_half(e, t_accB, x);
+        tmem_ld_half(e, t_accA, x);
         tmem_ld_half(e, t_orig, r);
         const float* b2 = w.ot_b2 + e.half * 64;
 #pragma unroll
@@ -651,6 +698,27 @@ struct PstNodeChain {
   int resampler_off = 0, resampler_n = 0;
 };
 
+// persistent grid of whole clusters: one CTA per SM, at most one per tile
+template <typename P>
+static int launch_clustered(void (*kernel)(P), const pst_model* m, cudaStream_t st, int num_tiles, const P& p) {
+  int grid = m->num_sms < num_tiles ? m->num_sms : num_tiles;
+  grid = (grid + kCluster - 1) / kCluster * kCluster;
+  if (grid > m->num_sms) grid = m->num_sms / kCluster * kCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, p) == cudaSuccess ? 1 : PST_ERR_CUDA;
+}
+
 int pst_prepare_node_chain(pst_model* m) {
   m->node_chain = new PstNodeChain();
   PstNodeChain& C = *m->node_chain;
@@ -668,15 +736,21 @@ int pst_prepare_node_chain(pst_model* m) {
       all.push_back(p);
     }
   };
+  // units of a chunked MLP in the issue order of chunked_mlp(): F1(0) F1(1) F2(0) F1(2) F2(1) ... F2(n-1)
+  auto push_chunked = [&](const float* W1, const float* W2, int hidden, int chunks) {
+    push_unit(W1, D, hidden, 0, 0);
+    if (chunks > 1) push_unit(W1, D, hidden, 0, 1);
+    for (int c = 0; c < chunks; ++c) {
+      push_unit(W2, hidden, D, c, 0);
+      if (c + 2 < chunks) push_unit(W1, D, hidden, 0, c + 2);
+    }
+  };
   const int L = m->cfg.gnn_layers;
   for (int l = 0; l < L; ++l) {
     const PstLayerW& w = m->w.layer[l];
     C.layer_off[l] = (int)all.size();
     push_unit(w.msg_w3, D, D, 0, 0);
-    for (int c = 0; c < 4; ++c) {
-      push_unit(w.ffn_w1, D, PST_FFN, 0, c);
-      push_unit(w.ffn_w2, PST_FFN, D, c, 0);
-    }
+    push_chunked(w.ffn_w1, w.ffn_w2, PST_FFN, 4);
     C.layer_nout[l] = 0;
     if (l < L - 1) {
       const PstLayerW& nx = m->w.layer[l + 1];
@@ -695,15 +769,8 @@ int pst_prepare_node_chain(pst_model* m) {
     push_unit(w.wg, D, D, 0, 0);
     push_unit(w.wv, D, D, 0, 0);
     push_unit(w.wo, D, D, 0, 0);
-    for (int c = 0; c < 2; ++c) {
-      push_unit(w.rt_w1, D, PST_TRANS, 0, c);
-      push_unit(w.rt_w2, PST_TRANS, D, c, 0);
-    }
-    if (b < m->cfg.num_blocks - 1)
-      for (int c = 0; c < 2; ++c) {
-        push_unit(w.ot_w1, D, PST_TRANS, 0, c);
-        push_unit(w.ot_w2, PST_TRANS, D, c, 0);
-      }
+    push_chunked(w.rt_w1, w.rt_w2, PST_TRANS, 2);
+    if (b < m->cfg.num_blocks - 1) push_chunked(w.ot_w1, w.ot_w2, PST_TRANS, 2);
   }
   C.resampler_n = (int)all.size() - C.resampler_off;
   if (!ok) return PST_ERR_BAD_ARGUMENT;
@@ -745,9 +812,7 @@ int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const
   p.R = R;
   p.num_tiles = (R + 127) / 128;
   p.idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  int grid = m->num_sms < p.num_tiles ? m->num_sms : p.num_tiles;
-  node_update_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
-  return 1;
+  return launch_clustered(node_update_kernel, m, st, p.num_tiles, p);
 }
 
 // z <- the whole resampler + head for downsampling_ratio == 1 (token t == residue t); h = node features after the GNN
@@ -768,7 +833,5 @@ int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h
   p.R = R;
   p.num_tiles = (R + 127) / 128;
   p.idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  int grid = m->num_sms < p.num_tiles ? m->num_sms : p.num_tiles;
-  resampler_df1_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
-  return 1;
+  return launch_clustered(resampler_df1_kernel, m, st, p.num_tiles, p);
 }
