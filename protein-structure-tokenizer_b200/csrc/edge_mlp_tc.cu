@@ -273,6 +273,12 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
   return fma2(hx, t, hx);
 }
 
+// 32-byte global load through the read-only path (LDG.E.256 on sm_100)
+__device__ __forceinline__ void ldg256(const uint32_t* ptr, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
 __device__ __forceinline__ uint32_t hadd2u(uint32_t a, uint32_t b) {
   const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
@@ -385,21 +391,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   unsigned long long prof_acc[16] = {0};
   long long prof_last = clock64();
 #endif
-  // gather indices of the first tile: sender row minus the base row of the tile's first receiver's structure
-  // (16 bits: a tile spans at most two structures), rows it*8 + sub, two per register
-  uint32_t nidx[8];
-  int nbase = 0;
+  // this thread's sender row (absolute) for its edge row of the first tile; fetched one tile ahead afterwards
+  int my_sender = 0;
   {
     const int t0 = blockIdx.x * kGroups + g;
-    const int nrow0 = t0 * kTileM;
-    if (t0 < p.num_tiles) nbase = __ldg(p.row_base + min(nrow0 / p.K, (p.E - 1) / p.K));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int ra = nrow0 + (2 * i) * 8 + sub, rb = ra + 8;
-      const uint32_t lo = (t0 < p.num_tiles && ra < p.E) ? (uint32_t)(__ldg(p.senders + ra) - nbase) : 0u;
-      const uint32_t hi = (t0 < p.num_tiles && rb < p.E) ? (uint32_t)(__ldg(p.senders + rb) - nbase) : 0u;
-      nidx[i] = lo | (hi << 16);
-    }
+    if (t0 < p.num_tiles) my_sender = __ldg(p.senders + min(t0 * kTileM + gt, p.E - 1));
   }
 
   for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
@@ -409,101 +405,51 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     const int first_recv = row0 / p.K;
     const int last_row = min(p.E - row0, kTileM);  // valid rows in this tile
     const int last_recv = (p.E - 1) / p.K;
-    // gather indices of this tile were fetched during the previous tile (nidx, relative to row nbase)
     tc_fence_before();
     group_sync(g);
     tc_fence_after();
     PHASE(0);
-    // ---- 0. accumulator <- (h.W1a)[sender] + (h.W1b + b1)[receiver] -----------------------------------
-    // One row-coalesced gather pass (16 threads x 16 B per row): sender row of the fp16 table + receiver row
-    // (the same for 50 consecutive edges), summed and written as fp16 into the A buffer in the operand image
-    // layout; each thread then reads its own row and writes it into its accumulator row in TMEM.
-    int raw[16];
-    {
-      // Every load of the pass is issued before its batch is consumed (a loop-carried load -> store form makes
-      // ptxas serialise one L2 round trip per row).  Order: the 16 sender rows; the next tile's sender indices
-      // (raw, packed only after the stores so that their latency hides behind the row loads); stores; this
-      // thread's receiver row for the preload pass, issued before the barrier so that it lands while waiting.
-      const uint4* psb = reinterpret_cast<const uint4*>(p.ps) + (size_t)nbase * (kD / 8) + c16;
-      uint4 a[16];
-#pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const uint32_t d = (it & 1) ? (nidx[it >> 1] >> 16) : (nidx[it >> 1] & 0xffffu);
-        a[it] = __ldg(psb + (size_t)d * (kD / 8));
-      }
+    // ---- 0. The edge-state tile starts moving into the (free) A buffer by TMA; meanwhile
+    //         accumulator row <- (h.W1a)[sender] + (h.W1b + b1)[receiver]  straight from global memory:
+    // each thread owns one edge row (the TMEM 32x32b layout), reads its sender's 256-byte row of the fp16 table
+    // with eight 32-byte loads (whole sectors: the per-thread access is as efficient as a row-coalesced one) and
+    // the receiver's row (shared by K consecutive edges: L1 broadcast), adds and writes its accumulator row.
+    // No shared-memory staging, no barrier between gather and preload, and the TMA latency hides behind it.
+    if (gt == 0) {
+      tma_tile_load(sA_addr, &tmap_e, row0, tbar_addr);
       const int nt = tile + gridDim.x * kGroups;
-      const int nrow0 = nt * kTileM;
-      if (nt < p.num_tiles) {
-        nbase = __ldg(p.row_base + min(nrow0 / p.K, last_recv));
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int ra = nrow0 + i * 8 + sub;
-          raw[i] = __ldg(p.senders + min(ra, p.E - 1));
-        }
+      if (nt < p.num_tiles) {  // warm L2 with the next tile's rows
+        tma_prefetch_2d(&tmap_e, 0, nt * kTileM);
+        tma_prefetch_2d(&tmap_e, 64, nt * kTileM);
       }
-      // + the receiver's row: a tile touches at most 4 receivers (K >= 43), this thread needs 16 B of each.
-      // Shared-memory / L1 data-pipe traffic is what bounds this kernel (ncu: l1tex data-pipe wavefronts 53-70 %
-      // of peak), so the row is NOT re-read per edge row: 4 small loads per thread, selected by row position.
-      uint4 brow[4];
+    }
+    {
+      uint32_t a[64];
+      const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)my_sender * kD);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ldg256(psr + i * 8, &a[i * 8]);
+      const uint32_t* prr = reinterpret_cast<const uint32_t*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
       {
-        const uint4* pr4 = reinterpret_cast<const uint4*>(p.pr) + c16;
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) brow[s4] = __ldg(pr4 + (size_t)min(first_recv + s4, last_recv) * (kD / 8));
+        const int nt = tile + gridDim.x * kGroups;
+        if (nt < p.num_tiles) my_sender = __ldg(p.senders + min(nt * kTileM + gt, p.E - 1));
       }
-      const int t1 = (first_recv + 1) * p.K - row0, t2 = t1 + p.K, t3 = t2 + p.K;  // first tile row of receiver 1, 2, 3
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int row = it * 8 + sub;
-        uint4 bb = brow[0];
-        if (row >= t1) bb = brow[1];
-        if (row >= t2) bb = brow[2];
-        if (row >= t3) bb = brow[3];
-        *reinterpret_cast<uint4*>(sA + offA + it * 1024) =
-            make_uint4(hadd2u(a[it].x, bb.x), hadd2u(a[it].y, bb.y), hadd2u(a[it].z, bb.z), hadd2u(a[it].w, bb.w));
-      }
-    }
-    {
-      const int nt = tile + gridDim.x * kGroups;
-      if (nt < p.num_tiles) {
-        const int nrow0 = nt * kTileM;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ra = nrow0 + (2 * i) * 8 + sub, rb = ra + 8;
-          const uint32_t lo = ra < p.E ? (uint32_t)(raw[2 * i] - nbase) : 0u;
-          const uint32_t hi = rb < p.E ? (uint32_t)(raw[2 * i + 1] - nbase) : 0u;
-          nidx[i] = lo | (hi << 16);
-        }
-        if (gt == 0) {  // warm L2 with the next tile's rows
-          tma_prefetch_2d(&tmap_e, 0, nrow0);
-          tma_prefetch_2d(&tmap_e, 64, nrow0);
-        }
-      }
-    }
-    group_sync(g);
-    PHASE(1);
-    {
-      // accumulator row <- staged addend row
-#pragma unroll 1
       for (int q = 0; q < 4; ++q) {
+        uint32_t b[16];
+        ldg256(prr + q * 16, &b[0]);
+        ldg256(prr + q * 16 + 8, &b[8]);
         float2 v[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 a = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
-          v[j * 4 + 0] = Unpack<__half>::two(a.x);
-          v[j * 4 + 1] = Unpack<__half>::two(a.y);
-          v[j * 4 + 2] = Unpack<__half>::two(a.z);
-          v[j * 4 + 3] = Unpack<__half>::two(a.w);
-        }
+        for (int c = 0; c < 16; ++c) v[c] = Unpack<__half>::two(hadd2u(a[q * 16 + c], b[c]));
         tmem_st32v(tmem_row + q * 32, v);
       }
     }
     tc_fence_before();
     group_sync(g);
     PHASE(2);
-    // ---- 1. e tile (16-bit, global) -> A image by TMA (rows beyond E are zero-filled); 2. GEMM 1: acc += e . W1[256:384].
-    // Only the issuing thread waits for the copy: the others go straight to the GEMM's barrier.
+    // ---- 1./2. GEMM 1: acc += e . W1[256:384] once the TMA copy of the e tile has landed (rows beyond E are
+    // zero-filled).  Only the issuing thread waits for the copy: the others go straight to the GEMM's barrier.
     if (gt == 0) {
-      tma_tile_load(sA_addr, &tmap_e, row0, tbar_addr);
       mbar_wait(tbar_addr, tparity);
       issue_gemm(tmem_acc, sA_addr, sW_addr, p.idesc, mbar_addr, /*accumulate_first=*/1u);
     }
