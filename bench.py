@@ -34,6 +34,9 @@ WORKLOADS = {
     "cfg2": (2, 256, 512, 4096, 1, 512),
     "cfg3": (3, 64, 1024, 64000, 1, 1024),
     "cfg4": (4, 256, 512, 64000, 4, 512),
+    # BASELINE configs[4] shape (length-bucketed 64-2048 residues, sharded by structure): a per-GPU pool of 224
+    # structures, lengths log-uniform on [64, 2048] snapped to multiples of 64, ragged batch
+    "cfg5": (5, 224, None, 64000, 1, 2048),
 }
 # algorithmic work per valid residue (reference formulation, live ops, 2*MAC)
 FLOP_PER_RESIDUE = {1: 44.91e6, 2: 44.6e6, 4: 44.39e6}
@@ -103,7 +106,13 @@ def make_batch(workload: str, rank: int):
 
     idx, n_struct, length, codebook, df, seq_max = WORKLOADS[workload]
     t0 = time.time()
-    bbs = syn.make_backbones(SEED + idx + 1000 * rank, [length] * n_struct, group=n_struct)
+    if length is None:
+        rng = np.random.default_rng(SEED + idx + 1000 * rank)
+        lens = np.exp(rng.uniform(np.log(64), np.log(2048), n_struct))
+        lengths = [int(min(2048, max(64, 64 * round(float(v) / 64)))) for v in lens]
+    else:
+        lengths = [length] * n_struct
+    bbs = syn.make_backbones(SEED + idx + 1000 * rank, lengths, group=n_struct)
     atoms, offsets = syn.pack_backbones(bbs)
     return bbs, atoms, offsets, (codebook, df, seq_max), time.time() - t0
 
@@ -321,7 +330,8 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp16": "f16 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate", "fp32": "f32"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": f"{workload}: {B}x{R // B}-residue synthetic backbones per GPU, codebook {codebook}, df={df}, "
+            "config": {"workload": f"{workload}: {B} synthetic backbones per GPU, {R} residues "
+                                   f"(lengths {int(np.diff(offsets).min())}..{int(np.diff(offsets).max())}), codebook {codebook}, df={df}, "
                                    f"K=50, random-init 'spread' weights", "precision": args.precision,
                        "l2": "working set per step (edge state 3.3 GB) far exceeds the 126 MB L2; no explicit flush",
                        "distinct_codes": distinct, "gen_seconds": round(gen_s, 1)},
