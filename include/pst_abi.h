@@ -50,7 +50,10 @@ typedef enum pst_status {
   PST_ERR_WORKSPACE_TOO_SMALL = -4,
   PST_ERR_CUDA = -5,
   PST_ERR_NO_DEVICE = -6,
-  PST_ERR_BAD_WEIGHTS = -7
+  PST_ERR_BAD_WEIGHTS = -7,
+  PST_ERR_PDB_MODEL_COUNT = -8,     /* the file does not hold exactly one model */
+  PST_ERR_PDB_INSERTION_CODE = -9,  /* a residue carries an insertion code */
+  PST_ERR_PDB_MALFORMED = -10       /* an ATOM / HETATM record is too short or has non-numeric fields */
 } pst_status;
 
 /* GEMM operand precision of the edge-level MLPs (accumulation is always fp32;
@@ -143,6 +146,16 @@ int pst_tokenize(const pst_model* model, void* stream, const float* atoms,
                  const uint8_t* atom_mask, int atoms_per_residue, const int32_t* offsets,
                  const int32_t* token_offsets, int num_structures, int total_residues,
                  int total_tokens, int32_t* tokens_out, void* workspace, size_t workspace_bytes);
+
+/* HOST function (no CUDA): PDB text -> atom37 arrays.  Replaces protein_structure_from_pdb_string
+ * (structure_tokenizer/data/protein_structure_sample.py:166-248) together with the BioPython PDBParser semantics it
+ * relies on (single model, chains and residues in order of first appearance, highest-occupancy altloc, atoms
+ * outside atom37 dropped, unknown residues -> UNK, insertion codes rejected).  Outputs are caller-owned host
+ * arrays with room for max_residues residues: positions f32 [max,37,3], gt_exists / atom_exists u8 [max,37],
+ * aatype i32 [max] (20 = UNK).  Call with the array pointers NULL to get *n_residues_out only.
+ * Returns PST_OK, PST_ERR_PDB_* or PST_ERR_WORKSPACE_TOO_SMALL (n_residues_out is then the needed count). */
+int pst_parse_pdb(const char* text, size_t text_bytes, int max_residues, float* atom37_positions,
+                  uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out);
 
 /* Device status word raised by kernels (0 = fine, PST_ERR_LENGTH_OUT_OF_RANGE ...).
  * Synchronises `stream`; not part of the hot path. */

@@ -21,6 +21,7 @@ SOURCES = {
     "node_chain_tc.cu": [],
     "quantize.cu": [],
     "api.cu": [],
+    "pdb_parse.cc": [],  # host-only C++ (PDB ingest)
 }
 
 
@@ -40,7 +41,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
         return OUT
     objs = []
     for src, extra in SOURCES.items():
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc(), *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

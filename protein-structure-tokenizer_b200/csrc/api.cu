@@ -141,6 +141,9 @@ const char* pst_status_string(int status) {
     case PST_ERR_CUDA: return "CUDA error";
     case PST_ERR_NO_DEVICE: return "no CUDA device";
     case PST_ERR_BAD_WEIGHTS: return "weight blob has the wrong size";
+    case PST_ERR_PDB_MODEL_COUNT: return "Only single model PDBs are supported";
+    case PST_ERR_PDB_INSERTION_CODE: return "PDB contains an insertion code; these are not supported";
+    case PST_ERR_PDB_MALFORMED: return "malformed ATOM / HETATM record";
     default: return "unknown status";
   }
 }

@@ -9,6 +9,8 @@ LIB_NAME = "libpst_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 PST_ABI_VERSION = 1
+PST_ERR_WORKSPACE_TOO_SMALL = -4
+PST_ERR_PDB_MODEL_COUNT, PST_ERR_PDB_INSERTION_CODE, PST_ERR_PDB_MALFORMED = -8, -9, -10
 PST_MAX_LEVELS = 8
 
 
@@ -45,6 +47,7 @@ SIGNATURES = {
     "pst_indexes_to_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pst_tokenize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pst_parse_pdb": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "pst_read_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pst_last_launch_count": (C.c_int, [C.c_void_p]),
     "pst_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

@@ -28,7 +28,7 @@ from typing import Any, Callable, List, Optional, Sequence
 import numpy as np
 
 from .config import TokenizerConfig
-from .pdb import structure_from_pdb_file
+from .pdb import structure_from_pdb_file_native as structure_from_pdb_file  # C++ parser behind the C ABI (pst_parse_pdb)
 from .weights import init_params, load_params_npz
 
 

