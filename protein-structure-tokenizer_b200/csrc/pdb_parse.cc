@@ -61,6 +61,19 @@ int atom_slot(const std::string& name) {
     if (name == kAtomTypes[i]) return i;
   return -1;
 }
+// the same for a fixed-column field, without allocating
+int atom_slot_field(const char* s, size_t n) {
+  size_t a = 0, b = n;
+  while (a < b && s[a] == ' ') ++a;
+  while (b > a && s[b - 1] == ' ') --b;
+  const size_t m = b - a;
+  if (m == 0 || m > 3) return -1;
+  for (int i = 0; i < 37; ++i) {
+    const char* t = kAtomTypes[i];
+    if (strlen(t) == m && memcmp(t, s + a, m) == 0) return i;
+  }
+  return -1;
+}
 
 std::string strip(const char* s, size_t n) {
   size_t a = 0, b = n;
@@ -70,7 +83,35 @@ std::string strip(const char* s, size_t n) {
 }
 
 // float(field): Python's float() of a fixed-column field, rounded to float32 like np.float32(str)
+// Fast path for plain fixed-point fields ("  -12.345"): mantissa / 10^k with both exactly representable in a double
+// is one correctly rounded division, i.e. the same double strtod (and Python's float()) returns.
 bool parse_float(const char* s, size_t n, float* out) {
+  {
+    size_t a = 0, b = n;
+    while (a < b && s[a] == ' ') ++a;
+    while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\r')) --b;
+    if (a < b) {
+      bool neg = false;
+      size_t i = a;
+      if (s[i] == '-' || s[i] == '+') { neg = s[i] == '-'; ++i; }
+      unsigned long long mant = 0;
+      int digits = 0, frac = -1;
+      bool ok = i < b;
+      for (; i < b; ++i) {
+        const char c = s[i];
+        if (c >= '0' && c <= '9') { mant = mant * 10 + (unsigned)(c - '0'); ++digits; if (frac >= 0) ++frac; }
+        else if (c == '.' && frac < 0) frac = 0;
+        else { ok = false; break; }
+      }
+      if (ok && digits > 0 && digits <= 15) {
+        static const double p10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+        double v = (double)mant;
+        if (frac > 0) v /= p10[frac];
+        *out = static_cast<float>(neg ? -v : v);
+        return true;
+      }
+    }
+  }
   std::string t = strip(s, n);
   if (t.empty()) return false;
   char* end = nullptr;
@@ -101,7 +142,9 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
   if (!text || !n_residues_out) return PST_ERR_BAD_ARGUMENT;
   *n_residues_out = 0;
   std::vector<Residue> residues;
-  std::unordered_map<std::string, int> index;  // residue id -> position in `residues`
+  std::unordered_map<unsigned long long, int> index;  // residue id -> position in `residues`
+  unsigned long long last_key = ~0ull;
+  int last_idx = -1;
   std::string chain_order;
   int models = 0;
   bool in_model = false, loose_atoms = false;
@@ -125,17 +168,29 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
     const long resseq = std::strtol(resseq_s.c_str(), &end, 10);
     if (resseq_s.empty() || *end != '\0') return PST_ERR_PDB_MALFORMED;
     const char icode = line[26];
-    std::string key(1, chain);
-    key += is_atom ? std::string(" ") : (resname == "HOH" || resname == "WAT" ? std::string("W") : "H_" + resname);
-    key += '|';
-    key += std::to_string(resseq);
-    key += icode;
-    auto it = index.find(key);
+    // residue id (chain, hetero flag, resseq, icode) packed into 64 bits: chain 8 | icode 8 | resseq + 2^15 16 |
+    // hetero kind 2 (0 ATOM, 1 water, 2 other HETATM) | the 3 resname characters 24 (other HETATM only)
+    unsigned long long key = ((unsigned long long)(unsigned char)chain << 56) | ((unsigned long long)(unsigned char)icode << 48) |
+                             ((unsigned long long)(unsigned)(resseq + 32768) << 32);
+    if (!is_atom) {
+      if (resname == "HOH" || resname == "WAT") key |= 1ull << 30;
+      else {
+        key |= 2ull << 30;
+        for (size_t i = 0; i < resname.size() && i < 3; ++i) key |= (unsigned long long)(unsigned char)resname[i] << (8 * i);
+      }
+    }
     Residue* res;
-    if (it == index.end()) {
+    int found = -1;
+    if (key == last_key) found = last_idx;
+    else {
+      auto it = index.find(key);
+      if (it != index.end()) found = it->second;
+    }
+    if (found < 0) {
       size_t rank = chain_order.find(chain);
       if (rank == std::string::npos) { rank = chain_order.size(); chain_order.push_back(chain); }
-      index.emplace(key, static_cast<int>(residues.size()));
+      found = static_cast<int>(residues.size());
+      index.emplace(key, found);
       residues.emplace_back();
       res = &residues.back();
       res->resname = resname;
@@ -145,9 +200,11 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
       res->chain_rank = static_cast<int>(rank);
       memset(res->atoms, 0, sizeof(res->atoms));
     } else {
-      res = &residues[it->second];
+      res = &residues[found];
     }
-    const int slot = atom_slot(strip(line + 12, 4));
+    last_key = key;
+    last_idx = found;
+    const int slot = atom_slot_field(line + 12, 4);
     if (slot < 0) continue;  // hydrogens and names outside atom37 are dropped
     float occ = 1.0f;
     if (n < 60 || !parse_float(line + 54, 6, &occ)) occ = 1.0f;
