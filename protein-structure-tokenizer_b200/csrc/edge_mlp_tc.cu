@@ -660,7 +660,7 @@ __device__ __forceinline__ uint32_t swz_k64(uint32_t row, uint32_t kk) {  // ele
 }
 
 template <typename T16>
-__global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams p) {
+__global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams p, const __grid_constant__ CUtensorMap tmap_e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sAall = smem + kEmbSmemW;
@@ -702,25 +702,40 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
     const int er = row0 + gt;
     const int last_row = min(p.E - row0, kTileM);
     // table row of this thread's edge: sender - receiver (local indices) + seq_max - 1
-    {
-      int t = 0;
-      if (er < p.E) {
-        const int recv = er / p.K;
-        t = __ldg(p.senders + er) - (recv - __ldg(p.row_base + recv)) + (p.seq_max - 1);
-      }
-      sTab[gt] = (uint16_t)t;
+    int trow = 0;
+    if (er < p.E) {
+      const int recv = er / p.K;
+      trow = __ldg(p.senders + er) - (recv - __ldg(p.row_base + recv)) + (p.seq_max - 1);
     }
     // ---- features -> fp16 hi / lo operand images (A_hi at K block 0, A_lo at K block 1 of the buffer) ----
     {
       const float* f0 = p.feat + (size_t)row0 * PST_EDGE_FEATURES;
       const int n_el = last_row * PST_EDGE_FEATURES;
-#pragma unroll 9
+      // all 27 loads of the thread in flight at once (one HBM round trip), then the next tile's block and sender
+      // indices are pulled into L2 (one 128-byte line per thread)
+      float x[PST_EDGE_FEATURES];
+#pragma unroll
       for (int i = 0; i < PST_EDGE_FEATURES; ++i) {
         const int idx = gt + i * 128;
-        const float x = idx < n_el ? __ldg(f0 + idx) : 0.f;
+        x[i] = idx < n_el ? __ldg(f0 + idx) : 0.f;
+      }
+      {
+        const int nt = tile + gridDim.x * kGroups;
+        if (nt < p.num_tiles) {
+          const size_t nrow0 = (size_t)nt * kTileM;
+          const char* nf = reinterpret_cast<const char*>(p.feat + nrow0 * PST_EDGE_FEATURES) + gt * 128;
+          if (gt < 108 && nrow0 * PST_EDGE_FEATURES * 4 + (size_t)gt * 128 < (size_t)p.E * PST_EDGE_FEATURES * 4)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nf));
+          if (gt >= 124 && nrow0 + (size_t)(gt - 124) * 32 < (size_t)p.E)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.senders + nrow0) + (gt - 124) * 128));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PST_EDGE_FEATURES; ++i) {
+        const int idx = gt + i * 128;
         const int r = idx / PST_EDGE_FEATURES, kk = idx - r * PST_EDGE_FEATURES;
-        const __half hi = __float2half_rn(x);
-        const __half lo = __float2half_rn(x - __half2float(hi));
+        const __half hi = __float2half_rn(x[i]);
+        const __half lo = __float2half_rn(x[i] - __half2float(hi));
         const uint32_t off = swz_k64(r, kk);
         *reinterpret_cast<__half*>(sA + off) = hi;
         *reinterpret_cast<__half*>(sA + kKBlockBytes + off) = lo;
@@ -733,6 +748,14 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
         *reinterpret_cast<uint16_t*>(sA + off) = 0;
         *reinterpret_cast<uint16_t*>(sA + kKBlockBytes + off) = 0;
       }
+    }
+    // this thread's row of the fp16 PE table (256 B, eight 32-byte loads): issued now, consumed in the epilogue, so
+    // the L2 latency hides behind the barrier and the MMA
+    uint32_t tab[64];
+    {
+      const uint32_t* tb = reinterpret_cast<const uint32_t*>(p.table + (size_t)trow * kD);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ldg256(tb + i * 8, &tab[i * 8]);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -751,39 +774,28 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
     mbar_wait(mbar_addr, parity);
     parity ^= 1;
     tc_fence_after();
-    // ---- table rows (fp16) gathered row-coalesced into the now free buffer, operand image layout --------
-    {
-      const uint4* tb = reinterpret_cast<const uint4*>(p.table) + c16;
-#pragma unroll 8
-      for (int it = 0; it < 16; ++it)
-        *reinterpret_cast<uint4*>(sA + offA + it * 1024) = __ldg(tb + (size_t)sTab[it * 8 + sub] * (kD / 8));
-    }
-    group_sync(g);
-    // ---- epilogue: acc + table row -> 16-bit edge state, in place (each thread only touches its own row) ----
-#pragma unroll 1
+    // ---- epilogue: acc + table row -> 16-bit edge state in the operand image layout of the (now free) buffer,
+    // which is also the layout of the TMA store boxes (each thread only touches its own row) ----
+#pragma unroll
     for (int q = 0; q < 4; ++q) {
       float2 v[16];
       tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
-        v[j * 4 + 0] = add2(v[j * 4 + 0], Unpack<__half>::two(pk.x));
-        v[j * 4 + 1] = add2(v[j * 4 + 1], Unpack<__half>::two(pk.y));
-        v[j * 4 + 2] = add2(v[j * 4 + 2], Unpack<__half>::two(pk.z));
-        v[j * 4 + 3] = add2(v[j * 4 + 3], Unpack<__half>::two(pk.w));
-      }
+      for (int c = 0; c < 16; ++c) v[c] = add2(v[c], Unpack<__half>::two(tab[q * 16 + c]));
       store_a_chunk2<T16>(sA, gt, q * 32, v);
     }
+    fence_proxy_async();
     tc_fence_before();
     group_sync(g);
-    {
-      uint4* dst = reinterpret_cast<uint4*>(p.e + (size_t)(row0 + sub) * kD) + c16;
-#pragma unroll 8
-      for (int it = 0; it < 16; ++it)
-        if (it * 8 + sub < last_row) dst[(size_t)it * 8 * (kD / 8)] = *reinterpret_cast<const uint4*>(sA + offA + it * 1024);
+    if (gt == 0) {  // rows beyond E are clipped by the tensor map
+      tma_store_2d(&tmap_e, 0, row0, sA_addr);
+      tma_store_2d(&tmap_e, 64, row0, sA_addr + kKBlockBytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     group_sync(g);
   }
+  if (gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -984,8 +996,10 @@ int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* f
   int grid = m->num_sms;
   const int need = (p.num_tiles + kGroups - 1) / kGroups;
   if (grid > need) grid = need;
-  if (m->cfg.precision == PST_PREC_FP16) edge_embed_tc_kernel<__half><<<grid, kThreads, kEmbSmemTotal, st>>>(p);
-  else edge_embed_tc_kernel<__nv_bfloat16><<<grid, kThreads, kEmbSmemTotal, st>>>(p);
+  CUtensorMap tmap;
+  if (int rc = make_edge_state_map(e, p.E, &tmap)) return rc;
+  if (m->cfg.precision == PST_PREC_FP16) edge_embed_tc_kernel<__half><<<grid, kThreads, kEmbSmemTotal, st>>>(p, tmap);
+  else edge_embed_tc_kernel<__nv_bfloat16><<<grid, kThreads, kEmbSmemTotal, st>>>(p, tmap);
   return 1;
 }
 
