@@ -137,6 +137,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 32-byte global accesses (LDG / STG .256 on sm_100): a thread that owns a whole row segment touches full sectors
+__device__ __forceinline__ void ld256f(const float* ptr, float* r) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(ptr)
+               : "memory");
+}
+__device__ __forceinline__ void st256f(float* ptr, const float* r) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]),
+               "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void st256u(void* ptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // tanh to ~1e-7 absolute: 1 - 2 / (exp(2u) + 1)   (exp overflow -> +inf -> 1, underflow -> 0 -> -1)
 __device__ __forceinline__ float tanh_fast(float u) { return 1.0f - __fdividef(2.0f, __expf(2.0f * u) + 1.0f); }
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -269,13 +287,16 @@ __device__ __forceinline__ void split_store_half(const Epi& e, uint8_t* set, con
   split_store(set, e.row, e.half * 64 + 32, x[1]);
 }
 __device__ __forceinline__ void load_row_half(const Epi& e, const float* row_ptr, bool valid, float (&x)[2][32]) {
-  const float4* src = reinterpret_cast<const float4*>(row_ptr + e.half * 64);
+  const float* src = row_ptr + e.half * 64;
 #pragma unroll
   for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 t = valid ? src[q * 8 + j] : make_float4(0, 0, 0, 0);
-      x[q][j * 4] = t.x; x[q][j * 4 + 1] = t.y; x[q][j * 4 + 2] = t.z; x[q][j * 4 + 3] = t.w;
+    for (int j = 0; j < 4; ++j) {
+      if (valid) ld256f(src + q * 32 + j * 8, &x[q][j * 8]);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[q][j * 8 + k] = 0.f;
+      }
     }
 }
 __device__ __forceinline__ void add_bias_half(const Epi& e, float (&x)[2][32], const float* __restrict__ bias) {
@@ -469,11 +490,11 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
     }
     layer_norm_row(e, x, p.ln1_s, p.ln1_o);
     if (valid) {
-      float4* hdst = reinterpret_cast<float4*>(p.h + (size_t)row * D + e.half * 64);
+      float* hdst = p.h + (size_t)row * D + e.half * 64;
 #pragma unroll
       for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) hdst[q * 8 + j] = make_float4(x[q][j * 4], x[q][j * 4 + 1], x[q][j * 4 + 2], x[q][j * 4 + 3]);
+        for (int j = 0; j < 4; ++j) st256f(hdst + q * 32 + j * 8, &x[q][j * 8]);
     }
     if (p.n_out > 0) {
       split_store_half(e, X, x);
@@ -487,15 +508,18 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
         tmem_ld_half(e, (o & 1) ? t_acc1 : t_acc0, x);
         if (p.out_bias[o]) add_bias_half(e, x, p.out_bias[o]);
         if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out[o] + (size_t)row * D + e.half * 64);
+          __half* dst = p.out[o] + (size_t)row * D + e.half * 64;
 #pragma unroll
           for (int q = 0; q < 2; ++q)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __half2 a = __floats2half2_rn(x[q][j * 8], x[q][j * 8 + 1]), b = __floats2half2_rn(x[q][j * 8 + 2], x[q][j * 8 + 3]);
-              const __half2 c2 = __floats2half2_rn(x[q][j * 8 + 4], x[q][j * 8 + 5]), d = __floats2half2_rn(x[q][j * 8 + 6], x[q][j * 8 + 7]);
-              dst[q * 4 + j] = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
-                                          *reinterpret_cast<const uint32_t*>(&c2), *reinterpret_cast<const uint32_t*>(&d));
+            for (int j = 0; j < 2; ++j) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const __half2 v2 = __floats2half2_rn(x[q][j * 16 + 2 * k], x[q][j * 16 + 2 * k + 1]);
+                pk[k] = *reinterpret_cast<const uint32_t*>(&v2);
+              }
+              st256u(dst + q * 32 + j * 16, pk);
             }
         }
         tc_before();
