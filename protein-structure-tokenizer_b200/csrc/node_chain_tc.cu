@@ -243,6 +243,12 @@ struct Epi {
   float* red;         // [2 stages][2 halves][128 rows]
 };
 
+// element j (0..31) of a 32-float parameter chunk, fetched as float4 (uniform address: one broadcast transaction)
+__device__ __forceinline__ float ldg4(const float* __restrict__ base, int j) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(base) + (j >> 2));
+  return (j & 3) == 0 ? t.x : (j & 3) == 1 ? t.y : (j & 3) == 2 ? t.z : t.w;
+}
+
 // LayerNorm over the full 128-wide row (biased variance of the centred row, eps 1e-5: gnn_layers.py:108-120,162-164;
 // hk.LayerNorm is the same formula); x = this thread's 64 columns
 __device__ __forceinline__ void layer_norm_row(const Epi& e, float (&x)[2][32], const float* __restrict__ scale,
@@ -271,7 +277,7 @@ __device__ __forceinline__ void layer_norm_row(const Epi& e, float (&x)[2][32], 
 #pragma unroll
   for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[q][j] = (__ldg(sc + q * 32 + j) * inv) * (x[q][j] - mean) + __ldg(of + q * 32 + j);
+    for (int j = 0; j < 32; ++j) x[q][j] = (ldg4(sc + q * 32, j) * inv) * (x[q][j] - mean) + ldg4(of + q * 32, j);
 }
 
 __device__ __forceinline__ void tmem_ld_half(const Epi& e, uint32_t region, float (&x)[2][32]) {
@@ -304,7 +310,7 @@ __device__ __forceinline__ void add_bias_half(const Epi& e, float (&x)[2][32], c
 #pragma unroll
   for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[q][j] += __ldg(b + q * 32 + j);
+    for (int j = 0; j < 32; ++j) x[q][j] += ldg4(b + q * 32, j);
 }
 
 struct Setup {
@@ -469,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
 #pragma unroll
       for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[q][j] += hh[q][j] + __ldg(b + q * 32 + j);
+        for (int j = 0; j < 32; ++j) x[q][j] += hh[q][j] + ldg4(b + q * 32, j);
     }
     layer_norm_row(e, x, p.ln0_s, p.ln0_o);
     tmem_st_half(e, t_h1, x);
@@ -486,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
 #pragma unroll
       for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[q][j] += h1[q][j] + __ldg(b + q * 32 + j);
+        for (int j = 0; j < 32; ++j) x[q][j] += h1[q][j] + ldg4(b + q * 32, j);
     }
     layer_norm_row(e, x, p.ln1_s, p.ln1_o);
     if (valid) {
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[q][j] *= sigmoid_f(g[q][j] + __ldg(bg + q * 32 + j));
+          for (int j = 0; j < 32; ++j) x[q][j] *= sigmoid_f(g[q][j] + ldg4(bg + q * 32, j));
       }
       split_store_half(e, X, x);
       publish();
@@ -622,7 +628,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + __ldg(bo + q * 32 + j);
+          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + ldg4(bo + q * 32, j);
       }
       tmem_st_half(e, t_res, x);
       // ---- resampled transition (modules.py:227-252): res += W2 . relu(W1 . LN(res) + b1) + b2 -----------------------
@@ -638,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + __ldg(b2 + q * 32 + j);
+          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + ldg4(b2 + q * 32, j);
       }
       tmem_st_half(e, t_res, x);
       // ---- original transition; its result is never read after the last block (modules.py:624-629) ---------------
@@ -655,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + __ldg(b2 + q * 32 + j);
+          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + ldg4(b2 + q * 32, j);
         tmem_st_half(e, t_orig, x);
       }
     }
