@@ -45,9 +45,9 @@ FLOP_PER_EDGE_MLP = 2 * 81920  # one 384->128->128->128 MLP on one edge (referen
 # message mode the third linear is applied after the mean over K (once per residue, by linear_tc)
 HW_FLOP_MSG = 2 * 2 * 128 * 128
 HW_FLOP_UPD = 2 * 3 * 128 * 128
-# DRAM bytes per launch of the dominant kernel, from the committed capture profiles/r01_edge_mlp_tc_ncu_full.md
-# (dram__bytes_read.sum + dram__bytes_write.sum at 256 x 512 residues): message mode 1.876 GB, update mode 3.395 GB
-NCU_DRAM_BYTES = {"msg": 1.876e9, "upd": 3.395e9, "residues": 131072}
+# DRAM bytes per launch of the dominant kernel, from the committed capture profiles/r01_kernels_ncu_full.md
+# (dram__bytes_read.sum + dram__bytes_write.sum at 256 x 512 residues): message mode 1.878 GB, update mode 3.419 GB
+NCU_DRAM_BYTES = {"msg": 1.878e9, "upd": 3.419e9, "residues": 131072}
 
 
 def load_peaks():
@@ -312,7 +312,7 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": ((prof_cnt[1] * NCU_DRAM_BYTES["msg"] + prof_cnt[2] * NCU_DRAM_BYTES["upd"]) / mlp_groups
                             * R / NCU_DRAM_BYTES["residues"]) if args.precision != "fp32" else None,
-                "traffic_source": "ncu --set full, profiles/r01_edge_mlp_tc_ncu_full.md (per launch, scaled to this batch)",
+                "traffic_source": "ncu --set full, profiles/r01_kernels_ncu_full.md (per launch, scaled to this batch)",
                 "algorithmic_bytes_per_launch": E * 256 * (prof_cnt[1] * 1 + prof_cnt[2] * 2) / mlp_groups,
                 "peak_source": f"{peaks['source']} (bf16_tflops_sustained, MEASURED_PEAKS.json)",
                 "hw_flops_tflops": E * (prof_cnt[1] * HW_FLOP_MSG + prof_cnt[2] * HW_FLOP_UPD) / (mlp_ms * 1e-3) / 1e12,
