@@ -224,6 +224,36 @@ __constant__ double c_rbf_scale[15] = {1.0, 1.5, 2.25, 3.375, 5.0625, 7.59375, 1
                                       38.443359375, 57.6650390625, 86.49755859375, 129.746337890625,
                                       194.6195068359375, 291.92926025390625};
 
+// 1 / 1.5**k: the RBF argument -d*d / 1.5**k (utils/protein_utils.py:266-270) is formed as a product; the one-ulp
+// (fp64) difference from the reference's division is 1e-14 relative on the result, far below the fp32 rounding.
+__constant__ double c_rbf_inv_scale[15] = {1.0 / 1.0, 1.0 / 1.5, 1.0 / 2.25, 1.0 / 3.375, 1.0 / 5.0625, 1.0 / 7.59375,
+                                          1.0 / 11.390625, 1.0 / 17.0859375, 1.0 / 25.62890625, 1.0 / 38.443359375,
+                                          1.0 / 57.6650390625, 1.0 / 86.49755859375, 1.0 / 129.746337890625,
+                                          1.0 / 194.6195068359375, 1.0 / 291.92926025390625};
+
+// exp(x) for x <= 0 to ~1e-11 relative, as a double that is then rounded to fp32 (the features are fp32: SURVEY A.4
+// gate <= 1 fp32 ulp from float32(exp_fp64)).  n = rint(x log2 e), r = x - n ln2 (two-term Cody-Waite), degree-9
+// Taylor polynomial on |r| <= 0.347 (remainder 7e-12), scaled by 2^n through the exponent field.  About a quarter
+// of the instructions of the library exp().  Below e^-104 = 2^-150.04 the fp32 result is 0.
+__device__ __forceinline__ double exp_neg_for_fp32(double x) {
+  if (x < -104.0) return 0.0;
+  const double n = rint(x * 1.4426950408889634);
+  double r = fma(-n, 6.93147180369123816490e-01, x);
+  r = fma(-n, 1.90821492927058770002e-10, r);
+  double p = 2.7557319223985893e-06;                 // 1/9!
+  p = fma(p, r, 2.4801587301587302e-05);             // 1/8!
+  p = fma(p, r, 1.9841269841269841e-04);             // 1/7!
+  p = fma(p, r, 1.3888888888888889e-03);             // 1/6!
+  p = fma(p, r, 8.3333333333333332e-03);             // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);             // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);             // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const long long bits = ((long long)(int)n + 1023) << 52;  // n >= -151: a normal double
+  return p * __longlong_as_double(bits);
+}
+
 constexpr int kKnnWarps = 8;
 constexpr unsigned long long kIdxMask = 0x7FFull;  // 11 bits: L <= 2048
 
@@ -321,7 +351,7 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
   float* out = feat + (size_t)row * K * PST_EDGE_FEATURES;
   for (int t = lane; t < K * 15; t += 32) {
     const int e = t / 15, f = t - e * 15;
-    out[e * PST_EDGE_FEATURES + f] = (float)exp(-s_d2[warp][e] / c_rbf_scale[f]);
+    out[e * PST_EDGE_FEATURES + f] = (float)exp_neg_for_fp32(-s_d2[warp][e] * c_rbf_inv_scale[f]);
   }
   const double ca_x = pi[3], ca_y = pi[4], ca_z = pi[5];
   for (int t = lane; t < K * 12; t += 32) {
