@@ -5,19 +5,21 @@
 //   message mode : agg = mean over the K edges of a receiver                (:364-377)
 //   update  mode : e   = MaskedLayerNorm(e + MLP(...))                        (:421-436)
 // The first linear is factorised, [h_s|h_r|e].W1 = (h.W1[0:128])[s] + (h.W1[128:256] + b1)[r] + e.W1[256:384]:
-// the two node-level products (ps, pr) are computed once per residue by the fp32 SGEMM and gathered
-// in this kernel's first epilogue, so only K = 128 goes through the tensor core per edge.  In message
-// mode the third linear commutes with the mean over K (no activation follows it), so it is applied to
-// the per-receiver mean of the second hidden layer by the caller: this kernel returns partial row sums.
+// the two node-level products (fp16 tables ps, pr) are computed once per residue by the node-level kernels
+// (node_chain_tc.cu / linear_tc.cu) and gathered here straight into the accumulator, so only K = 128 goes
+// through the tensor core per edge.  In message mode the third linear commutes with the mean over K (no
+// activation follows it), so it is applied to the per-receiver mean of the second hidden layer by the node
+// kernel: this kernel returns per-receiver partial row sums (computed by one more MMA, see below).
 //
 // Structure: persistent CTAs (one per SM, 512 threads).  The three 128x128 16-bit weight matrices of
 // the MLP stay resident in shared memory (96 KB, canonical K-major SWIZZLE_128B UMMA layout, image
 // built once at model load).  Four independent "tile groups" of 4 warps each own a 128-edge tile, a
 // 32 KB A-operand buffer and a 128-column fp32 accumulator in TMEM (4 x 128 = all 512 columns); a
-// group runs   load e -> MMA1 -> epilogue1 (gather+GELU, fp32 regs -> 16-bit smem) -> MMA2 ->
-// epilogue2 -> [MMA3 -> epilogue3 (residual + LayerNorm)]   serially, and the four groups interleave
-// on the SM so one group's MMA overlaps the others' epilogues.  In the 32x32b TMEM load layout each
-// thread owns one accumulator row (= one edge), so the LayerNorm and the gathers are thread-local.
+// group runs   [TMA load of e  ||  gather ps[s] + pr[r] -> accumulator]  -> MMA1 -> epilogue1 (GELU, fp32 regs ->
+// 16-bit smem) -> MMA2 -> epilogue2 -> {MMA3 -> TMA re-read of e -> residual + LayerNorm -> TMA store  |
+// row-sum MMA -> partial sums}   serially, and the four groups interleave on the SM so one group's MMA and
+// memory waits overlap the others' epilogues.  In the 32x32b TMEM load layout each thread owns one accumulator
+// row (= one edge), so the LayerNorm and the gathers are thread-local.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -176,18 +178,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// GELU, tanh form (jax.nn.gelu default): 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3).
-// tanh.approx.f32 (one MUFU op, relative error 2^-11) is below the 16-bit rounding the result gets
-// when it is repacked as the next GEMM's operand; measured with the oracle: no change in token agreement.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float c0 = 0.7978845608f, c1 = 0.0356774081f;  // sqrt(2/pi), sqrt(2/pi) * 0.044715
-  float u = x * fmaf(c1, x * x, c0);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
-
+// GELU is the tanh form (jax.nn.gelu default): 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3); see gelu2().
+// tanh.approx.f32 (one MUFU op, relative error 2^-11) is below the 16-bit rounding the result gets when it is
+// repacked as the next GEMM's operand; measured with the oracle: no change in token agreement.
 template <typename T16>
 struct Pack;
 template <>
@@ -300,13 +293,11 @@ __device__ __forceinline__ void store_a_chunk2(uint8_t* sA, int row, int k0, con
   }
 }
 
-// ---- staging through the group's (currently free) 32 KB A buffer ---------------------------------
-// Global traffic is always issued row-coalesced (16 threads x 16 B of one row per request); the
-// thread-per-row view the TMEM 32x32b layout needs is obtained by a shared-memory transpose:
-// fp32 staging tile S = [128 rows][64 fp32], float4 slot j of row r stored at slot j ^ (r & 7)
-// (conflict-free for both the 16-threads-per-row and the thread-per-row access); 16-bit tiles use the
-// operand image layout itself.  In the 16-threads-per-row loops row = it*8 + sub, so (row & 7) == sub
-// and every offset is (loop-invariant constant) + it * stride.
+// ---- data movement -----------------------------------------------------------------------------------------
+// The 16-bit edge-state tile moves by TMA (load, re-read for the residual, store): its two [128 x 64] SWIZZLE_128B
+// boxes are the K-major operand image.  The gathered addend rows never touch shared memory: each thread reads its
+// own sender / receiver rows with 32-byte loads and writes its accumulator row with tcgen05.st.  Activations are
+// written thread-per-row into the operand image (16-byte chunks at chunk ^ (row & 7): conflict-free).
 // Optional per-phase cycle accounting (debug builds only: -DPST_EDGE_PROFILE): group 0 / thread 0 of every
 // CTA accumulates clock64() deltas per phase into g_edge_prof[mode][phase].
 #ifdef PST_EDGE_PROFILE
@@ -329,7 +320,6 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   uint8_t* sW = smem;
   uint8_t* sAall = smem + kSmemW;
   float* sVec = reinterpret_cast<float*>(smem + kSmemW + kSmemA);                 // b2, b3, ln_s, ln_o [128] each
-  int* sBaseAll = reinterpret_cast<int*>(smem + kSmemW + kSmemA + 2048);          // [groups][4]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemW + kSmemA + 2048 + 64);
   uint64_t* tbar = mbar + kGroups;  // per group: completion of the TMA loads of the edge-state tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbar + kGroups);
@@ -341,13 +331,6 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   const int wq = warp & 3;          // TMEM lane quarter this warp may access
   uint8_t* sA = sAall + g * kMatBytes;
   uint8_t* sSel = sW + 2 * kMatBytes + g * 4096;  // message mode only: the W3 slot is not loaded
-  float* S = reinterpret_cast<float*>(sA);
-  int* sBase = sBaseAll + g * 4;
-  const int sub = gt >> 4, c16 = gt & 15;  // 16 threads per row, 8 rows per pass
-  const uint32_t offA = (uint32_t)((c16 >> 3) * kKBlockBytes + sub * 128 + (((c16 & 7) ^ sub) << 4));  // + it*1024
-  const uint32_t offS = (uint32_t)(sub * 64 + ((c16 ^ sub) << 2));                                    // + it*512 (floats)
-  const int gx = gt & 7;
-
   // ---- one-time setup -------------------------------------------------------------------------
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_image);
@@ -401,7 +384,6 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
     const int row0 = tile * kTileM;
     const int er = row0 + gt;
-    const bool valid = er < p.E;
     const int first_recv = row0 / p.K;
     const int last_row = min(p.E - row0, kTileM);  // valid rows in this tile
     const int last_recv = (p.E - 1) / p.K;
@@ -664,15 +646,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sAall = smem + kEmbSmemW;
-  uint16_t* sTabAll = reinterpret_cast<uint16_t*>(smem + kEmbSmemW + kSmemA);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kEmbSmemW + kSmemA + kGroups * 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kGroups);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = warp >> 2, gt = tid & 127, wq = warp & 3;
   uint8_t* sA = sAall + g * kMatBytes;
-  uint16_t* sTab = sTabAll + g * 128;
-  const int sub = gt >> 4, c16 = gt & 15;
-  const uint32_t offA = (uint32_t)((c16 >> 3) * kKBlockBytes + sub * 128 + (((c16 & 7) ^ sub) << 4));
 
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
