@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "pst", "libpst_b200.so")
+OUT = os.environ.get("PST_BUILD_OUT") or os.path.join(HERE, "pst", "libpst_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 SOURCES = {
@@ -33,7 +33,7 @@ def nvcc() -> str:
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_prof" if os.environ.get("PST_EDGE_PROFILE") else "build")
     os.makedirs(objdir, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "pst_abi.h"), __file__]
     newest = max(os.path.getmtime(d) for d in deps)

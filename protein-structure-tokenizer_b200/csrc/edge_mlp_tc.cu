@@ -254,18 +254,19 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
       : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
   return *reinterpret_cast<float2*>(&d);
 }
-// GELU (tanh form) of two values: 5 packed ops + 2 MUFU.TANH
+// GELU (tanh form) of two values.  The kernel computes G(x) = 2 gelu(x) = x + x tanh(u), u = x (c0 + c1 x^2): the
+// factor 0.5 is folded into the operand that consumes the activation (W2 / W3 images and the row-sum selection
+// matrix are scaled by 0.5 at build time: exact in fp16 / bf16), which saves one packed op per pair.
+constexpr float kActScale = 0.5f;   // what the consumer of G(x) multiplies by
 __device__ __forceinline__ float2 gelu2(float2 x) {
   const float2 x2 = mul2(x, x);
-  const float2 p = fma2(x2, make_float2(0.0713548162f, 0.0713548162f), make_float2(1.5957691216f, 1.5957691216f));
-  const float2 hx = mul2(x, make_float2(0.5f, 0.5f));
-  const float2 u = mul2(hx, p);  // sqrt(2/pi) (x + 0.044715 x^3)
+  const float2 p = fma2(x2, make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f));
+  const float2 u = mul2(x, p);  // sqrt(2/pi) (x + 0.044715 x^3)
   float2 t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
   asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
-  return fma2(hx, t, hx);
+  return fma2(x, t, x);
 }
-
 // 32-byte global load through the read-only path (LDG.E.256 on sm_100)
 __device__ __forceinline__ void ldg256(const uint32_t* ptr, uint32_t* r) {
   asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -290,6 +291,35 @@ __device__ __forceinline__ void store_a_chunk2(uint8_t* sA, int row, int k0, con
     pk.z = Pack<T16>::two(v[c * 4 + 2].x, v[c * 4 + 2].y);
     pk.w = Pack<T16>::two(v[c * 4 + 3].x, v[c * 4 + 3].y);
     *reinterpret_cast<uint4*>(sA + swz_offset(row, k0 + c * 8)) = pk;
+  }
+}
+
+// One GELU epilogue: accumulator row (128 fp32 columns in TMEM) [+ bias] -> G(x) -> 16-bit operand image row.
+// (Measured and rejected: software-pipelining the TMEM loads over two register sets (+2 %), tanh.approx.f16x2 with
+// the last fma in fp16x2 (+4 % and 0.06 % fewer equal tokens): the kernel is not bound by the XU pipe or TMEM latency.)
+template <typename T16, bool BIAS>
+__device__ __forceinline__ void gelu_chunk(uint8_t* sA, int gt, int q, const float* sBias, float2 (&v)[16]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (BIAS) {
+      const float4 b = *reinterpret_cast<const float4*>(sBias + q * 32 + c * 4);
+      v[c * 2] = gelu2(add2(v[c * 2], make_float2(b.x, b.y)));
+      v[c * 2 + 1] = gelu2(add2(v[c * 2 + 1], make_float2(b.z, b.w)));
+    } else {
+      v[c * 2] = gelu2(v[c * 2]);
+      v[c * 2 + 1] = gelu2(v[c * 2 + 1]);
+    }
+  }
+  store_a_chunk2<T16>(sA, gt, q * 32, v);
+}
+
+template <typename T16, bool BIAS>
+__device__ __forceinline__ void gelu_epilogue(uint32_t tmem_row, uint8_t* sA, int gt, const float* sBias) {
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    float2 v[16];
+    tmem_ld32v(tmem_row + q * 32, v);
+    gelu_chunk<T16, BIAS>(sA, gt, q, sBias, v);
   }
 }
 
@@ -397,6 +427,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     // with eight 32-byte loads (whole sectors: the per-thread access is as efficient as a row-coalesced one) and
     // the receiver's row (shared by K consecutive edges: L1 broadcast), adds and writes its accumulator row.
     // No shared-memory staging, no barrier between gather and preload, and the TMA latency hides behind it.
+    // (Measured and rejected: dropping the barrier at the top of the loop and deferring the wait for the previous
+    // tile's TMA store until after the gather: the exposed latency only moves to the wait for the e tile, 0.2 %.)
     if (gt == 0) {
       tma_tile_load(sA_addr, &tmap_e, row0, tbar_addr);
       const int nt = tile + gridDim.x * kGroups;
@@ -442,14 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     tc_fence_after();
     PHASE(4);
     // ---- 3. epilogue 1: GELU -> A image ------------------------------------------------------------------
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      float2 v[16];
-      tmem_ld32v(tmem_row + q * 32, v);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = gelu2(v[c]);
-      store_a_chunk2<T16>(sA, gt, q * 32, v);
-    }
+    gelu_epilogue<T16, false>(tmem_row, sA, gt, sVec);
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
@@ -462,18 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     PHASE(6);
     if (MODE == 1) {
       // ---- 5a. epilogue 2: + b2, GELU -> A image; GEMM 3; epilogue 3: residual + LayerNorm -------------
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float2 v[16];
-        tmem_ld32v(tmem_row + q * 32, v);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 b = *reinterpret_cast<const float4*>(sVec + q * 32 + c * 4);
-          v[c * 2] = gelu2(add2(v[c * 2], make_float2(b.x, b.y)));
-          v[c * 2 + 1] = gelu2(add2(v[c * 2 + 1], make_float2(b.z, b.w)));
-        }
-        store_a_chunk2<T16>(sA, gt, q * 32, v);
-      }
+      gelu_epilogue<T16, true>(tmem_row, sA, gt, sVec);
       fence_proxy_async();
       tc_fence_before();
       group_sync(g);
@@ -550,18 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       // as an MN-major A operand (M = the 128 channels, K = the 128 edge rows: the same bytes, transposed by the
       // descriptor), times a 0/1 selection matrix Sel^T [N = 16 (4 used) x K = 128 rows] built per tile, gives
       // D[channel, receiver] in fp32 in 16 TMEM columns; thread = channel reads its 4 sums.
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float2 v[16];
-        tmem_ld32v(tmem_row + q * 32, v);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 b = *reinterpret_cast<const float4*>(sVec + q * 32 + c * 4);
-          v[c * 2] = gelu2(add2(v[c * 2], make_float2(b.x, b.y)));
-          v[c * 2 + 1] = gelu2(add2(v[c * 2 + 1], make_float2(b.z, b.w)));
-        }
-        store_a_chunk2<__half>(sA, gt, q * 32, v);
-      }
+      gelu_epilogue<__half, true>(tmem_row, sA, gt, sVec);
       {
         // Sel^T[s][r] for r = gt: K block r >> 6, row s (128 B each), 16-byte chunk ((r & 63) >> 3) ^ s
         uint8_t* sel = sSel + (gt >> 6) * 2048 + ((gt & 7) << 1);
@@ -570,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         for (int s4 = 0; s4 < 4; ++s4) {
           const int lo_u = (first_recv + s4) * p.K - row0;
           const bool in = gt >= lo_u && gt < lo_u + p.K && gt < last_row;
-          *reinterpret_cast<uint16_t*>(sel + s4 * 128 + ((kc ^ s4) << 4)) = in ? (uint16_t)0x3C00 : (uint16_t)0;
+          *reinterpret_cast<uint16_t*>(sel + s4 * 128 + ((kc ^ s4) << 4)) = in ? (kActScale == 0.5f ? (uint16_t)0x3800 : (uint16_t)0x3C00) : (uint16_t)0;  // 0.5 or 1.0
         }
       }
       fence_proxy_async();
@@ -823,12 +826,12 @@ __global__ void combine_partials_kernel(const float* __restrict__ partial, int K
 }
 
 template <typename T16>
-__global__ void build_weight_image_kernel(const float* __restrict__ w, uint16_t* __restrict__ image) {
+__global__ void build_weight_image_kernel(const float* __restrict__ w, uint16_t* __restrict__ image, float scale) {
   // w: fp32 [128 (k), 128 (n)] row-major; image element (n, k) at swz_offset(n, k)
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 128 * 128) return;
   int k = idx >> 7, n = idx & 127;
-  T16 v = T16(w[idx]);
+  T16 v = T16(w[idx] * scale);  // scale = 0.5 for the consumers of G(x) = 2 gelu(x): exact
   image[swz_offset(n, k) >> 1] = *reinterpret_cast<uint16_t*>(&v);
 }
 
@@ -858,9 +861,9 @@ int pst_prepare_tc_weights(pst_model* m) {
       for (int j = 0; j < 3; ++j) {
         uint16_t* dst = m->tc_dev + ((size_t)(l * 2 + t) * per_mlp + (size_t)j * kMatBytes) / 2;
         if (m->cfg.precision == PST_PREC_FP16)
-          build_weight_image_kernel<__half><<<64, 256>>>(src[t][j], dst);
+          build_weight_image_kernel<__half><<<64, 256>>>(src[t][j], dst, j > 0 ? kActScale : 1.0f);
         else
-          build_weight_image_kernel<__nv_bfloat16><<<64, 256>>>(src[t][j], dst);
+          build_weight_image_kernel<__nv_bfloat16><<<64, 256>>>(src[t][j], dst, j > 0 ? kActScale : 1.0f);
       }
   }
   {

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 LIB_NAME = "libpst_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# PST_LIB_PATH: developer override (instrumented builds for tools/); still the same library, still no fallback
+LIB_PATH = os.environ.get("PST_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 PST_ABI_VERSION = 1
 PST_ERR_WORKSPACE_TOO_SMALL = -4

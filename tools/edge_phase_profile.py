@@ -17,7 +17,7 @@ for it in range(3):
     tok.tokenize_device(a, None, o, t, len(bbs), int(offsets[-1]), int(toff[-1])); torch.cuda.synchronize()
     lib.pst_debug_edge_profile(out, 1)
 v = np.array(list(out), dtype=np.float64).reshape(2, 16)
-names = ["idx+sync", "gather+sync", "preload+sync", "e load+sync", "MMA1 wait", "epi1+sync", "MMA2 wait", "epi2+sync", "MMA3 wait", "reload+sync", "pass1", "pass2+sync", "copyout+sync", "msg epi2"]
+names = ["top sync", "-", "gather+st+sync", "e wait+issue (t0)", "MMA1 wait", "epi1+sync", "MMA2 wait", "epi2+sync", "MMA3 wait", "reload wait", "LN pass1", "LN pass2+sync", "store issue", "msg epi2+sum+st"]
 for mode, launches, label in ((0, 3, "message"), (1, 2, "update")):
     tiles_per_cta = 51200 / 148 / 4
     tot = v[mode].sum()
