@@ -410,6 +410,15 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     const int t0 = blockIdx.x * kGroups + g;
     if (t0 < p.num_tiles) my_sender = __ldg(p.senders + min(t0 * kTileM + gt, p.E - 1));
   }
+  // The sender's row of the fp16 table (256 B, eight 32-byte loads) is fetched ONE TILE AHEAD into registers: the
+  // loads are issued at the end of the previous tile (registers are free there) and their L2 latency (there is no L1
+  // to speak of next to 226 KB of shared memory) hides behind that tile's last MMA / TMA store.
+  uint32_t a[64];
+  {
+    const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)my_sender * kD);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ldg256(psr + i * 8, &a[i * 8]);
+  }
 
   for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
     const int row0 = tile * kTileM;
@@ -438,14 +447,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       }
     }
     {
-      uint32_t a[64];
-      const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)my_sender * kD);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ldg256(psr + i * 8, &a[i * 8]);
       const uint32_t* prr = reinterpret_cast<const uint32_t*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
       {
         const int nt = tile + gridDim.x * kGroups;
-        if (nt < p.num_tiles) my_sender = __ldg(p.senders + min(nt * kTileM + gt, p.E - 1));
+        my_sender = nt < p.num_tiles ? __ldg(p.senders + min(nt * kTileM + gt, p.E - 1)) : 0;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -550,6 +555,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       fence_proxy_async();
       group_sync(g);
       PHASE(11);
+      {  // next tile's sender row (row 0 when there is none: a valid address, never used)
+        const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)my_sender * kD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ldg256(psr + i * 8, &a[i * 8]);
+      }
       if (gt == 0) {  // TMA store of the new edge state (rows beyond E are clipped); the buffer is reused afterwards
         tma_store_2d(&tmap_e, 0, row0, sA_addr);
         tma_store_2d(&tmap_e, 64, row0, sA_addr + kKBlockBytes);
@@ -588,6 +598,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
                    p.idesc_sum, j > 0 ? 1u : 0u);
         }
         umma_commit(mbar_addr);
+      }
+      {  // next tile's sender row (row 0 when there is none: a valid address, never used)
+        const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)my_sender * kD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ldg256(psr + i * 8, &a[i * 8]);
       }
       mbar_wait(mbar_addr, parity);
       parity ^= 1;
