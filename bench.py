@@ -233,12 +233,17 @@ def run_ours(args):
     def step_resident():
         tok.tokenize_device(atoms_dev, None, offs_dev, toff_dev, B, R, T, out=tokens_dev)
 
+    # end-to-end step: pinned host buffers -> persistent device staging buffers -> fused call -> pinned host tokens
+    # (persistent staging keeps the argument set of the call constant, so the library replays its CUDA graph)
+    atoms_stage, offs_stage, toff_stage = torch.empty_like(atoms_dev), torch.empty_like(offs_dev), torch.empty_like(toff_dev)
+    tokens_stage = torch.empty_like(tokens_dev)
+
     def step_e2e():
-        a = atoms_pin.to(dev, non_blocking=True)
-        o = offs_pin.to(dev, non_blocking=True)
-        t = toff_pin.to(dev, non_blocking=True)
-        tk = tok.tokenize_device(a, None, o, t, B, R, T)
-        out_pin.copy_(tk, non_blocking=True)
+        atoms_stage.copy_(atoms_pin, non_blocking=True)
+        offs_stage.copy_(offs_pin, non_blocking=True)
+        toff_stage.copy_(toff_pin, non_blocking=True)
+        tok.tokenize_device(atoms_stage, None, offs_stage, toff_stage, B, R, T, out=tokens_stage)
+        out_pin.copy_(tokens_stage, non_blocking=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -268,12 +273,16 @@ def run_ours(args):
     if tok.read_status() != 0:
         raise SystemExit("device status != 0 after warm-up")
 
-    tok.profile_enable(True)
+    # timed region: the fused call replays its CUDA graph (captured during warm-up: repeated argument set)
     with ClockSampler(local_rank) as clk:
         ms_total = timed(step_resident, args.steps)
+    launches = tok.launches * args.steps
+    # kernel-level pass for the roofline: the same K steps again with the library's event spans around the k-NN and
+    # edge-MLP launch groups (spans switch the graph replay off: kernels are enqueued one by one)
+    tok.profile_enable(True)
+    ms_prof_total = timed(step_resident, args.steps)
     prof_ms, prof_cnt = tok.profile_collect()
     tok.profile_enable(False)
-    launches = tok.launches * args.steps
 
     for _ in range(2):
         step_e2e()
@@ -284,6 +293,7 @@ def run_ours(args):
     step_resident()
     torch.cuda.synchronize()
     assert bool((ref_tokens == tokens_dev).all()), "non-deterministic tokens"
+    assert bool((tokens_stage == tokens_dev).all()), "end-to-end pass and resident pass disagree"
     assert int(tokens_dev.max()) < cfg.num_codes and int(tokens_dev.min()) >= 0
     distinct = int(torch.unique(tokens_dev).numel())
 
@@ -321,7 +331,10 @@ def run_ours(args):
                 # known launch structure (3 message + 2 edge-update MLPs per step), not from raw span counts
                 "launch_groups_per_step": 2 * cfg.gnn_layers - 1,
                 "share_of_step": (prof_ms[1] / max(1, prof_cnt[1]) * cfg.gnn_layers
-                                  + prof_ms[2] / max(1, prof_cnt[2]) * (cfg.gnn_layers - 1)) / ms_step,
+                                  + prof_ms[2] / max(1, prof_cnt[2]) * (cfg.gnn_layers - 1)) / (ms_prof_total / args.steps),
+                "timing": f"CUDA-event spans around each launch group in a second pass of the same {args.steps} steps "
+                          f"({ms_prof_total / args.steps:.3f} ms/step, kernels enqueued one by one); the timed region "
+                          f"itself replays the call's CUDA graph ({ms_step:.3f} ms/step)",
                 "featurize_knn_ms_per_step": prof_ms[0] / max(1, prof_cnt[0]),
                 "end_to_end_frac": value / world * FLOP_PER_RESIDUE.get(df, 44.91e6) / 1e12 / peak,
             }
@@ -334,7 +347,8 @@ def run_ours(args):
                                    f"(lengths {int(np.diff(offsets).min())}..{int(np.diff(offsets).max())}), codebook {codebook}, df={df}, "
                                    f"K=50, random-init 'spread' weights", "precision": args.precision,
                        "l2": "working set per step (edge state 3.3 GB) far exceeds the 126 MB L2; no explicit flush",
-                       "distinct_codes": distinct, "gen_seconds": round(gen_s, 1)},
+                       "distinct_codes": distinct, "gen_seconds": round(gen_s, 1),
+                       "launch": "one CUDA-graph replay per step (pst_tokenize's graph cache)"},
             "clocks": clk.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "residues/s", "h2d_bytes_per_step": int(atoms.nbytes + offsets.nbytes + tok_off.nbytes),
                     "d2h_bytes_per_step": int(T * 4)},

@@ -7,6 +7,57 @@
 
 #include "pst_internal.h"
 
+#include <mutex>
+#include <vector>
+
+struct PstGraphKey {
+  const void *atoms, *mask, *offsets, *token_offsets, *tokens, *workspace;
+  size_t ws_bytes;
+  int apr, B, R, T;
+  bool operator==(const PstGraphKey& o) const {
+    return atoms == o.atoms && mask == o.mask && offsets == o.offsets && token_offsets == o.token_offsets &&
+           tokens == o.tokens && workspace == o.workspace && ws_bytes == o.ws_bytes && apr == o.apr && B == o.B &&
+           R == o.R && T == o.T;
+  }
+};
+struct PstGraphEntry {
+  PstGraphKey key;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+  bool failed = false;
+  unsigned long long last_use = 0;
+};
+struct PstGraphCache {
+  static constexpr size_t kMaxEntries = 8;
+  std::mutex mu;
+  std::vector<PstGraphEntry> entries;
+  unsigned long long clock = 0;
+  bool enabled = true;
+  PstGraphEntry* find(const PstGraphKey& k) {
+    for (auto& e : entries)
+      if (e.key == k) return &e;
+    return nullptr;
+  }
+  void insert(const PstGraphKey& k) {
+    if (entries.size() >= kMaxEntries) {  // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < entries.size(); ++i)
+        if (entries[i].last_use < entries[lru].last_use) lru = i;
+      if (entries[lru].exec) cudaGraphExecDestroy(entries[lru].exec);
+      entries.erase(entries.begin() + lru);
+    }
+    PstGraphEntry e;
+    e.key = k;
+    e.last_use = ++clock;
+    entries.push_back(e);
+  }
+  void clear() {
+    for (auto& e : entries)
+      if (e.exec) cudaGraphExecDestroy(e.exec);
+    entries.clear();
+  }
+};
+
 int pst_prepare_tc_weights(pst_model* m);  // edge_mlp_tc.cu
 
 namespace {
@@ -170,6 +221,8 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   m->device = device;
   m->launch_count = 0;
   m->tc_dev = nullptr;
+  m->graphs = new (std::nothrow) PstGraphCache();
+  if (m->graphs) { const char* g = getenv("PST_CUDA_GRAPH"); m->graphs->enabled = !(g && g[0] == '0'); }
   m->linear_tc = nullptr;
   m->node_chain = nullptr;
   m->embed_img_dev = nullptr;
@@ -216,6 +269,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
 void pst_model_destroy(pst_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
+  if (m->graphs) { m->graphs->clear(); delete m->graphs; }
   if (m->blob_dev) cudaFree(m->blob_dev);
   if (m->tc_dev) cudaFree(m->tc_dev);
   pst_destroy_node_chain(m);
@@ -328,15 +382,11 @@ int pst_indexes_to_codes(const pst_model* m, void* stream, const int32_t* tokens
   return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
 }
 
-int pst_tokenize(const pst_model* m, void* stream, const float* atoms, const uint8_t* atom_mask,
-                 int atoms_per_residue, const int32_t* offsets, const int32_t* token_offsets, int num_structures,
-                 int total_residues, int total_tokens, int32_t* tokens_out, void* workspace,
-                 size_t workspace_bytes) {
-  int rc = check_batch(m, offsets, num_structures, total_residues, workspace, workspace_bytes, total_tokens);
-  if (rc != PST_OK) return rc;
-  if (!atoms || !token_offsets || !tokens_out || atoms_per_residue < 4) return PST_ERR_BAD_ARGUMENT;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PST_CUDA_OK(cudaSetDevice(m->device));
+// Enqueues the fused call on `st` (eagerly, or into the graph being captured on it).
+static int tokenize_enqueue(const pst_model* m, cudaStream_t st, const float* atoms, const uint8_t* atom_mask,
+                            int atoms_per_residue, const int32_t* offsets, const int32_t* token_offsets,
+                            int num_structures, int total_residues, int total_tokens, int32_t* tokens_out,
+                            void* workspace) {
   PstWorkspace ws = pst_carve_workspace(m, workspace, total_residues, total_residues);
   PST_CUDA_OK(cudaMemsetAsync(ws.status, 0, 4 * sizeof(int32_t), st));
   int count;
@@ -352,6 +402,67 @@ int pst_tokenize(const pst_model* m, void* stream, const float* atoms, const uin
   count += pst_launch_quantize(m, st, ws.z, total_tokens, tokens_out, nullptr);
   m->launch_count = count;
   return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+}
+
+int pst_tokenize(const pst_model* m, void* stream, const float* atoms, const uint8_t* atom_mask,
+                 int atoms_per_residue, const int32_t* offsets, const int32_t* token_offsets, int num_structures,
+                 int total_residues, int total_tokens, int32_t* tokens_out, void* workspace,
+                 size_t workspace_bytes) {
+  int rc = check_batch(m, offsets, num_structures, total_residues, workspace, workspace_bytes, total_tokens);
+  if (rc != PST_OK) return rc;
+  if (!atoms || !token_offsets || !tokens_out || atoms_per_residue < 4) return PST_ERR_BAD_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PST_CUDA_OK(cudaSetDevice(m->device));
+  // ---- CUDA-graph path: the launch sequence depends only on the arguments below (the host never reads device
+  // data), so a call that repeats them replays the graph captured on their second occurrence.  Not used on the
+  // legacy / per-thread default streams (capture is not allowed there), while the caller is itself capturing
+  // (the launches then go into the caller's graph), or while the profiling spans are on.
+  PstGraphCache* gc = m->graphs;
+  const bool named_stream = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (gc && gc->enabled && named_stream && !m->prof_on) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+      PstGraphKey key{atoms, atom_mask, offsets, token_offsets, tokens_out, workspace, workspace_bytes,
+                      atoms_per_residue, num_structures, total_residues, total_tokens};
+      std::lock_guard<std::mutex> lock(gc->mu);
+      PstGraphEntry* e = gc->find(key);
+      if (!e) {
+        gc->insert(key);  // first sighting: run eagerly below, capture if it comes back
+      } else if (e->exec) {
+        e->last_use = ++gc->clock;
+        m->launch_count = e->launches;
+        return cudaGraphLaunch(e->exec, st) == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+      } else if (!e->failed) {
+        e->last_use = ++gc->clock;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          const int crc = tokenize_enqueue(m, st, atoms, atom_mask, atoms_per_residue, offsets, token_offsets,
+                                           num_structures, total_residues, total_tokens, tokens_out, workspace);
+          const cudaError_t end = cudaStreamEndCapture(st, &graph);
+          if (crc == PST_OK && end == cudaSuccess && graph &&
+              cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess) {
+            e->launches = m->launch_count;
+            cudaGraphDestroy(graph);
+            return cudaGraphLaunch(e->exec, st) == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+          }
+          if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();  // a failed capture is not an error of the call: enqueue eagerly from now on
+        e->exec = nullptr;
+        e->failed = true;
+      }
+    }
+  }
+  return tokenize_enqueue(m, st, atoms, atom_mask, atoms_per_residue, offsets, token_offsets, num_structures,
+                          total_residues, total_tokens, tokens_out, workspace);
+}
+
+int pst_graph_cache_enable(const pst_model* m, int enable) {
+  if (!m || !m->graphs) return PST_ERR_BAD_ARGUMENT;
+  std::lock_guard<std::mutex> lock(m->graphs->mu);
+  m->graphs->enabled = enable != 0;
+  if (!enable) m->graphs->clear();
+  return PST_OK;
 }
 
 }  // extern "C"

@@ -72,6 +72,9 @@ struct pst_model {
   float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
   int32_t basis[PST_C8], half_width[PST_C8];
   mutable int launch_count;
+  // CUDA-graph cache of the fused hot call (api.cu): a pst_tokenize call whose arguments (pointers and sizes) repeat
+  // is captured once and replayed, which removes the launch gaps between its ~110 dependent kernels
+  mutable struct PstGraphCache* graphs;
   // optional per-kernel-group timing (pst_profile_*): CUDA events recorded on the call's stream
   mutable bool prof_on;
   mutable int prof_n;

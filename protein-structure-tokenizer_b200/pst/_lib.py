@@ -51,6 +51,7 @@ SIGNATURES = {
     "pst_parse_pdb": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "pst_read_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pst_last_launch_count": (C.c_int, [C.c_void_p]),
+    "pst_graph_cache_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pst_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pst_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }

@@ -60,6 +60,9 @@ class StructureTokenizer:
         self._h = handle
         self._ws = None
         self.launches = 0
+        # pst_tokenize replays a CUDA graph for repeated argument sets, which needs a named stream: when the caller is
+        # on the default stream the fused call runs on this side stream, ordered with the caller's stream on both sides
+        self._side = torch.cuda.Stream(device=self.device)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -151,11 +154,23 @@ class StructureTokenizer:
         t = self.torch
         tokens = out if out is not None else t.empty((T,), dtype=t.int32, device=self.device)
         ws = self._workspace(R, B)
-        _lib.check(self.lib.pst_tokenize(self._h, self._stream(), atoms.data_ptr(), _ptr(atom_mask), int(atoms.shape[1]),
-                                         offsets_dev.data_ptr(), token_offsets_dev.data_ptr(), B, R, T,
-                                         tokens.data_ptr(), ws.data_ptr(), ws.numel()), "pst_tokenize")
+        cur = t.cuda.current_stream(self.device)
+        on_default = cur.cuda_stream == 0
+        run = self._side if on_default else cur
+        if on_default:
+            run.wait_stream(cur)
+        rc = self.lib.pst_tokenize(self._h, run.cuda_stream, atoms.data_ptr(), _ptr(atom_mask), int(atoms.shape[1]),
+                                   offsets_dev.data_ptr(), token_offsets_dev.data_ptr(), B, R, T,
+                                   tokens.data_ptr(), ws.data_ptr(), ws.numel())
+        if on_default:
+            cur.wait_stream(run)  # later work on the caller's stream (and reuse of these buffers) is ordered after the call
+        _lib.check(rc, "pst_tokenize")
         self.launches = self.lib.pst_last_launch_count(self._h)
         return tokens
+
+    def graph_cache_enable(self, on: bool = True) -> None:
+        """CUDA-graph replay of repeated pst_tokenize calls (on by default; see include/pst_abi.h)."""
+        _lib.check(self.lib.pst_graph_cache_enable(self._h, int(on)), "pst_graph_cache_enable")
 
     def profile_enable(self, on: bool = True) -> None:
         _lib.check(self.lib.pst_profile_enable(self._h, int(on)), "pst_profile_enable")

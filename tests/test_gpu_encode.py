@@ -155,3 +155,49 @@ def test_tensor_core_modes_match_oracle(built_lib, precision, codebook, df, mean
     assert np.isfinite(z).all()
     assert errs.mean() <= mean_tol and errs.max() <= max_tol, (float(errs.mean()), float(errs.max()))
     assert agree / total >= min_agree, agree / total
+
+
+def test_graph_replay_matches_eager_and_follows_new_data(built_lib):
+    """pst_tokenize replays a CUDA graph when its argument set repeats (include/pst_abi.h: pst_graph_cache_enable).
+    The replayed call must give the tokens of the eager call, and, because only pointers and sizes are baked into
+    the graph, follow new contents written into the same buffers."""
+    import torch
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(4096, 1, precision="fp16")
+    tok = StructureTokenizer(cfg, init_params(cfg, 1, "rich"))
+    lengths = [80, 130, 64, 200]
+    batches = [syn.pack_backbones(syn.make_backbones(seed, lengths)) for seed in (3, 4)]
+    offs = batches[0][1]
+    toff = tok.token_offsets(offs)
+    B, R, T = len(lengths), int(offs[-1]), int(toff[-1])
+    o_dev, t_dev = torch.from_numpy(offs).cuda(), torch.from_numpy(toff).cuda()
+
+    # eager results (graph cache off), fresh buffers
+    tok.graph_cache_enable(False)
+    eager = [tok.tokenize_device(torch.from_numpy(a).cuda(), None, o_dev, t_dev, B, R, T).clone() for a, _ in batches]
+    tok.graph_cache_enable(True)
+
+    stage = torch.empty((R, 4, 3), dtype=torch.float32, device="cuda")
+    out = torch.empty((T,), dtype=torch.int32, device="cuda")
+    for rep in range(3):  # call 1 eager (first sighting), call 2 captures + replays, call 3 replays
+        for (a, _), want in zip(batches, eager):
+            stage.copy_(torch.from_numpy(a))
+            out.zero_()
+            tok.tokenize_device(stage, None, o_dev, t_dev, B, R, T, out=out)
+            torch.cuda.synchronize()
+            assert torch.equal(out, want), rep
+    assert tok.read_status() == 0
+    # the same on an explicitly named stream
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for rep in range(3):
+            stage.copy_(torch.from_numpy(batches[1][0]), non_blocking=False)
+            out.zero_()
+            tok.tokenize_device(stage, None, o_dev, t_dev, B, R, T, out=out)
+            s.synchronize()
+            assert torch.equal(out, eager[1]), rep
+    tok.close()
