@@ -22,6 +22,7 @@ from __future__ import annotations
 import logging
 import os
 import time
+from concurrent.futures import ThreadPoolExecutor
 from itertools import cycle, islice
 from typing import Any, Callable, List, Optional, Sequence
 
@@ -46,6 +47,17 @@ def load_structure(pdb_file_path: str, num_neighbor: int, padding_num_residue: i
             f"We currently don't support protein with less than {num_neighbor} residues"
             f"given: {sample.nb_residues}")
     return sample.device_arrays()
+
+
+def load_and_build_batch(files_paths: Sequence[str], max_seq_len: int, pad_token_id: int) -> np.ndarray:
+    """Token files back in: `<stem>_tokens.npy` (uint32 (1, n)) -> int32 [len(files), max_seq_len], truncated to
+    max_seq_len and right-padded with pad_token_id (scripts/inference_runner.py:114-133; the pad id comes from
+    config/structure_tokenizer/data/ablation_df_*.yaml `pad_token_id`)."""
+    out = np.full((len(files_paths), max_seq_len), pad_token_id, np.int32)
+    for i, path in enumerate(files_paths):
+        seq = np.load(path).astype(np.int32).reshape(1, -1)[:, :max_seq_len]
+        out[i, : seq.shape[-1]] = seq[0]
+    return out
 
 
 class _TokenizeFn:
@@ -128,14 +140,30 @@ class InferenceRunner:
         num_iteration = len(pdbs) // effective_batch_size + int((len(pdbs) % effective_batch_size) > 0)
         total = num_iteration * effective_batch_size
         pdbs = list(islice(cycle(pdbs), total))  # repeat the list to a multiple of the batch size
-        for it in range(num_iteration):
-            start = it * effective_batch_size
-            files = pdbs[start : start + effective_batch_size]
-            t0 = time.perf_counter()
-            batch = [load_structure(f, data_config.graph_max_neighbor, data_config.seq_max_size) for f in files]
-            out = quantize(model_params, random_key, batch)
-            for f, tok in zip(files, out["tokens"]):
+        # Host pipeline around the device call: the next batch is read and parsed (C++ parser, the GIL is released
+        # inside the ctypes call) and the previous batch's files are written while the GPU works on the current one.
+        # Errors keep the reference's order: a batch's parse error is raised when that batch's turn comes.
+        def load(it: int):
+            files = pdbs[it * effective_batch_size : (it + 1) * effective_batch_size]
+            return files, [load_structure(f, data_config.graph_max_neighbor, data_config.seq_max_size) for f in files]
+
+        def save(files, tokens):
+            for f, tok in zip(files, tokens):
                 name = os.path.basename(f).split(".pdb")[0]
                 np.save(os.path.join(token_save_path, name + "_tokens"), np.asarray(tok, np.uint32).reshape(1, -1))
-            if logger is not None:
-                logger.info(f"Took {time.perf_counter() - t0}s to tokenize")
+
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            nxt = pool.submit(load, 0) if num_iteration else None
+            pending_save = None
+            for it in range(num_iteration):
+                t0 = time.perf_counter()
+                files, batch = nxt.result()
+                nxt = pool.submit(load, it + 1) if it + 1 < num_iteration else None
+                out = quantize(model_params, random_key, batch)
+                if pending_save is not None:
+                    pending_save.result()
+                pending_save = pool.submit(save, files, out["tokens"])
+                if logger is not None:
+                    logger.info(f"Took {time.perf_counter() - t0}s to tokenize")
+            if pending_save is not None:
+                pending_save.result()

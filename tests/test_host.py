@@ -83,3 +83,17 @@ def test_synthetic_backbones_are_seeded_and_physical():
     assert atoms.shape == (160, 4, 3) and list(offs) == [0, 64, 160]
     L = syn.bucketed_lengths(1, 1000)
     assert L.min() >= 64 and L.max() <= 2048 and (L % 64 == 0).all()
+
+
+def test_load_and_build_batch_pads_and_truncates(tmp_path):
+    """Token files -> padded int32 batch (scripts/inference_runner.py:114-133)."""
+    from pst.inference_runner import load_and_build_batch
+
+    a = np.arange(5, dtype=np.uint32).reshape(1, -1)
+    b = (np.arange(9, dtype=np.uint32) + 100).reshape(1, -1)
+    np.save(tmp_path / "a_tokens", a)
+    np.save(tmp_path / "b_tokens", b)
+    out = load_and_build_batch([str(tmp_path / "a_tokens.npy"), str(tmp_path / "b_tokens.npy")], 7, 4097)
+    assert out.dtype == np.int32 and out.shape == (2, 7)
+    assert out[0].tolist() == [0, 1, 2, 3, 4, 4097, 4097]
+    assert out[1].tolist() == [100, 101, 102, 103, 104, 105, 106]
