@@ -534,8 +534,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
       const float mean = (sum2.x + sum2.y) * (1.0f / kD);
       const float var = fmaxf((sq2.x + sq2.y) * (1.0f / kD) - mean * mean, 0.f);
       const float inv = rsqrtf(var + 1e-5f);
-      const float2 inv2 = make_float2(inv, inv), nmean2 = make_float2(-mean, -mean);
-      // pass 2: y = v * (inv * scale) + (offset - mean * inv * scale) -> 16-bit image of the new edge state
+      const float2 inv2 = make_float2(inv, inv), nmi2 = make_float2(-mean * inv, -mean * inv);
+      // pass 2: y = ((v - mean) * inv) * scale + offset (two packed fmas per pair) -> 16-bit image of the new edge state
       // (each thread touches only its own row of the buffer: no barrier between the passes), then a
       // row-coalesced copy-out.
 #pragma unroll 1
@@ -546,9 +546,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
         for (int c = 0; c < 8; ++c) {
           const float4 ls = *reinterpret_cast<const float4*>(sVec + 256 + q * 32 + c * 4);
           const float4 lo = *reinterpret_cast<const float4*>(sVec + 384 + q * 32 + c * 4);
-          const float2 a0 = mul2(make_float2(ls.x, ls.y), inv2), a1 = mul2(make_float2(ls.z, ls.w), inv2);
-          v[c * 2] = fma2(v[c * 2], a0, fma2(nmean2, a0, make_float2(lo.x, lo.y)));
-          v[c * 2 + 1] = fma2(v[c * 2 + 1], a1, fma2(nmean2, a1, make_float2(lo.z, lo.w)));
+          v[c * 2] = fma2(fma2(v[c * 2], inv2, nmi2), make_float2(ls.x, ls.y), make_float2(lo.x, lo.y));
+          v[c * 2 + 1] = fma2(fma2(v[c * 2 + 1], inv2, nmi2), make_float2(ls.z, ls.w), make_float2(lo.z, lo.w));
         }
         store_a_chunk2<T16>(sA, gt, q * 32, v);
       }
@@ -966,6 +965,7 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   if (mode == 0) {
     if (half) edge_mlp_tc_kernel<__half, 0><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
     else edge_mlp_tc_kernel<__nv_bfloat16, 0><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
+    if (!agg_out) return 1;  // the fused node kernel reads the partial sums directly
     combine_partials_kernel<<<(R + 7) / 8, 256, 0, st>>>(partial, K, R, agg_out);
     return 2;
   }

@@ -424,13 +424,13 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
         // message MLP: returns the per-receiver mean of the 2nd hidden layer; the 3rd linear commutes with
         // that mean (no activation follows it) and is applied by the node kernel
         PstSpan span(m, st, 1);
-        int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, ws.senders_abs, row_base, ws.partial, R, ws.tmp);
+        int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, ws.senders_abs, row_base, ws.partial, R, nullptr);  // the node kernel sums the partials itself
         if (n < 0) return n;
         L.count += n;
       }
       {
         PstSpan span(m, st, 3);
-        int n = pst_launch_node_update(m, st, l, ws.tmp, ws.h, R, ps2, pr2, ps, pr);
+        int n = pst_launch_node_update(m, st, l, ws.partial, ws.h, R, ps2, pr2, ps, pr);
         if (n < 0) return n;
         L.count += n;
       }

@@ -427,7 +427,8 @@ __device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_
 
 // ------------------------------------------------------------------------------------------------------------
 struct NodeUpdateParams {
-  const float* tbar;  // [R,128]
+  const float* partial;  // [num_edge_tiles][4][128]: per-receiver partial row sums written by the message-mode edge kernel
+  int K;
   float* h;           // [R,128] in / out
   const float *b3, *ln0_s, *ln0_o, *ffn_b1, *ffn_b2, *ln1_s, *ln1_o;
   const uint8_t* const* sched;
@@ -461,7 +462,24 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
     const bool valid = row < p.R;
     float x[2][32];
     // ---- 1. agg = tbar . W3 -------------------------------------------------------------------------------
-    load_row_half(e, p.tbar + (size_t)row * D, valid, x);
+    // tbar[row] = (sum of the partial row sums of the one or two 128-edge tiles that hold the row's K edges) / K
+    {
+      const int e0 = row * p.K, t0 = e0 >> 7, t1 = (e0 + p.K - 1) >> 7;
+      load_row_half(e, p.partial + ((size_t)t0 * 4 + (row - (t0 * 128) / p.K)) * D, valid, x);
+      if (valid && t1 != t0) {
+        float y[2][32];
+        load_row_half(e, p.partial + ((size_t)t1 * 4 + (row - (t1 * 128) / p.K)) * D, true, y);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[q][j] += y[q][j];
+      }
+      const float kf = (float)p.K;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[q][j] = x[q][j] / kf;
+    }
     split_store_half(e, X, x);
     publish();
     G.issue(X_addr, t_acc0, 0u);
@@ -821,13 +839,13 @@ void pst_destroy_node_chain(pst_model* m) {
 
 // h <- node update of MPNN layer `layer` (see the header); for layer < last also the four fp16 addend tables:
 // out_edge_s/r for this layer's edge MLP, out_msg_s/r for the next layer's message MLP.
-int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* tbar, float* h, int R,
+int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, float* h, int R,
                            uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r) {
   if (!m->node_chain || R <= 0) return 0;
   const PstNodeChain& C = *m->node_chain;
   const PstLayerW& w = m->w.layer[layer];
   NodeUpdateParams p{};
-  p.tbar = tbar; p.h = h;
+  p.partial = partial; p.K = m->cfg.num_neighbor; p.h = h;
   p.b3 = w.msg_b3; p.ln0_s = w.ln0_s; p.ln0_o = w.ln0_o; p.ffn_b1 = w.ffn_b1; p.ffn_b2 = w.ffn_b2; p.ln1_s = w.ln1_s; p.ln1_o = w.ln1_o;
   p.sched = C.sched_dev + C.layer_off[layer];
   p.n_sched = C.layer_n[layer];

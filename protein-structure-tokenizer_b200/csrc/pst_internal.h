@@ -171,7 +171,7 @@ int pst_launch_linear_tc(const pst_model* m, cudaStream_t st, const float* A, co
 const uint8_t* pst_linear_tc_image(const pst_model* m, const float* W, int K, int N);
 int pst_prepare_node_chain(pst_model* m);
 void pst_destroy_node_chain(pst_model* m);
-int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* tbar, float* h, int R,
+int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, float* h, int R,
                            uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r);
 int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z);
 
