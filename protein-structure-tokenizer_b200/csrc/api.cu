@@ -148,7 +148,7 @@ PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T) {
   const size_t RT = (size_t)(R > T ? R : T);
   ws.status = (int32_t*)take(4 * sizeof(int32_t));
   ws.row_base = (int32_t*)take((size_t)R * sizeof(int32_t));
-  ws.redo = (int32_t*)take((size_t)R * sizeof(int32_t));
+  ws.redo = (int32_t*)take((size_t)(R + 1) * sizeof(int32_t));  // [0] = count, [1..] = rows
   ws.prep = (double*)take((size_t)R * PST_PREP_STRIDE * sizeof(double));
   ws.cen4 = (double*)take((size_t)R * 4 * sizeof(double));
   ws.senders = (int32_t*)take(E * sizeof(int32_t));
@@ -227,6 +227,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   m->node_chain = nullptr;
   m->embed_img_dev = nullptr;
   m->table16_dev = nullptr;
+  m->layer0_tables = nullptr;
   m->prof_on = false;
   m->prof_n = 0;
   for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i) m->prof_ev[i] = nullptr;
@@ -259,6 +260,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
     int rc = pst_prepare_tc_weights(m);
     if (rc == PST_OK) rc = pst_prepare_linear_tc(m);
     if (rc == PST_OK) rc = pst_prepare_node_chain(m);
+    if (rc == PST_OK) rc = pst_prepare_layer0_tables(m);
     if (rc != PST_OK) { pst_model_destroy(m); return rc; }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) { pst_model_destroy(m); return PST_ERR_CUDA; }
@@ -276,6 +278,7 @@ void pst_model_destroy(pst_model* m) {
   pst_destroy_linear_tc(m);
   if (m->embed_img_dev) cudaFree(m->embed_img_dev);
   if (m->table16_dev) cudaFree(m->table16_dev);
+  if (m->layer0_tables) cudaFree(m->layer0_tables);
   for (int i = 0; i < 2 * PST_PROF_MAX_SPANS; ++i)
     if (m->prof_ev[i]) cudaEventDestroy(m->prof_ev[i]);
   delete m;

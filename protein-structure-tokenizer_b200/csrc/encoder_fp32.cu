@@ -203,6 +203,21 @@ __global__ void node_embed_kernel(const float* __restrict__ table, const int32_t
       *reinterpret_cast<const float4*>(table + (size_t)local * D + lane * 4);
 }
 
+// Tensor-core modes: the same lookup plus the two layer-1 addend tables.  h0 depends only on the position inside the
+// structure, so (h0 . W1[0:128]) and (h0 . W1[128:256] + b1) of the first message MLP are position-indexed constant
+// tables as well (computed once at model creation by the same tensor-core linear, pst_prepare_layer0_tables).
+__global__ void node_embed_tables_kernel(const float* __restrict__ table, const __half* __restrict__ ps0,
+                                         const __half* __restrict__ pr0, const int32_t* __restrict__ row_base,
+                                         float* __restrict__ h, __half* __restrict__ ps, __half* __restrict__ pr, int rows) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const size_t local = (size_t)(row - row_base[row]);
+  *reinterpret_cast<float4*>(h + (size_t)row * D + lane * 4) = *reinterpret_cast<const float4*>(table + local * D + lane * 4);
+  *reinterpret_cast<uint2*>(ps + (size_t)row * D + lane * 4) = *reinterpret_cast<const uint2*>(ps0 + local * D + lane * 4);
+  *reinterpret_cast<uint2*>(pr + (size_t)row * D + lane * 4) = *reinterpret_cast<const uint2*>(pr0 + local * D + lane * 4);
+}
+
 // res0[t] = token_table[t - token_offsets[b]]             (modules.py:486-500)
 __global__ void token_embed_kernel(const float* __restrict__ table, const int32_t* __restrict__ token_offsets, int B,
                                    float* __restrict__ res, int T) {
@@ -380,6 +395,23 @@ struct Launcher {
 
 }  // namespace
 
+// Model creation (tensor-core modes, after pst_prepare_linear_tc): the layer-1 addend tables by position,
+// [2][seq_max_size][128] fp16, from the node PE table with the tensor-core linear the per-batch path used to run.
+int pst_prepare_layer0_tables(pst_model* m) {
+  const int n = m->cfg.seq_max_size;
+  if (cudaMalloc(&m->layer0_tables, (size_t)2 * n * D * sizeof(uint16_t)) != cudaSuccess) return PST_ERR_CUDA;
+  Launcher L{nullptr};
+  L.model = m;
+  const PstLayerW& w0 = m->w.layer[0];
+  float* ps0 = reinterpret_cast<float*>(m->layer0_tables);
+  float* pr0 = reinterpret_cast<float*>(m->layer0_tables + (size_t)n * D);
+  const int before = L.count;
+  L.gemm(m->w.node_table, w0.msg_w1, ps0, n, D, D, Launcher::epi(nullptr), 1);
+  L.gemm(m->w.node_table, w0.msg_w1 + D * D, pr0, n, D, D, Launcher::epi(w0.msg_b1), 1);
+  (void)before;
+  return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+}
+
 int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edge_feat,
                            const int32_t* senders, const int32_t* offsets,
                            const int32_t* token_offsets, int B, int R, int T, float* z_out,
@@ -393,7 +425,13 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   int32_t* row_base = ws.row_base;
   row_base_kernel<<<(R + 255) / 256, 256, 0, st>>>(offsets, B, R, row_base);
   ++L.count;
-  node_embed_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->w.node_table, row_base, ws.h, R);
+  if (tc && m->layer0_tables)
+    node_embed_tables_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->w.node_table, reinterpret_cast<const __half*>(m->layer0_tables),
+                                                         reinterpret_cast<const __half*>(m->layer0_tables) + (size_t)cfg.seq_max_size * D,
+                                                         row_base, ws.h, reinterpret_cast<__half*>(ws.ps),
+                                                         reinterpret_cast<__half*>(ws.pr), R);
+  else
+    node_embed_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->w.node_table, row_base, ws.h, R);
   ++L.count;
   {
     size_t smem = 2 * ((size_t)K * 28 * sizeof(float) + (size_t)K * sizeof(int));
@@ -416,9 +454,11 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     uint16_t* ps2 = reinterpret_cast<uint16_t*>(ws.agg);
     uint16_t* pr2 = reinterpret_cast<uint16_t*>(ws.u);
     L.count += pst_launch_abs_senders(m, st, senders, row_base, R, ws.senders_abs);
-    const PstLayerW& w0 = m->w.layer[0];
-    L.gemm(ws.h, w0.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr), 1);
-    L.gemm(ws.h, w0.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w0.msg_b1), 1);
+    if (!m->layer0_tables) {
+      const PstLayerW& w0 = m->w.layer[0];
+      L.gemm(ws.h, w0.msg_w1, ws.ps, R, D, D, Launcher::epi(nullptr), 1);
+      L.gemm(ws.h, w0.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w0.msg_b1), 1);
+    }
     for (int l = 0; l < cfg.gnn_layers; ++l) {
       {
         // message MLP: returns the per-receiver mean of the 2nd hidden layer; the 3rd linear commutes with

@@ -80,15 +80,12 @@ __device__ __forceinline__ bool key_greater(unsigned long long ka, int ia, unsig
 // sorted (bitonic network in shared memory, keys = fp64 bit patterns, which order
 // like the values because distances are >= +0) and the first K+1 ranks are used.
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads)
-knn_feature_kernel(const double* __restrict__ prep, const int32_t* __restrict__ offsets, int B, int R,
-                   int K, int max_len, int32_t* __restrict__ senders, float* __restrict__ feat,
-                   int32_t* __restrict__ status, const int32_t* __restrict__ redo) {
+__device__ __forceinline__ void knn_feature_row(const int row, const double* __restrict__ prep, const int32_t* __restrict__ offsets,
+                                                int B, int R, int K, int max_len, int32_t* __restrict__ senders,
+                                                float* __restrict__ feat, int32_t* __restrict__ status) {
   extern __shared__ unsigned long long smem_keys[];
   __shared__ int s_struct[2];
-  const int row = blockIdx.x;
   const int tid = threadIdx.x;
-  if (redo && !redo[row]) return;  // second pass: only the rows the warp kernel flagged
   if (tid == 0) {
     int lo = 0, hi = B;  // largest b with offsets[b] <= row
     while (hi - lo > 1) {
@@ -176,6 +173,27 @@ knn_feature_kernel(const double* __restrict__ prep, const int32_t* __restrict__ 
   }
 }
 
+// every row (configurations the warp kernel does not cover)
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
+knn_feature_kernel(const double* __restrict__ prep, const int32_t* __restrict__ offsets, int B, int R, int K, int max_len,
+                   int32_t* __restrict__ senders, float* __restrict__ feat, int32_t* __restrict__ status) {
+  knn_feature_row<kThreads>(blockIdx.x, prep, offsets, B, R, K, max_len, senders, feat, status);
+}
+
+// only the rows the warp kernel flagged: redo[0] = how many, redo[1..] = which (normally none: a small fixed grid
+// reads the count and leaves, instead of one block per row finding its flag clear)
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
+knn_feature_redo_kernel(const double* __restrict__ prep, const int32_t* __restrict__ offsets, int B, int R, int K, int max_len,
+                        int32_t* __restrict__ senders, float* __restrict__ feat, int32_t* __restrict__ status,
+                        const int32_t* __restrict__ redo) {
+  const int n = redo[0];
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    knn_feature_row<kThreads>(redo[1 + i], prep, offsets, B, R, K, max_len, senders, feat, status);
+    __syncthreads();  // the shared key / index arrays are reused by the next row
+  }
+}
 
 // -------------------------------------------------------------------------------------------------
 // Warp-per-row k-NN: the L distances of a row are streamed in chunks of 64 (2 per lane); each chunk is
@@ -327,7 +345,7 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
     bool clash = (2 * lane + 1 <= K + 2) && ((b0 >> 11) == (b1 >> 11)) && (b1 != 0xFFFFFFFFFFFFFFFFull);
     clash = clash || ((2 * lane + 2 <= K + 2) && lane < 31 && ((b1 >> 11) == (nxt >> 11)) && (nxt != 0xFFFFFFFFFFFFFFFFull));
     if (__any_sync(0xffffffffu, clash)) {
-      if (lane == 0) redo[row] = 1;
+      if (lane == 0) redo[1 + atomicAdd(redo, 1)] = row;
       return;
     }
   }
@@ -384,16 +402,17 @@ int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(knn_feature_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (m->cfg.num_neighbor <= 60 && m->cfg.max_len <= 2048) {
-    cudaMemsetAsync(redo, 0, (size_t)R * sizeof(int32_t), st);
+    cudaMemsetAsync(redo, 0, sizeof(int32_t), st);  // the counter
     knn_warp_kernel<<<(R + kKnnWarps - 1) / kKnnWarps, kKnnWarps * 32, 0, st>>>(
         prep, reinterpret_cast<const double4*>(cen4), offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len, senders,
         edge_feat, status, redo);
     // exact recompute of the (normally zero) rows flagged above
-    knn_feature_kernel<kThreads><<<R, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,
-                                                           senders, edge_feat, status, redo);
+    cudaFuncSetAttribute(knn_feature_redo_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    knn_feature_redo_kernel<kThreads><<<min(R, 2 * m->num_sms), kThreads, smem, st>>>(
+        prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len, senders, edge_feat, status, redo);
     return 3;
   }
   knn_feature_kernel<kThreads><<<R, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,
-                                                         senders, edge_feat, status, nullptr);
+                                                         senders, edge_feat, status);
   return 2;
 }

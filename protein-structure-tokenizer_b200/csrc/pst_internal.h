@@ -66,6 +66,7 @@ struct pst_model {
   PstTcWeights tc;
   uint16_t* embed_img_dev;   // hi/lo fp16 images of W_edge[128:155] (tensor-core input embedding)
   uint16_t* table16_dev;     // fp16 copy of edge_pe_table
+  uint16_t* layer0_tables;   // [2][seq_max][128] fp16: layer-1 message-MLP addend tables by position (tensor-core modes)
   PstLinearRegistry* linear_tc;  // split-fp16 operand images of the node-level weights (tensor-core modes)
   PstNodeChain* node_chain;      // weight streaming schedules of the fused node-level kernels (node_chain_tc.cu)
   // FSQ constants (model/quantize.py:175-181), fp32
@@ -101,7 +102,7 @@ size_t pst_fill_weight_pointers(const pst_config& cfg, const float* base, PstWei
 struct PstWorkspace {
   int32_t* status;       // [4]
   int32_t* row_base;     // [R]
-  int32_t* redo;         // [R] rows the packed-key k-NN kernel hands to the exact kernel
+  int32_t* redo;         // [1 + R] count, then the rows the packed-key k-NN kernel hands to the exact kernel
   double* prep;          // [R,16]
   double* cen4;          // [R,4] centroid (x,y,z,0): compact copy for the k-NN scan
   int32_t* senders;      // [E]
@@ -171,6 +172,7 @@ int pst_launch_linear_tc(const pst_model* m, cudaStream_t st, const float* A, co
 const uint8_t* pst_linear_tc_image(const pst_model* m, const float* W, int K, int N);
 int pst_prepare_node_chain(pst_model* m);
 void pst_destroy_node_chain(pst_model* m);
+int pst_prepare_layer0_tables(pst_model* m);  // encoder_fp32.cu
 int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, float* h, int R,
                            uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r);
 int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z);
