@@ -336,6 +336,15 @@ def run_ours(args):
                           f"({ms_prof_total / args.steps:.3f} ms/step, kernels enqueued one by one); the timed region "
                           f"itself replays the call's CUDA graph ({ms_step:.3f} ms/step)",
                 "featurize_knn_ms_per_step": prof_ms[0] / max(1, prof_cnt[0]),
+                # per-step kernel-group times of the same pass (group average x groups per step)
+                "kernel_ms_per_step": {
+                    "featurize_knn": prof_ms[0] / max(1, prof_cnt[0]),
+                    "input_embeddings": prof_ms[4] / max(1, prof_cnt[4]),
+                    "message_mlp": prof_ms[1] / max(1, prof_cnt[1]) * cfg.gnn_layers,
+                    "node_update": prof_ms[3] / max(1, prof_cnt[3]) * cfg.gnn_layers,
+                    "edge_update_mlp": prof_ms[2] / max(1, prof_cnt[2]) * (cfg.gnn_layers - 1),
+                    "resampler_head_df1": prof_ms[5] / max(1, prof_cnt[5]) if prof_cnt[5] else None,
+                },
                 "end_to_end_frac": value / world * FLOP_PER_RESIDUE.get(df, 44.91e6) / 1e12 / peak,
             }
         line = {

@@ -691,17 +691,21 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
   const uint32_t tmem_row = tmem_acc + ((uint32_t)(wq * 32) << 16);
   const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), mbar_addr = smem_u32(&mbar[g]);
   uint32_t parity = 0;
+  // table row of this thread's edge: sender - receiver (local indices) + seq_max - 1; the two dependent index loads
+  // are issued one tile ahead
+  auto table_row = [&](int tile_) {
+    const int er_ = tile_ * kTileM + gt;
+    if (tile_ >= p.num_tiles || er_ >= p.E) return 0;
+    const int recv = er_ / p.K;
+    return __ldg(p.senders + er_) - (recv - __ldg(p.row_base + recv)) + (p.seq_max - 1);
+  };
+  int trow_next = table_row(blockIdx.x * kGroups + g);
+  bool store_pending = false;  // thread gt == 0: a TMA store of the previous tile may still be reading the buffer
 
   for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
     const int row0 = tile * kTileM;
-    const int er = row0 + gt;
     const int last_row = min(p.E - row0, kTileM);
-    // table row of this thread's edge: sender - receiver (local indices) + seq_max - 1
-    int trow = 0;
-    if (er < p.E) {
-      const int recv = er / p.K;
-      trow = __ldg(p.senders + er) - (recv - __ldg(p.row_base + recv)) + (p.seq_max - 1);
-    }
+    const int trow = trow_next;
     // ---- features -> fp16 hi / lo operand images (A_hi at K block 0, A_lo at K block 1 of the buffer) ----
     {
       const float* f0 = p.feat + (size_t)row0 * PST_EDGE_FEATURES;
@@ -725,6 +729,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.senders + nrow0) + (gt - 124) * 128));
         }
       }
+      trow_next = table_row(tile + gridDim.x * kGroups);
+      // the buffer is free once the previous tile's TMA store has read it: waited for here, behind the loads above
+      if (gt == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      group_sync(g);
 #pragma unroll
       for (int i = 0; i < PST_EDGE_FEATURES; ++i) {
         const int idx = gt + i * 128;
@@ -746,12 +754,12 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
     }
     // this thread's row of the fp16 PE table (256 B, eight 32-byte loads): issued now, consumed in the epilogue, so
     // the L2 latency hides behind the barrier and the MMA
-    uint32_t tab[64];
-    {
-      const uint32_t* tb = reinterpret_cast<const uint32_t*>(p.table + (size_t)trow * kD);
+    // (in two halves: the second one is issued at the start of the epilogue and lands while the first is consumed,
+    // which keeps the kernel clear of register spills: with 226 KB of shared memory there is no L1 behind local memory)
+    uint32_t tabA[32], tabB[32];
+    const uint32_t* tb = reinterpret_cast<const uint32_t*>(p.table + (size_t)trow * kD);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ldg256(tb + i * 8, &tab[i * 8]);
-    }
+    for (int i = 0; i < 4; ++i) ldg256(tb + i * 8, &tabA[i * 8]);
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
@@ -772,11 +780,13 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
     // ---- epilogue: acc + table row -> 16-bit edge state in the operand image layout of the (now free) buffer,
     // which is also the layout of the TMA store boxes (each thread only touches its own row) ----
 #pragma unroll
+    for (int i = 0; i < 4; ++i) ldg256(tb + 32 + i * 8, &tabB[i * 8]);
+#pragma unroll
     for (int q = 0; q < 4; ++q) {
       float2 v[16];
       tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = add2(v[c], Unpack<__half>::two(tab[q * 16 + c]));
+      for (int c = 0; c < 16; ++c) v[c] = add2(v[c], Unpack<__half>::two(q < 2 ? tabA[q * 16 + c] : tabB[(q - 2) * 16 + c]));
       store_a_chunk2<T16>(sA, gt, q * 32, v);
     }
     fence_proxy_async();
@@ -786,9 +796,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
       tma_store_2d(&tmap_e, 0, row0, sA_addr);
       tma_store_2d(&tmap_e, 64, row0, sA_addr + kKBlockBytes);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      store_pending = true;
     }
-    group_sync(g);
   }
   if (gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();

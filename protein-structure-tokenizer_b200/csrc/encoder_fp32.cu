@@ -423,6 +423,8 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   Launcher L{st};
   if (tc) L.model = m;
   int32_t* row_base = ws.row_base;
+  {  // input embeddings
+  PstSpan embed_span(m, st, 4);
   row_base_kernel<<<(R + 255) / 256, 256, 0, st>>>(offsets, B, R, row_base);
   ++L.count;
   if (tc && m->layer0_tables)
@@ -444,6 +446,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       if (n < 0) return n;
     }
     ++L.count;
+  }
   }
   if (tc) {
     // Tensor-core modes: edge-level kernels (edge_mlp_tc.cu) alternate with ONE fused node-level kernel per layer
@@ -519,7 +522,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   // ---- resampler (CrossAttentionScaler, 3 blocks) -------------------------------------------
   if (tc && cfg.downsampling_ratio == 1) {
     // df = 1: token t attends residue t alone, the three blocks + head are row-local: one fused kernel
-    PstSpan span(m, st, 3);
+    PstSpan span(m, st, 5);
     int n = pst_launch_resampler_df1(m, st, ws.h, row_base, R, z_out);
     if (n < 0) return n;
     return L.count + n;

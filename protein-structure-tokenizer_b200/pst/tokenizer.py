@@ -176,10 +176,10 @@ class StructureTokenizer:
         _lib.check(self.lib.pst_profile_enable(self._h, int(on)), "pst_profile_enable")
 
     def profile_collect(self):
-        """-> (ms[4], groups[4]) accumulated since the last collect; kinds: 0 featurise+k-NN,
-        1 message MLP, 2 edge-update MLP."""
-        ms = (C.c_float * 4)()
-        cnt = (C.c_int * 4)()
+        """-> (ms[8], groups[8]) accumulated since the last collect; kinds: 0 featurise+k-NN, 1 message MLP,
+        2 edge-update MLP, 3 node update, 4 input embeddings, 5 fused df=1 resampler + head."""
+        ms = (C.c_float * 8)()
+        cnt = (C.c_int * 8)()
         _lib.check(self.lib.pst_profile_collect(self._h, ms, cnt), "pst_profile_collect")
         return list(ms), list(cnt)
 

@@ -9,7 +9,7 @@ for v in "$@"; do
 import json
 try:
     d = json.loads([l for l in open("gpurun_out/${tag}_$v.json") if l.startswith("{")][-1])
-    print("$v", "ms/step %.3f" % d["ms_per_step"], "edge avg launch ms %.4f" % d["roofline"]["avg_launch_ms"], "agree", d.get("token_agreement"))
+    print("$v", "ms/step %.3f" % d["ms_per_step"], {k: (round(x, 3) if x else x) for k, x in d["roofline"]["kernel_ms_per_step"].items()}, (d.get("token_agreement") or {}).get("vs_gpu_fp32_mode_pct"))
 except Exception as e:
     print("$v", "failed", e)
 PY
