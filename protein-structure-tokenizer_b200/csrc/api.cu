@@ -392,14 +392,19 @@ static int tokenize_enqueue(const pst_model* m, cudaStream_t st, const float* at
                             void* workspace) {
   PstWorkspace ws = pst_carve_workspace(m, workspace, total_residues, total_residues);
   PST_CUDA_OK(cudaMemsetAsync(ws.status, 0, 4 * sizeof(int32_t), st));
+  // Tensor-core modes: the features travel to the embedding kernel in the compact layout (16 floats per edge; the
+  // RBFs are evaluated there in fp32).  The fp32 mode and the two-call path (pst_featurize_knn + pst_encode_graph)
+  // use the 27 fp32 features of the reference.
+  const int compact = (m->cfg.precision != PST_PREC_FP32 && pst_featurize_compact_ok(m)) ? 1 : 0;
   int count;
   {
     PstSpan span(m, st, 0);
     count = pst_launch_featurize(m, st, atoms, atom_mask, atoms_per_residue, offsets, num_structures,
-                                 total_residues, ws.senders, ws.edge_feat, ws.prep, ws.cen4, ws.status, ws.redo);
+                                 total_residues, ws.senders, ws.edge_feat, ws.prep, ws.cen4, ws.status, ws.redo, compact);
   }
+  if (count < 0) return count;
   int n = pst_launch_encode_fp32(m, st, ws.edge_feat, ws.senders, offsets, token_offsets, num_structures,
-                                 total_residues, total_tokens, ws.z, ws);
+                                 total_residues, total_tokens, ws.z, ws, compact);
   if (n < 0) return n;
   count += n;
   count += pst_launch_quantize(m, st, ws.z, total_tokens, tokens_out, nullptr);

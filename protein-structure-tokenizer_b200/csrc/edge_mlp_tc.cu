@@ -646,7 +646,7 @@ constexpr uint32_t kEmbSmemTotal = kEmbSmemW + kSmemA + kGroups * 256 + 64;
 struct EmbedParams {
   const uint16_t* w_img;     // hi image (16 KB) then lo image (16 KB)
   const __half* table;       // [2*seq_max-1, 128] fp16
-  const float* feat;         // [E, 27]
+  const float* feat;         // [E, 27], or [E, 16] in the compact layout (see the kernel)
   const int32_t* senders;    // [E]
   const int32_t* row_base;   // [R]
   uint16_t* e;               // [E, 128] out
@@ -658,7 +658,7 @@ __device__ __forceinline__ uint32_t swz_k64(uint32_t row, uint32_t kk) {  // ele
   return row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1));
 }
 
-template <typename T16>
+template <typename T16, bool COMPACT>
 __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams p, const __grid_constant__ CUtensorMap tmap_e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
@@ -707,6 +707,68 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
     const int last_row = min(p.E - row0, kTileM);
     const int trow = trow_next;
     // ---- features -> fp16 hi / lo operand images (A_hi at K block 0, A_lo at K block 1 of the buffer) ----
+    if (COMPACT) {
+      // Fused tokenize path: 16 floats per edge from the k-NN kernel, [d*d, 12 orientation features, 0, 0, 0].  Each
+      // thread reads its own edge row (four 16-byte loads, whole sectors), evaluates the 15 RBFs exp(-d*d / 1.5^k)
+      // (utils/protein_utils.py:257-281) in fp32 with ex2.approx (relative error ~1e-6 where the value matters: far
+      // below the fp16 rounding of the embedding it feeds; the fp64 features of pst_featurize_knn are untouched) and
+      // writes its row of both images with eight 16-byte stores.
+      const int er = row0 + gt;
+      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;
+      if (gt < last_row) {
+        const float4* src = reinterpret_cast<const float4*>(p.feat + (size_t)er * 16);
+        r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2); r3 = __ldg(src + 3);
+      }
+      {
+        const int nt = tile + gridDim.x * kGroups;
+        if (nt < p.num_tiles) {
+          const size_t nrow0 = (size_t)nt * kTileM;
+          if (gt < 64 && nrow0 + (size_t)gt * 2 < (size_t)p.E)  // 128 rows x 64 B = 64 lines
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.feat + nrow0 * 16) + gt * 128));
+          if (gt >= 124 && nrow0 + (size_t)(gt - 124) * 32 < (size_t)p.E)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.senders + nrow0) + (gt - 124) * 128));
+        }
+      }
+      trow_next = table_row(tile + gridDim.x * kGroups);
+      float f[32];
+      {
+        // -log2(e) / 1.5^k, k = 0..14
+        constexpr float kC[15] = {-1.44269504f, -0.961796694f, -0.641197796f, -0.427465197f, -0.284976798f,
+                                  -0.189984532f, -0.126656355f, -0.0844375698f, -0.0562917132f, -0.0375278088f,
+                                  -0.0250185392f, -0.0166790261f, -0.0111193507f, -0.00741290049f, -0.00494193366f};
+#pragma unroll
+        for (int k = 0; k < 15; ++k) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f[k]) : "f"(r0.x * kC[k]));
+        f[15] = r0.y; f[16] = r0.z; f[17] = r0.w;
+        f[18] = r1.x; f[19] = r1.y; f[20] = r1.z; f[21] = r1.w;
+        f[22] = r2.x; f[23] = r2.y; f[24] = r2.z; f[25] = r2.w;
+        f[26] = r3.x;
+#pragma unroll
+        for (int k = 27; k < 32; ++k) f[k] = 0.f;
+        if (gt >= last_row) {
+#pragma unroll
+          for (int k = 0; k < 15; ++k) f[k] = 0.f;
+        }
+      }
+      // the buffer is free once the previous tile's TMA store has read it: waited for here, behind the loads above
+      if (gt == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      group_sync(g);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = f[c * 8 + 2 * j], b = f[c * 8 + 2 * j + 1];
+          const __half2 h = __floats2half2_rn(a, b);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+          hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+          lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const uint32_t off = swz_k64(gt, c * 8);
+        *reinterpret_cast<uint4*>(sA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sA + kKBlockBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    } else
     {
       const float* f0 = p.feat + (size_t)row0 * PST_EDGE_FEATURES;
       const int n_el = last_row * PST_EDGE_FEATURES;
@@ -895,8 +957,10 @@ int pst_prepare_tc_weights(pst_model* m) {
     if (cudaMalloc(&m->table16_dev, (size_t)n_table * sizeof(uint16_t)) != cudaSuccess) return PST_ERR_CUDA;
     build_embed_images_kernel<<<32, 256>>>(m->w.edge_feat_w, m->embed_img_dev);
     to_half_kernel<<<(n_table + 255) / 256, 256>>>(m->w.edge_pe_table, reinterpret_cast<__half*>(m->table16_dev), n_table);
-    if (cudaFuncSetAttribute(edge_embed_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemTotal) != cudaSuccess ||
-        cudaFuncSetAttribute(edge_embed_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemTotal) != cudaSuccess)
+    if (cudaFuncSetAttribute(edge_embed_tc_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemTotal) != cudaSuccess ||
+        cudaFuncSetAttribute(edge_embed_tc_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemTotal) != cudaSuccess ||
+        cudaFuncSetAttribute(edge_embed_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemTotal) != cudaSuccess ||
+        cudaFuncSetAttribute(edge_embed_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemTotal) != cudaSuccess)
       return PST_ERR_CUDA;
   }
   if (cudaGetLastError() != cudaSuccess) return PST_ERR_CUDA;
@@ -984,7 +1048,7 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
 }
 
 int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* feat, const int32_t* senders,
-                             const int32_t* row_base, int R, uint16_t* e) {
+                             const int32_t* row_base, int R, uint16_t* e, int compact) {
   EmbedParams p{};
   p.w_img = m->embed_img_dev;
   p.table = reinterpret_cast<const __half*>(m->table16_dev);
@@ -1003,8 +1067,14 @@ int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* f
   if (grid > need) grid = need;
   CUtensorMap tmap;
   if (int rc = make_edge_state_map(e, p.E, &tmap)) return rc;
-  if (m->cfg.precision == PST_PREC_FP16) edge_embed_tc_kernel<__half><<<grid, kThreads, kEmbSmemTotal, st>>>(p, tmap);
-  else edge_embed_tc_kernel<__nv_bfloat16><<<grid, kThreads, kEmbSmemTotal, st>>>(p, tmap);
+  const bool half = m->cfg.precision == PST_PREC_FP16;
+  if (compact) {
+    if (half) edge_embed_tc_kernel<__half, true><<<grid, kThreads, kEmbSmemTotal, st>>>(p, tmap);
+    else edge_embed_tc_kernel<__nv_bfloat16, true><<<grid, kThreads, kEmbSmemTotal, st>>>(p, tmap);
+  } else {
+    if (half) edge_embed_tc_kernel<__half, false><<<grid, kThreads, kEmbSmemTotal, st>>>(p, tmap);
+    else edge_embed_tc_kernel<__nv_bfloat16, false><<<grid, kThreads, kEmbSmemTotal, st>>>(p, tmap);
+  }
   return 1;
 }
 

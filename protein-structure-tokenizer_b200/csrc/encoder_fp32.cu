@@ -415,7 +415,7 @@ int pst_prepare_layer0_tables(pst_model* m) {
 int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edge_feat,
                            const int32_t* senders, const int32_t* offsets,
                            const int32_t* token_offsets, int B, int R, int T, float* z_out,
-                           PstWorkspace& ws) {
+                           PstWorkspace& ws, int compact_features) {
   const pst_config& cfg = m->cfg;
   const int K = cfg.num_neighbor;
   const int E = R * K;
@@ -438,11 +438,12 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   {
     size_t smem = 2 * ((size_t)K * 28 * sizeof(float) + (size_t)K * sizeof(int));
     const int grid = (R + 1) / 2;
+    if (compact_features && cfg.precision == PST_PREC_FP32) return PST_ERR_UNSUPPORTED_CONFIG;
     if (cfg.precision == PST_PREC_FP32)
       edge_embed_kernel<float><<<grid, 128, smem, st>>>(edge_feat, senders, row_base, m->w.edge_pe_table, m->w.edge_feat_w, K,
                                                         cfg.seq_max_size, R, ws.e);
     else {
-      int n = pst_launch_edge_embed_tc(m, st, edge_feat, senders, row_base, R, reinterpret_cast<uint16_t*>(ws.e));
+      int n = pst_launch_edge_embed_tc(m, st, edge_feat, senders, row_base, R, reinterpret_cast<uint16_t*>(ws.e), compact_features);
       if (n < 0) return n;
     }
     ++L.count;

@@ -79,7 +79,10 @@ __device__ __forceinline__ bool key_greater(unsigned long long ka, int ia, unsig
 // One block per residue row.  Distances to every residue of the same structure are
 // sorted (bitonic network in shared memory, keys = fp64 bit patterns, which order
 // like the values because distances are >= +0) and the first K+1 ranks are used.
-template <int kThreads>
+// COMPACT (the fused tokenize path of the tensor-core modes): instead of the 27 fp32 features the kernels write
+// 16 floats per edge, [d*d, p, q, k, t (12 orientation features), 0, 0, 0]; the 15 RBFs exp(-d*d / 1.5^k) are then
+// evaluated in fp32 by the edge-embedding kernel that consumes them (edge_mlp_tc.cu), see pst_launch_featurize.
+template <int kThreads, bool COMPACT>
 __device__ __forceinline__ void knn_feature_row(const int row, const double* __restrict__ prep, const int32_t* __restrict__ offsets,
                                                 int B, int R, int K, int max_len, int32_t* __restrict__ senders,
                                                 float* __restrict__ feat, int32_t* __restrict__ status) {
@@ -101,8 +104,9 @@ __device__ __forceinline__ void knn_feature_row(const int row, const double* __r
   if (L < K || L > max_len) {
     if (tid == 0) atomicMin(status, (int)PST_ERR_LENGTH_OUT_OF_RANGE);
     for (int e = tid; e < K; e += kThreads) senders[(size_t)row * K + e] = 0;
+    constexpr int kStride = COMPACT ? 16 : PST_EDGE_FEATURES;
     if (feat)
-      for (int t = tid; t < K * PST_EDGE_FEATURES; t += kThreads) feat[(size_t)row * K * PST_EDGE_FEATURES + t] = 0.f;
+      for (int t = tid; t < K * kStride; t += kThreads) feat[(size_t)row * K * kStride + t] = 0.f;
     return;
   }
   int n_pad = 64;
@@ -144,6 +148,32 @@ __device__ __forceinline__ void knn_feature_row(const int row, const double* __r
   if (!feat) return;
 
   const double ca_x = pi[3], ca_y = pi[4], ca_z = pi[5];
+  if (COMPACT) {
+    float* out = feat + (size_t)row * K * 16;
+    for (int t = tid; t < K * 16; t += kThreads) {
+      const int e = t >> 4, c = t & 15;
+      const int j = s_idx[first + e];
+      double val = 0.0;
+      if (c == 0) {
+        const double d = __longlong_as_double((long long)smem_keys[first + e]);
+        val = d * d;
+      } else if (c <= 12) {
+        const int g = (c - 1) / 3, r = (c - 1) - 3 * g;
+        const double* pj = prep + (size_t)(base + j) * PST_PREP_STRIDE;
+        double vx, vy, vz;
+        if (g == 0) {
+          vx = pj[3] - ca_x; vy = pj[4] - ca_y; vz = pj[5] - ca_z;
+        } else {
+          const double* sv = pj + 3 + 3 * g;
+          vx = sv[0]; vy = sv[1]; vz = sv[2];
+        }
+        const double* b = pi + 6 + 3 * r;
+        val = b[0] * vx + b[1] * vy + b[2] * vz;
+      }
+      out[t] = (float)val;
+    }
+    return;
+  }
   float* out = feat + (size_t)row * K * PST_EDGE_FEATURES;
   for (int t = tid; t < K * PST_EDGE_FEATURES; t += kThreads) {
     int e = t / PST_EDGE_FEATURES;
@@ -178,19 +208,19 @@ template <int kThreads>
 __global__ void __launch_bounds__(kThreads)
 knn_feature_kernel(const double* __restrict__ prep, const int32_t* __restrict__ offsets, int B, int R, int K, int max_len,
                    int32_t* __restrict__ senders, float* __restrict__ feat, int32_t* __restrict__ status) {
-  knn_feature_row<kThreads>(blockIdx.x, prep, offsets, B, R, K, max_len, senders, feat, status);
+  knn_feature_row<kThreads, false>(blockIdx.x, prep, offsets, B, R, K, max_len, senders, feat, status);
 }
 
 // only the rows the warp kernel flagged: redo[0] = how many, redo[1..] = which (normally none: a small fixed grid
 // reads the count and leaves, instead of one block per row finding its flag clear)
-template <int kThreads>
+template <int kThreads, bool COMPACT>
 __global__ void __launch_bounds__(kThreads)
 knn_feature_redo_kernel(const double* __restrict__ prep, const int32_t* __restrict__ offsets, int B, int R, int K, int max_len,
                         int32_t* __restrict__ senders, float* __restrict__ feat, int32_t* __restrict__ status,
                         const int32_t* __restrict__ redo) {
   const int n = redo[0];
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    knn_feature_row<kThreads>(redo[1 + i], prep, offsets, B, R, K, max_len, senders, feat, status);
+    knn_feature_row<kThreads, COMPACT>(redo[1 + i], prep, offsets, B, R, K, max_len, senders, feat, status);
     __syncthreads();  // the shared key / index arrays are reused by the next row
   }
 }
@@ -283,6 +313,7 @@ __device__ __forceinline__ unsigned long long packed_key(const double4& ci, cons
   return (bits & ~kIdxMask) | (unsigned long long)j;
 }
 
+template <bool COMPACT>
 __global__ void __launch_bounds__(kKnnWarps * 32)
 knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen4, const int32_t* __restrict__ offsets,
                 int B, int R, int K, int max_len, int32_t* __restrict__ senders, float* __restrict__ feat,
@@ -307,8 +338,9 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
   if (L < K || L > max_len) {
     if (lane == 0) atomicMin(status, (int)PST_ERR_LENGTH_OUT_OF_RANGE);
     for (int e = lane; e < K; e += 32) senders[(size_t)row * K + e] = 0;
+    constexpr int kStride = COMPACT ? 16 : PST_EDGE_FEATURES;
     if (feat)
-      for (int t = lane; t < K * PST_EDGE_FEATURES; t += 32) feat[(size_t)row * K * PST_EDGE_FEATURES + t] = 0.f;
+      for (int t = lane; t < K * kStride; t += 32) feat[(size_t)row * K * kStride + t] = 0.f;
     return;
   }
   const double4 ci = cen4[row];
@@ -366,6 +398,32 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
     s_d2[warp][e] = d * d;
   }
   __syncwarp();
+  if (COMPACT) {
+    // 16 floats per edge: [d*d, 12 orientation features, 0, 0, 0]; item -> lane keeps consecutive lanes on consecutive floats
+    float* out = feat + (size_t)row * K * 16;
+    const double ca_x = pi[3], ca_y = pi[4], ca_z = pi[5];
+    for (int t = lane; t < K * 16; t += 32) {
+      const int e = t >> 4, c = t & 15;
+      double val = 0.0;
+      if (c == 0) {
+        val = s_d2[warp][e];
+      } else if (c <= 12) {
+        const int g = (c - 1) / 3, r = (c - 1) - 3 * g;
+        const double* pj = prep + (size_t)(base + s_j[warp][first + e]) * PST_PREP_STRIDE;
+        double vx, vy, vz;
+        if (g == 0) {
+          vx = pj[3] - ca_x; vy = pj[4] - ca_y; vz = pj[5] - ca_z;
+        } else {
+          const double* sv = pj + 3 + 3 * g;
+          vx = sv[0]; vy = sv[1]; vz = sv[2];
+        }
+        const double* b = pi + 6 + 3 * r;
+        val = b[0] * vx + b[1] * vy + b[2] * vz;
+      }
+      out[t] = (float)val;
+    }
+    return;
+  }
   float* out = feat + (size_t)row * K * PST_EDGE_FEATURES;
   for (int t = lane; t < K * 15; t += 32) {
     const int e = t / 15, f = t - e * 15;
@@ -390,9 +448,13 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
 
 }  // namespace
 
+// the compact feature layout exists on the warp-kernel path only
+bool pst_featurize_compact_ok(const pst_model* m) { return m->cfg.num_neighbor <= 60 && m->cfg.max_len <= 2048; }
+
 int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms,
                          const uint8_t* mask, int apr, const int32_t* offsets, int B, int R,
-                         int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status, int32_t* redo) {
+                         int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status, int32_t* redo,
+                         int compact) {
   if (R <= 0) return 0;
   prep_kernel<<<(R + 127) / 128, 128, 0, st>>>(atoms, mask, apr, R, prep, reinterpret_cast<double4*>(cen4));
   int n_pad = 64;
@@ -403,15 +465,24 @@ int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms
     cudaFuncSetAttribute(knn_feature_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (m->cfg.num_neighbor <= 60 && m->cfg.max_len <= 2048) {
     cudaMemsetAsync(redo, 0, sizeof(int32_t), st);  // the counter
-    knn_warp_kernel<<<(R + kKnnWarps - 1) / kKnnWarps, kKnnWarps * 32, 0, st>>>(
-        prep, reinterpret_cast<const double4*>(cen4), offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len, senders,
-        edge_feat, status, redo);
-    // exact recompute of the (normally zero) rows flagged above
-    cudaFuncSetAttribute(knn_feature_redo_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    knn_feature_redo_kernel<kThreads><<<min(R, 2 * m->num_sms), kThreads, smem, st>>>(
-        prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len, senders, edge_feat, status, redo);
+    const dim3 wg((R + kKnnWarps - 1) / kKnnWarps), rg(min(R, 2 * m->num_sms));
+    if (compact) {
+      knn_warp_kernel<true><<<wg, kKnnWarps * 32, 0, st>>>(prep, reinterpret_cast<const double4*>(cen4), offsets, B, R,
+                                                            m->cfg.num_neighbor, m->cfg.max_len, senders, edge_feat, status, redo);
+      // exact recompute of the (normally zero) rows flagged above
+      cudaFuncSetAttribute(knn_feature_redo_kernel<kThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      knn_feature_redo_kernel<kThreads, true><<<rg, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,
+                                                                           senders, edge_feat, status, redo);
+    } else {
+      knn_warp_kernel<false><<<wg, kKnnWarps * 32, 0, st>>>(prep, reinterpret_cast<const double4*>(cen4), offsets, B, R,
+                                                             m->cfg.num_neighbor, m->cfg.max_len, senders, edge_feat, status, redo);
+      cudaFuncSetAttribute(knn_feature_redo_kernel<kThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      knn_feature_redo_kernel<kThreads, false><<<rg, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,
+                                                                            senders, edge_feat, status, redo);
+    }
     return 3;
   }
+  if (compact) return PST_ERR_UNSUPPORTED_CONFIG;  // callers ask pst_featurize_compact_ok() first
   knn_feature_kernel<kThreads><<<R, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,
                                                          senders, edge_feat, status);
   return 2;

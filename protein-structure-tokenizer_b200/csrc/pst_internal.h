@@ -136,12 +136,13 @@ PstWorkspace pst_carve_workspace(const pst_model* m, void* base, int R, int T_up
 int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms,
                          const uint8_t* mask, int apr, const int32_t* offsets, int B, int R,
                          int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status,
-                         int32_t* redo);
+                         int32_t* redo, int compact = 0);
+bool pst_featurize_compact_ok(const pst_model* m);
 
 int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edge_feat,
                            const int32_t* senders, const int32_t* offsets,
                            const int32_t* token_offsets, int B, int R, int T, float* z_out,
-                           PstWorkspace& ws);
+                           PstWorkspace& ws, int compact_features = 0);
 
 int pst_launch_quantize(const pst_model* m, cudaStream_t st, const float* z, int n,
                         int32_t* tokens, float* bounded);
@@ -160,7 +161,7 @@ size_t pst_tc_partial_floats(int R, int K);
 int pst_launch_abs_senders(const pst_model* m, cudaStream_t st, const int32_t* senders, const int32_t* row_base, int R,
                            int32_t* senders_abs);
 int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* feat, const int32_t* senders,
-                             const int32_t* row_base, int R, uint16_t* e);
+                             const int32_t* row_base, int R, uint16_t* e, int compact = 0);
 
 // node-level linears on tensor cores (linear_tc.cu)
 int pst_prepare_linear_tc(pst_model* m);
