@@ -221,6 +221,8 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   m->device = device;
   m->launch_count = 0;
   m->tc_dev = nullptr;
+  m->blob_host = nullptr;
+  m->blob_dev = nullptr;
   m->graphs = new (std::nothrow) PstGraphCache();
   if (m->graphs) { const char* g = getenv("PST_CUDA_GRAPH"); m->graphs->enabled = !(g && g[0] == '0'); }
   m->linear_tc = nullptr;
@@ -239,6 +241,9 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   if (cudaMemcpy(m->blob_dev, blob_host, blob_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaFree(m->blob_dev); delete m; return PST_ERR_CUDA;
   }
+  m->blob_host = static_cast<float*>(malloc(blob_floats * sizeof(float)));
+  if (!m->blob_host) { cudaFree(m->blob_dev); delete m; return PST_ERR_BAD_ARGUMENT; }
+  memcpy(m->blob_host, blob_host, blob_floats * sizeof(float));
   pst_fill_weight_pointers(m->cfg, m->blob_dev, &m->w);
   // FSQ constants in fp32, operation order of model/quantize.py:177-180
   int basis = 1;
@@ -273,6 +278,7 @@ void pst_model_destroy(pst_model* m) {
   cudaSetDevice(m->device);
   if (m->graphs) { m->graphs->clear(); delete m->graphs; }
   if (m->blob_dev) cudaFree(m->blob_dev);
+  free(m->blob_host);
   if (m->tc_dev) cudaFree(m->tc_dev);
   pst_destroy_node_chain(m);
   pst_destroy_linear_tc(m);

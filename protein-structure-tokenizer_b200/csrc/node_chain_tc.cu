@@ -31,6 +31,8 @@
 
 #include <vector>
 
+#include <cstring>
+
 #include "pst_internal.h"
 
 namespace {
@@ -251,8 +253,12 @@ __device__ __forceinline__ float ldg4(const float* __restrict__ base, int j) {
 
 // LayerNorm over the full 128-wide row (biased variance of the centred row, eps 1e-5: gnn_layers.py:108-120,162-164;
 // hk.LayerNorm is the same formula); x = this thread's 64 columns
-__device__ __forceinline__ void layer_norm_row(const Epi& e, float (&x)[2][32], const float* __restrict__ scale,
-                                               const float* __restrict__ offset) {
+// Per-channel parameter vectors (biases, LayerNorm scale / offset) are passed BY VALUE inside the kernel parameter
+// struct and read from the constant bank (`cv`, offsets in floats): next to 226 KB of shared memory there is no L1 to
+// speak of, so the same vectors read through the global path cost an L2 round trip in every epilogue
+// (measured upper bound: 0.19 ms of the 1.9 ms the two node-level kernels take per step).
+template <int N>
+__device__ __forceinline__ void layer_norm_row(const Epi& e, float (&x)[2][32], const float (&cv)[N], int scale, int offset) {
   float s = 0.f;
 #pragma unroll
   for (int q = 0; q < 2; ++q)
@@ -272,12 +278,11 @@ __device__ __forceinline__ void layer_norm_row(const Epi& e, float (&x)[2][32], 
   e.red[256 + e.half * 128 + e.row] = v;
   epi_sync();
   const float inv = rsqrtf((e.red[256 + e.row] + e.red[256 + 128 + e.row]) * (1.0f / D) + 1e-5f);
-  const float* sc = scale + e.half * 64;
-  const float* of = offset + e.half * 64;
+  const int sc = scale + e.half * 64, of = offset + e.half * 64;
 #pragma unroll
   for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[q][j] = (ldg4(sc + q * 32, j) * inv) * (x[q][j] - mean) + ldg4(of + q * 32, j);
+    for (int j = 0; j < 32; ++j) x[q][j] = (cv[sc + q * 32 + j] * inv) * (x[q][j] - mean) + cv[of + q * 32 + j];
 }
 
 __device__ __forceinline__ void tmem_ld_half(const Epi& e, uint32_t region, float (&x)[2][32]) {
@@ -305,12 +310,23 @@ __device__ __forceinline__ void load_row_half(const Epi& e, const float* row_ptr
       }
     }
 }
-__device__ __forceinline__ void add_bias_half(const Epi& e, float (&x)[2][32], const float* __restrict__ bias) {
-  const float* b = bias + e.half * 64;
+template <int N>
+__device__ __forceinline__ void add_bias_half(const Epi& e, float (&x)[2][32], const float (&cv)[N], int bias) {
+  const int b = bias + e.half * 64;
 #pragma unroll
   for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[q][j] += ldg4(b + q * 32, j);
+    for (int j = 0; j < 32; ++j) x[q][j] += cv[b + q * 32 + j];
+}
+// x += r + bias
+template <int N>
+__device__ __forceinline__ void add_residual_bias_half(const Epi& e, float (&x)[2][32], const float (&r)[2][32],
+                                                       const float (&cv)[N], int bias) {
+  const int b = bias + e.half * 64;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + cv[b + q * 32 + j];
 }
 
 struct Setup {
@@ -387,25 +403,15 @@ __device__ __forceinline__ void publish() {
 // activation of chunk c is computed in registers while the tensor core still reads U for chunk c - 1; only the
 // store into U waits for it.  Issue order F1(0) F1(1) F2(0) F1(2) F2(1) ... == wait order.  Result in acc_out
 // (complete on return).  NOTE the schedule of weight half-units must list the units in this issue order.
-template <int ACT>  // 1 gelu(tanh), 2 relu
+template <int ACT, int N>  // 1 gelu(tanh), 2 relu
 __device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_addr, uint8_t* U, uint32_t U_addr,
                                             uint32_t accH0, uint32_t accH1, uint32_t acc_out, int chunks,
-                                            const float* __restrict__ b1) {
+                                            const float (&cv)[N], int b1) {
   G.issue(X_addr, accH0, 0u);
   if (chunks > 1) G.issue(X_addr, accH1, 0u);
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
-    float bv[2][32];
-    {
-      const float* b = b1 + c * 128 + e.half * 64;
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(b + q * 32) + j);
-          bv[q][j * 4] = t.x; bv[q][j * 4 + 1] = t.y; bv[q][j * 4 + 2] = t.z; bv[q][j * 4 + 3] = t.w;
-        }
-    }
+    const int b = b1 + c * 128 + e.half * 64;
     G.wait_next();  // X . W1[:, c]
     float v[2][32];
     tmem_ld_half(e, (c & 1) ? accH1 : accH0, v);
@@ -413,7 +419,7 @@ __device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_
     for (int q = 0; q < 2; ++q)
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float t = v[q][j] + bv[q][j];
+        const float t = v[q][j] + cv[b + q * 32 + j];
         v[q][j] = ACT == 1 ? gelu_tanh(t) : fmaxf(t, 0.f);
       }
     if (c > 0) G.wait_next();  // u_{c-1} . W2[c-1, :] has read U
@@ -430,16 +436,17 @@ struct NodeUpdateParams {
   const float* partial;  // [num_edge_tiles][4][128]: per-receiver partial row sums written by the message-mode edge kernel
   int K;
   float* h;           // [R,128] in / out
-  const float *b3, *ln0_s, *ln0_o, *ffn_b1, *ffn_b2, *ln1_s, *ln1_o;
   const uint8_t* const* sched;
   int n_sched, n_out;
-  const float* out_bias[4];
   __half* out[4];
+  // parameter vectors by value (constant bank), offsets in floats
+  enum { kB3 = 0, kLn0S = 128, kLn0O = 256, kFfnB1 = 384, kFfnB2 = 896, kLn1S = 1024, kLn1O = 1152, kOutBias = 1280, kCv = 1792 };
+  float cv[kCv];      // out_bias[o] at kOutBias + 128 o (zeros where the table has no bias)
   int R, num_tiles;
   uint32_t idesc;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdateParams p) {
+__global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_constant__ NodeUpdateParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
@@ -489,30 +496,22 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
       float hh[2][32];
       tmem_ld_half(e, t_acc0, x);
       load_row_half(e, p.h + (size_t)row * D, valid, hh);
-      const float* b = p.b3 + e.half * 64;
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[q][j] += hh[q][j] + ldg4(b + q * 32, j);
+      add_residual_bias_half(e, x, hh, p.cv, NodeUpdateParams::kB3);
     }
-    layer_norm_row(e, x, p.ln0_s, p.ln0_o);
+    layer_norm_row(e, x, p.cv, NodeUpdateParams::kLn0S, NodeUpdateParams::kLn0O);
     tmem_st_half(e, t_h1, x);
     split_store_half(e, X, x);
     publish();
     // ---- 3. FFN 128 -> 512 -> 128 (gnn_layers.py:385-394), hidden chunked 4 x 128 ---------------------------------
-    chunked_mlp<1>(G, e, X_addr, U, U_addr, t_acc1, t_acc0, t_acc2, 4, p.ffn_b1);
+    chunked_mlp<1>(G, e, X_addr, U, U_addr, t_acc1, t_acc0, t_acc2, 4, p.cv, NodeUpdateParams::kFfnB1);
     // ---- 4. h2 = LN1(h1 + ffn + b2) -> global h, X images ------------------------------------------------------
     {
       float h1[2][32];
       tmem_ld_half(e, t_acc2, x);
       tmem_ld_half(e, t_h1, h1);
-      const float* b = p.ffn_b2 + e.half * 64;
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[q][j] += h1[q][j] + ldg4(b + q * 32, j);
+      add_residual_bias_half(e, x, h1, p.cv, NodeUpdateParams::kFfnB2);
     }
-    layer_norm_row(e, x, p.ln1_s, p.ln1_o);
+    layer_norm_row(e, x, p.cv, NodeUpdateParams::kLn1S, NodeUpdateParams::kLn1O);
     if (valid) {
       float* hdst = p.h + (size_t)row * D + e.half * 64;
 #pragma unroll
@@ -530,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
         if (o + 1 < p.n_out) G.issue(X_addr, ((o + 1) & 1) ? t_acc1 : t_acc0, 0u);
         G.wait_next();
         tmem_ld_half(e, (o & 1) ? t_acc1 : t_acc0, x);
-        if (p.out_bias[o]) add_bias_half(e, x, p.out_bias[o]);
+        add_bias_half(e, x, p.cv, NodeUpdateParams::kOutBias + o * 128);
         if (valid) {
           __half* dst = p.out[o] + (size_t)row * D + e.half * 64;
 #pragma unroll
@@ -558,17 +557,16 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(NodeUpdatePara
 }
 
 // ------------------------------------------------------------------------------------------------------------
-struct ResamplerBlockP {
-  const float *qn_s, *qn_o, *dn_s, *dn_o, *bg, *bo;
-  const float *rt_ln_s, *rt_ln_o, *rt_b1, *rt_b2;
-  const float *ot_ln_s, *ot_ln_o, *ot_b1, *ot_b2;
+// offsets (floats) of one block's vectors inside ResamplerParams::cv; block b starts at b * kBlk
+struct RB {
+  enum { kQnS = 0, kQnO = 128, kDnS = 256, kDnO = 384, kBg = 512, kBo = 640, kRtLnS = 768, kRtLnO = 896, kRtB1 = 1024,
+         kRtB2 = 1280, kOtLnS = 1408, kOtLnO = 1536, kOtB1 = 1664, kOtB2 = 1920, kBlk = 2048 };
 };
 struct ResamplerParams {
   const float* h;            // [R,128] node features after the GNN ("original" track input)
   const float* token_table;  // [max_out_len,128] PE of the token index (modules.py:486-500)
   const int32_t* row_base;   // [R] first row of the structure a row belongs to (df = 1: token index == row)
   float* z;                  // [R,8] pre-quantisation latents, unused columns 0
-  ResamplerBlockP blk[PST_MAX_BLOCKS];
   int num_blocks;
   const float* down_w;       // [128,8]
   const float* down_b;       // [8]
@@ -577,9 +575,12 @@ struct ResamplerParams {
   int n_sched;
   int R, num_tiles;
   uint32_t idesc;
+  enum { kMaxBlocks = 3 };  // every released config has 3 (config/structure_tokenizer/model/shared.yaml); 4 would not fit the 32 KB parameter space
+  float cv[kMaxBlocks * RB::kBlk];  // parameter vectors by value (constant bank)
 };
+static_assert(sizeof(ResamplerParams) <= 32764, "kernel parameter space");
 
-__global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerParams p) {
+__global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid_constant__ ResamplerParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
@@ -611,13 +612,13 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
     }
 #pragma unroll 1
     for (int b = 0; b < p.num_blocks; ++b) {
-      const ResamplerBlockP& w = p.blk[b];
+      const int w = b * RB::kBlk;
       // ---- cross attention, df = 1 (modules.py:303-380,407-424): res += (v * sigmoid(gate)) . Wo + bo ------------
       tmem_ld_half(e, t_res, x);
-      layer_norm_row(e, x, w.qn_s, w.qn_o);
+      layer_norm_row(e, x, p.cv, w + RB::kQnS, w + RB::kQnO);
       split_store_half(e, X, x);
       tmem_ld_half(e, t_orig, x);
-      layer_norm_row(e, x, w.dn_s, w.dn_o);
+      layer_norm_row(e, x, p.cv, w + RB::kDnS, w + RB::kDnO);
       split_store_half(e, U, x);
       publish();
       G.issue(X_addr, t_accA, 0u);  // gate = LNq(res) . Wg
@@ -628,11 +629,11 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
         float g[2][32];
         tmem_ld_half(e, t_accA, g);
         tmem_ld_half(e, t_accB, x);
-        const float* bg = w.bg + e.half * 64;
+        const int bg = w + RB::kBg + e.half * 64;
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[q][j] *= sigmoid_f(g[q][j] + ldg4(bg + q * 32, j));
+          for (int j = 0; j < 32; ++j) x[q][j] *= sigmoid_f(g[q][j] + p.cv[bg + q * 32 + j]);
       }
       split_store_half(e, X, x);
       publish();
@@ -642,44 +643,32 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(ResamplerPar
         float r[2][32];
         tmem_ld_half(e, t_accA, x);
         tmem_ld_half(e, t_res, r);
-        const float* bo = w.bo + e.half * 64;
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + ldg4(bo + q * 32, j);
+        add_residual_bias_half(e, x, r, p.cv, w + RB::kBo);
       }
       tmem_st_half(e, t_res, x);
       // ---- resampled transition (modules.py:227-252): res += W2 . relu(W1 . LN(res) + b1) + b2 -----------------------
-      layer_norm_row(e, x, w.rt_ln_s, w.rt_ln_o);
+      layer_norm_row(e, x, p.cv, w + RB::kRtLnS, w + RB::kRtLnO);
       split_store_half(e, X, x);
       publish();
-      chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accA, 2, w.rt_b1);  // 2 chunks: the output reuses accA
+      chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accA, 2, p.cv, w + RB::kRtB1);  // 2 chunks: the output reuses accA
       {
         float r[2][32];
         tmem_ld_half(e, t_accA, x);
         tmem_ld_half(e, t_res, r);
-        const float* b2 = w.rt_b2 + e.half * 64;
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + ldg4(b2 + q * 32, j);
+        add_residual_bias_half(e, x, r, p.cv, w + RB::kRtB2);
       }
       tmem_st_half(e, t_res, x);
       // ---- original transition; its result is never read after the last block (modules.py:624-629) ---------------
       if (b < p.num_blocks - 1) {
         tmem_ld_half(e, t_orig, x);
-        layer_norm_row(e, x, w.ot_ln_s, w.ot_ln_o);
+        layer_norm_row(e, x, p.cv, w + RB::kOtLnS, w + RB::kOtLnO);
         split_store_half(e, X, x);
         publish();
-        chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accA, 2, w.ot_b1);
+        chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accA, 2, p.cv, w + RB::kOtB1);
         float r[2][32];
         tmem_ld_half(e, t_accA, x);
         tmem_ld_half(e, t_orig, r);
-        const float* b2 = w.ot_b2 + e.half * 64;
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[q][j] += r[q][j] + ldg4(b2 + q * 32, j);
+        add_residual_bias_half(e, x, r, p.cv, w + RB::kOtB2);
         tmem_st_half(e, t_orig, x);
       }
     }
@@ -846,16 +835,21 @@ int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const
   const PstLayerW& w = m->w.layer[layer];
   NodeUpdateParams p{};
   p.partial = partial; p.K = m->cfg.num_neighbor; p.h = h;
-  p.b3 = w.msg_b3; p.ln0_s = w.ln0_s; p.ln0_o = w.ln0_o; p.ffn_b1 = w.ffn_b1; p.ffn_b2 = w.ffn_b2; p.ln1_s = w.ln1_s; p.ln1_o = w.ln1_o;
+  auto put = [&](int off, const float* dev, int n) {  // device pointer into the weight blob -> its host copy
+    if (dev) memcpy(p.cv + off, m->blob_host + (dev - m->blob_dev), (size_t)n * sizeof(float));
+  };
+  put(NodeUpdateParams::kB3, w.msg_b3, 128); put(NodeUpdateParams::kLn0S, w.ln0_s, 128); put(NodeUpdateParams::kLn0O, w.ln0_o, 128);
+  put(NodeUpdateParams::kFfnB1, w.ffn_b1, 512); put(NodeUpdateParams::kFfnB2, w.ffn_b2, 128);
+  put(NodeUpdateParams::kLn1S, w.ln1_s, 128); put(NodeUpdateParams::kLn1O, w.ln1_o, 128);
   p.sched = C.sched_dev + C.layer_off[layer];
   p.n_sched = C.layer_n[layer];
   p.n_out = C.layer_nout[layer];
   if (p.n_out) {
     const PstLayerW& nx = m->w.layer[layer + 1];
-    p.out[0] = reinterpret_cast<__half*>(out_edge_s); p.out_bias[0] = nullptr;
-    p.out[1] = reinterpret_cast<__half*>(out_edge_r); p.out_bias[1] = w.edge_b1;
-    p.out[2] = reinterpret_cast<__half*>(out_msg_s);  p.out_bias[2] = nullptr;
-    p.out[3] = reinterpret_cast<__half*>(out_msg_r);  p.out_bias[3] = nx.msg_b1;
+    p.out[0] = reinterpret_cast<__half*>(out_edge_s);
+    p.out[1] = reinterpret_cast<__half*>(out_edge_r); put(NodeUpdateParams::kOutBias + 128, w.edge_b1, 128);
+    p.out[2] = reinterpret_cast<__half*>(out_msg_s);
+    p.out[3] = reinterpret_cast<__half*>(out_msg_r);  put(NodeUpdateParams::kOutBias + 384, nx.msg_b1, 128);
   }
   p.R = R;
   p.num_tiles = (R + 127) / 128;
@@ -866,14 +860,20 @@ int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const
 // z <- the whole resampler + head for downsampling_ratio == 1 (token t == residue t); h = node features after the GNN
 int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z) {
   if (!m->node_chain || R <= 0 || m->cfg.downsampling_ratio != 1) return 0;
+  if (m->cfg.num_blocks > ResamplerParams::kMaxBlocks) return PST_ERR_UNSUPPORTED_CONFIG;
   const PstNodeChain& C = *m->node_chain;
   ResamplerParams p{};
   p.h = h; p.token_table = m->w.token_table; p.row_base = row_base; p.z = z;
   p.num_blocks = m->cfg.num_blocks;
   for (int b = 0; b < p.num_blocks; ++b) {
     const PstBlockW& w = m->w.block[b];
-    p.blk[b] = ResamplerBlockP{w.qn_s, w.qn_o, w.dn_s, w.dn_o, w.bg, w.bo, w.rt_ln_s, w.rt_ln_o, w.rt_b1, w.rt_b2,
-                               w.ot_ln_s, w.ot_ln_o, w.ot_b1, w.ot_b2};
+    auto put = [&](int off, const float* dev, int n) {
+      memcpy(p.cv + b * RB::kBlk + off, m->blob_host + (dev - m->blob_dev), (size_t)n * sizeof(float));
+    };
+    put(RB::kQnS, w.qn_s, 128); put(RB::kQnO, w.qn_o, 128); put(RB::kDnS, w.dn_s, 128); put(RB::kDnO, w.dn_o, 128);
+    put(RB::kBg, w.bg, 128); put(RB::kBo, w.bo, 128);
+    put(RB::kRtLnS, w.rt_ln_s, 128); put(RB::kRtLnO, w.rt_ln_o, 128); put(RB::kRtB1, w.rt_b1, 256); put(RB::kRtB2, w.rt_b2, 128);
+    put(RB::kOtLnS, w.ot_ln_s, 128); put(RB::kOtLnO, w.ot_ln_o, 128); put(RB::kOtB1, w.ot_b1, 256); put(RB::kOtB2, w.ot_b2, 128);
   }
   p.down_w = m->w.down_w; p.down_b = m->w.down_b; p.C = m->cfg.num_levels;
   p.sched = C.sched_dev + C.resampler_off;

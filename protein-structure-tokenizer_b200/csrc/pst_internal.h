@@ -60,6 +60,7 @@ struct pst_model {
   int device;
   int num_sms;
   float* blob_dev;
+  float* blob_host;          // host copy of the blob: small parameter vectors are passed to kernels by value
   size_t blob_floats;
   PstWeights w;
   uint16_t* tc_dev;
