@@ -88,12 +88,24 @@ class _TokenizeFn:
         tokens: List[Optional[np.ndarray]] = [None] * len(batch)
         # structures are independent: contiguous shards, one per device (the reference's [Dev, B] reshape)
         per = (len(batch) + n_dev - 1) // n_dev
-        for d, dev in enumerate(self.devices):
-            part = batch[d * per : (d + 1) * per]
-            if not part:
-                continue
-            out = self._get(params, dev).tokenize([a for a, _ in part], [m for _, m in part])
-            tokens[d * per : d * per + len(part)] = out
+        shards = [(d, dev, batch[d * per : (d + 1) * per]) for d, dev in enumerate(self.devices)]
+        shards = [s for s in shards if s[2]]
+        for _, dev, _ in shards:  # tokenizers are created on the calling thread (one model per device)
+            self._get(params, dev)
+
+        def run(shard):
+            d, dev, part = shard
+            return d, self._tok[dev].tokenize([a for a, _ in part], [m for _, m in part])
+
+        if len(shards) > 1:
+            # one host thread per device, like pmap's per-device dispatch: the devices work concurrently (the GIL is
+            # released inside the CUDA calls and copies)
+            with ThreadPoolExecutor(max_workers=len(shards)) as pool:
+                results = list(pool.map(run, shards))
+        else:
+            results = [run(s) for s in shards]
+        for d, out in results:
+            tokens[d * per : d * per + len(out)] = out
         return {"tokens": tokens}
 
 

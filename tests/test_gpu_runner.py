@@ -66,3 +66,26 @@ def test_casp14_tokens_fp16_agree_with_oracle(built_lib, casp14):
         agree += int((t == ref).sum())
         total += len(ref)
     assert agree / total >= 0.995, agree / total
+
+
+def test_two_devices_concurrently_match_one_device(built_lib):
+    """The runner's callable shards a batch over the visible devices (pmap's [Dev, B] reshape,
+    scripts/inference_runner.py:299-306) and drives them from one host thread each."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.inference_runner import InferenceRunner
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(4096, 1, precision="fp16")
+    params = init_params(cfg, 0, "spread")
+    bbs = syn.make_backbones(5, [90, 64, 130, 77, 101])
+    batch = [(bb, None) for bb in bbs]
+    one = InferenceRunner.prepare_tokenize_fn(cfg, [0])(params, None, batch)["tokens"]
+    two = InferenceRunner.prepare_tokenize_fn(cfg, [0, 1])(params, None, batch)["tokens"]
+    assert len(one) == len(two) == len(bbs)
+    for a, b in zip(one, two):
+        assert np.array_equal(a, b)
