@@ -63,12 +63,15 @@ class StructureTokenizer:
         # pst_tokenize replays a CUDA graph for repeated argument sets, which needs a named stream: when the caller is
         # on the default stream the fused call runs on this side stream, ordered with the caller's stream on both sides
         self._side = torch.cuda.Stream(device=self.device)
+        self._copy = torch.cuda.Stream(device=self.device)  # H2D / D2H copies of the chunk pipeline (tokenize)
+        self._slots = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self.lib.pst_model_destroy(self._h)
             self._h = C.c_void_p()
         self._ws = None
+        self._slots = None
 
     def __del__(self):
         try:
@@ -202,30 +205,105 @@ class StructureTokenizer:
         """structures: one fp32 array [L, A, 3] per protein (A = 4: N,CA,C,O; A = 37: atom37),
         only valid residues; masks: optional u8/bool [L, A].  Returns one uint32 token
         array [floor(L/df)] per protein (the dtype the reference saves,
-        scripts/inference_runner.py:315-321)."""
+        scripts/inference_runner.py:315-321).
+
+        The structures are processed in chunks of at most `max_rows_per_call` residues through a two-slot pipeline:
+        while the GPU works on chunk i, the host packs chunk i + 1 into pinned staging buffers and its H2D copy runs on
+        a second stream; tokens and the device status word come back the same way."""
         t = self.torch
         lengths = [int(s.shape[0]) for s in structures]
         offs_all = np.zeros(len(lengths) + 1, np.int64)
         offs_all[1:] = np.cumsum(lengths)
         self.check_lengths(offs_all)
-        results: List[np.ndarray] = []
-        for a, b in self._chunks(lengths):
-            atoms = np.ascontiguousarray(np.concatenate([np.asarray(s, np.float32) for s in structures[a:b]], axis=0))
-            offsets = (offs_all[a : b + 1] - offs_all[a]).astype(np.int32)
-            tok_off = self.token_offsets(offsets)
-            mask_dev = None
-            if masks is not None and any(m is not None for m in masks[a:b]):
-                mk = np.concatenate([np.ones(s.shape[:2], np.uint8) if m is None else np.asarray(m, np.uint8)
-                                     for s, m in zip(structures[a:b], masks[a:b])], axis=0)
-                mask_dev = t.from_numpy(np.ascontiguousarray(mk)).to(self.device, non_blocking=True)
-            atoms_dev = t.from_numpy(atoms).to(self.device, non_blocking=True)
-            offsets_dev = t.from_numpy(offsets).to(self.device, non_blocking=True)
-            tok_off_dev = t.from_numpy(tok_off).to(self.device, non_blocking=True)
-            R, T = int(offsets[-1]), int(tok_off[-1])
-            tokens = self.tokenize_device(atoms_dev, mask_dev, offsets_dev, tok_off_dev, b - a, R, T).cpu().numpy()
-            st = self.read_status()
+        if not lengths:
+            return []
+        chunks = self._chunks(lengths)
+        A = int(structures[0].shape[1])
+        use_mask = masks is not None and any(m is not None for m in masks)
+        cap_rows = max(int(offs_all[b] - offs_all[a]) for a, b in chunks)
+        cap_b = max(b - a for a, b in chunks)
+        slots = self._pipeline_slots(min(2, len(chunks)), cap_rows, cap_b, A, use_mask)
+        self._workspace(cap_rows, cap_b)  # sized for the largest chunk up front: no reallocation inside the pipeline
+        main = t.cuda.current_stream(self.device)
+        results: List[Optional[np.ndarray]] = [None] * len(lengths)
+
+        def finish(sl):
+            a, b, tok_off = sl["job"]
+            sl["done"].synchronize()
+            st = int(sl["status_pin"][0])
             if st != 0:
                 raise _lib.PstError(st, "pst_tokenize (device status)")
+            tokens = sl["tokens_pin"].numpy()
             for i in range(b - a):
-                results.append(tokens[tok_off[i] : tok_off[i + 1]].astype(np.uint32))
-        return results
+                results[a + i] = tokens[tok_off[i] : tok_off[i + 1]].astype(np.uint32)
+            sl["job"] = None
+
+        for ci, (a, b) in enumerate(chunks):
+            sl = slots[ci % len(slots)]
+            if sl["job"] is not None:
+                finish(sl)
+            offsets = (offs_all[a : b + 1] - offs_all[a]).astype(np.int32)
+            tok_off = self.token_offsets(offsets)
+            R, T, B = int(offsets[-1]), int(tok_off[-1]), b - a
+            atoms_np = sl["atoms_pin"].numpy()
+            for i in range(a, b):
+                atoms_np[offsets[i - a] : offsets[i - a + 1]] = structures[i]
+            if use_mask:
+                mask_np = sl["mask_pin"].numpy()
+                for i in range(a, b):
+                    m = masks[i]
+                    mask_np[offsets[i - a] : offsets[i - a + 1]] = 1 if m is None else np.asarray(m, np.uint8)
+            sl["offs_pin"].numpy()[: B + 1] = offsets
+            sl["toff_pin"].numpy()[: B + 1] = tok_off
+            with t.cuda.stream(self._copy):
+                self._copy.wait_event(sl["computed"])  # the slot's previous call has consumed its device inputs
+                sl["atoms"][:R].copy_(sl["atoms_pin"][:R], non_blocking=True)
+                if use_mask:
+                    sl["mask"][:R].copy_(sl["mask_pin"][:R], non_blocking=True)
+                sl["offs"][: B + 1].copy_(sl["offs_pin"][: B + 1], non_blocking=True)
+                sl["toff"][: B + 1].copy_(sl["toff_pin"][: B + 1], non_blocking=True)
+                sl["in_ready"].record(self._copy)
+            main.wait_event(sl["in_ready"])
+            self.tokenize_device(sl["atoms"][:R], sl["mask"][:R] if use_mask else None, sl["offs"], sl["toff"], B, R, T,
+                                 out=sl["tokens"][:T])
+            sl["status_pin"].copy_(self._ws[:4].view(t.int32)[:1], non_blocking=True)  # status word: start of the workspace
+            sl["computed"].record(main)
+            with t.cuda.stream(self._copy):
+                self._copy.wait_event(sl["computed"])
+                sl["tokens_pin"][:T].copy_(sl["tokens"][:T], non_blocking=True)
+                sl["done"].record(self._copy)
+            sl["job"] = (a, b, tok_off)
+        order = sorted((sl for sl in slots if sl["job"] is not None), key=lambda sl: sl["job"][0])
+        for sl in order:
+            finish(sl)
+        return results  # type: ignore[return-value]
+
+    def _pipeline_slots(self, n: int, rows: int, nb: int, A: int, use_mask: bool):
+        """Pinned host + device staging buffers of the chunk pipeline (grow-only, kept between calls)."""
+        t = self.torch
+        key = (A, use_mask)
+        st = getattr(self, "_slots", None)
+        if st is None or st["key"] != key or st["rows"] < rows or st["nb"] < nb or len(st["slots"]) < n:
+            rows = max(rows, st["rows"] if st and st["key"] == key else 0)
+            nb = max(nb, st["nb"] if st and st["key"] == key else 0)
+            slots = []
+            for _ in range(max(n, len(st["slots"]) if st and st["key"] == key else 0)):
+                slots.append({
+                    "atoms_pin": t.empty((rows, A, 3), dtype=t.float32).pin_memory(),
+                    "mask_pin": t.empty((rows, A), dtype=t.uint8).pin_memory() if use_mask else None,
+                    "offs_pin": t.empty((nb + 1,), dtype=t.int32).pin_memory(),
+                    "toff_pin": t.empty((nb + 1,), dtype=t.int32).pin_memory(),
+                    "tokens_pin": t.empty((rows,), dtype=t.int32).pin_memory(),
+                    "status_pin": t.zeros((1,), dtype=t.int32).pin_memory(),
+                    "atoms": t.empty((rows, A, 3), dtype=t.float32, device=self.device),
+                    "mask": t.empty((rows, A), dtype=t.uint8, device=self.device) if use_mask else None,
+                    "offs": t.empty((nb + 1,), dtype=t.int32, device=self.device),
+                    "toff": t.empty((nb + 1,), dtype=t.int32, device=self.device),
+                    "tokens": t.empty((rows,), dtype=t.int32, device=self.device),
+                    "in_ready": t.cuda.Event(), "computed": t.cuda.Event(), "done": t.cuda.Event(), "job": None,
+                })
+            st = {"key": key, "rows": rows, "nb": nb, "slots": slots}
+            self._slots = st
+        for sl in st["slots"]:
+            sl["job"] = None
+        return st["slots"][:n]

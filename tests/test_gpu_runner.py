@@ -89,3 +89,33 @@ def test_two_devices_concurrently_match_one_device(built_lib):
     assert len(one) == len(two) == len(bbs)
     for a, b in zip(one, two):
         assert np.array_equal(a, b)
+
+
+def test_chunk_pipeline_matches_single_call(built_lib):
+    """tokenize() splits long inputs into chunks of max_rows_per_call residues and pipelines them over two staging
+    slots; the tokens must not depend on the chunking (structures are independent), with and without atom masks."""
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(4096, 1, precision="fp16")
+    params = init_params(cfg, 0, "spread")
+    lengths = [64, 200, 90, 150, 77, 300, 64, 128, 51, 260, 99]
+    bbs = syn.make_backbones(9, lengths)
+    whole = StructureTokenizer(cfg, params).tokenize(bbs)
+    small = StructureTokenizer(cfg, params, max_rows_per_call=400)
+    assert len(small._chunks(lengths)) >= 4
+    for rep in range(2):  # second pass reuses the staging slots
+        parts = small.tokenize(bbs)
+        assert len(parts) == len(whole)
+        for a, b, L in zip(whole, parts, lengths):
+            assert a.dtype == np.uint32 and a.shape == (L,) and np.array_equal(a, b)
+    # atom37 input with masks through the same pipeline
+    a37 = [syn.backbone_to_atom37(bb) for bb in bbs]
+    structs = [np.ascontiguousarray(p, np.float32) for p, _, _ in a37]
+    masks = [(g & e).astype(np.uint8) for _, g, e in a37]
+    parts = small.tokenize(structs, masks)
+    for a, b in zip(whole, parts):
+        assert np.array_equal(a, b)
+    assert small.tokenize([]) == []
