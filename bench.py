@@ -47,6 +47,8 @@ HW_FLOP_MSG = 2 * 2 * 128 * 128
 HW_FLOP_UPD = 2 * 3 * 128 * 128
 # DRAM bytes per launch of the dominant kernel, from the committed capture profiles/r01_kernels_ncu_full.md
 # (dram__bytes_read.sum + dram__bytes_write.sum at 256 x 512 residues): message mode 1.877 GB, update mode 3.415 GB
+# edge features handed from the k-NN kernel to the embedding: 50 edges x 27 fp32 (reference layout) or x 16 fp32 (compact)
+K_FEAT_BYTES_FULL, K_FEAT_BYTES_COMPACT = 50 * 27 * 4, 50 * 16 * 4
 NCU_DRAM_BYTES = {"msg": 1.877e9, "upd": 3.415e9, "residues": 131072}
 
 
@@ -374,6 +376,18 @@ def run_ours(args):
                     "resampler_head_df1": prof_ms[5] / max(1, prof_cnt[5]) if prof_cnt[5] else None,
                 },
                 "end_to_end_frac": value / world * FLOP_PER_RESIDUE.get(df, 44.91e6) / 1e12 / peak,
+                # the HBM-side kernels of the path against the measured copy bandwidth (SURVEY section 8d byte counts;
+                # the k-NN kernel is fp64-ALU / shuffle bound in practice)
+                "hbm_kernels": [
+                    {"kernel": "featurise + k-NN (frames, centroids, top-K, orientation features)", "bound": "hbm",
+                     "bytes_per_residue": 72 + 200 + (K_FEAT_BYTES_COMPACT if args.precision != "fp32" else K_FEAT_BYTES_FULL),
+                     "achieved": R * (72 + 200 + (K_FEAT_BYTES_COMPACT if args.precision != "fp32" else K_FEAT_BYTES_FULL))
+                                 / (prof_ms[0] / max(1, prof_cnt[0]) * 1e-3) / 1e9 if prof_cnt[0] else None,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s"},
+                    {"kernel": "FSQ quantiser (bound, round, pack)", "bound": "hbm", "bytes_per_token": 36,
+                     "achieved": T * 36 / (prof_ms[6] / max(1, prof_cnt[6]) * 1e-3) / 1e9 if prof_cnt[6] else None,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s"},
+                ],
             }
         line = {
             "metric": "residues/sec tokenized", "value": value, "unit": "residues/s", "n_gpus": world, "steps": args.steps,

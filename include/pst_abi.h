@@ -178,7 +178,7 @@ int pst_last_launch_count(const pst_model* model);
 
 /* Optional per-kernel-group timing for bench.py's roofline: when enabled, the hot calls record
  * CUDA event pairs on their stream around (kind 0) featurise + k-NN, (1) message-MLP launches,
- * (2) edge-update-MLP launches, (3) node updates, (4) input embeddings, (5) the fused df = 1 resampler + head.
+ * (2) edge-update-MLP launches, (3) node updates, (4) input embeddings, (5) the fused df = 1 resampler + head, (6) the FSQ quantiser.
  * pst_profile_collect synchronises those events, adds the elapsed milliseconds and launch-group counts per
  * kind into ms_out[8] / count_out[8], and resets. */
 int pst_profile_enable(const pst_model* model, int enable);

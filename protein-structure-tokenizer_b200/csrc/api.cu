@@ -413,7 +413,10 @@ static int tokenize_enqueue(const pst_model* m, cudaStream_t st, const float* at
                                  total_residues, total_tokens, ws.z, ws, compact);
   if (n < 0) return n;
   count += n;
-  count += pst_launch_quantize(m, st, ws.z, total_tokens, tokens_out, nullptr);
+  {
+    PstSpan span(m, st, 6);
+    count += pst_launch_quantize(m, st, ws.z, total_tokens, tokens_out, nullptr);
+  }
   m->launch_count = count;
   return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;
 }

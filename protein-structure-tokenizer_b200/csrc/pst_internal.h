@@ -15,7 +15,7 @@
 #define PST_FEAT_PAD 32   // 27 edge features padded to 32 GEMM rows
 #define PST_PREP_STRIDE 16 // doubles per residue in the prep record
 #define PST_PROF_MAX_SPANS 512
-#define PST_PROF_KINDS 8   // 0 featurise+knn, 1 message MLP, 2 edge-update MLP, 3 node update, 4 input embeddings, 5 resampler + head (+ FSQ)
+#define PST_PROF_KINDS 8   // 0 featurise+knn, 1 message MLP, 2 edge-update MLP, 3 node update, 4 input embeddings, 5 resampler + head, 6 FSQ quantiser
 
 // ---- prepared weight blob (fp32), see pst/weights.py for the packer ----------
 struct PstLayerW {

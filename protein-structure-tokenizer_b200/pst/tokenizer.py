@@ -180,7 +180,7 @@ class StructureTokenizer:
 
     def profile_collect(self):
         """-> (ms[8], groups[8]) accumulated since the last collect; kinds: 0 featurise+k-NN, 1 message MLP,
-        2 edge-update MLP, 3 node update, 4 input embeddings, 5 fused df=1 resampler + head."""
+        2 edge-update MLP, 3 node update, 4 input embeddings, 5 fused df=1 resampler + head, 6 FSQ quantiser."""
         ms = (C.c_float * 8)()
         cnt = (C.c_int * 8)()
         _lib.check(self.lib.pst_profile_collect(self._h, ms, cnt), "pst_profile_collect")
