@@ -201,3 +201,31 @@ def test_graph_replay_matches_eager_and_follows_new_data(built_lib):
             s.synchronize()
             assert torch.equal(out, eager[1]), rep
     tok.close()
+
+
+def test_fused_call_agrees_with_the_two_call_path(built_lib):
+    """pst_tokenize hands the features to the embedding kernel in a compact layout and evaluates the 15 RBFs there in
+    fp32; pst_featurize_knn + pst_encode_graph + pst_quantize use the reference's 27 fp32 features (fp64 math).  The
+    difference is far below the fp16 rounding of the edge embedding: the token ids must agree (>= 99.9 %)."""
+    import torch
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(64000, 1, precision="fp16")
+    tok = StructureTokenizer(cfg, init_params(cfg, 1, "rich"))
+    lengths = [300, 64, 512, 187, 96, 450]
+    atoms, offs = syn.pack_backbones(syn.make_backbones(21, lengths))
+    toff = tok.token_offsets(offs)
+    B, R, T = len(lengths), int(offs[-1]), int(toff[-1])
+    a, o, t = torch.from_numpy(atoms).cuda(), torch.from_numpy(offs).cuda(), torch.from_numpy(toff).cuda()
+    fused = tok.tokenize_device(a, None, o, t, B, R, T).clone()
+    senders, feats = tok.featurize_device(a, None, o, B, R)
+    z = tok.encode_graph_device(feats, senders, o, t, B, R, T)
+    two_call = tok.quantize_device(z)
+    torch.cuda.synchronize()
+    assert tok.read_status() == 0
+    agree = float((fused == two_call).float().mean())
+    assert agree >= 0.999, agree
+    tok.close()
