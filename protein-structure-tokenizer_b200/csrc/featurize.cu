@@ -350,27 +350,60 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
   // the current 64-th smallest cannot change the result and is skipped after the distance evaluation.
   const int c_home = (row - base) >> 6;
   unsigned long long bound = 0xFFFFFFFFFFFFFFFFull;
+  // Only keys below the current bound can enter the result.  They are few per chunk once the home chunk has set the
+  // bound (about 100 per row over all other chunks at L = 512), so they are COMPACTED into a 64-entry buffer (ballot +
+  // popc, order irrelevant: the keys are unique) and one sort-and-merge round is spent per full buffer instead of
+  // per chunk (3.4 instead of 5.1 rounds per row at L = 512, 3.9 instead of 6.2 at L = 2 048).
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(s_d2[warp]);  // free until the feature phase
+  int cnt = 0;
+  auto merge_sorted = [&](unsigned long long a0, unsigned long long a1) {
+    // a ascending; reversed: element e <- element 63 - e (lane 31 - lane, registers swapped); min against b gives a
+    // bitonic sequence holding the 64 smallest of the union
+    const unsigned long long r0 = __shfl_xor_sync(0xffffffffu, a1, 31), r1 = __shfl_xor_sync(0xffffffffu, a0, 31);
+    b0 = r0 < b0 ? r0 : b0;
+    b1 = r1 < b1 ? r1 : b1;
+    bitonic_stages(b0, b1, lane, 64);  // bitonic -> ascending
+    bound = __shfl_sync(0xffffffffu, b1, 31);  // largest of the current 64 smallest
+  };
+  auto flush = [&]() {
+    __syncwarp();
+    unsigned long long x0 = 2 * lane < cnt ? buf[2 * lane] : 0xFFFFFFFFFFFFFFFFull;
+    unsigned long long x1 = 2 * lane + 1 < cnt ? buf[2 * lane + 1] : 0xFFFFFFFFFFFFFFFFull;
+    __syncwarp();
+    bitonic_sort64(x0, x1, lane);
+    merge_sorted(x0, x1);
+    cnt = 0;
+  };
+  const unsigned lt = (1u << lane) - 1u;
   for (int step = 0; step < 2 * n_chunks; ++step) {
     const int delta = (step + 1) >> 1;
     const int c = (step & 1) ? c_home + delta : c_home - delta;
     if (step > 0 && (c < 0 || c >= n_chunks)) continue;
     const int j0 = c * 64 + 2 * lane;
-    unsigned long long a0 = packed_key(ci, cen4, base, j0, L);
-    unsigned long long a1 = packed_key(ci, cen4, base, j0 + 1, L);
-    if (step > 0 && !__any_sync(0xffffffffu, a0 < bound || a1 < bound)) continue;
-    bitonic_sort64(a0, a1, lane);
-    if (step == 0) {
+    const unsigned long long a0 = packed_key(ci, cen4, base, j0, L);
+    const unsigned long long a1 = packed_key(ci, cen4, base, j0 + 1, L);
+    if (step == 0) {  // the home chunk sets the first bound
       b0 = a0;
       b1 = a1;
-    } else {
-      // reversed chunk: element e <- element 63 - e  (lane 31 - lane, registers swapped)
-      const unsigned long long r0 = __shfl_xor_sync(0xffffffffu, a1, 31), r1 = __shfl_xor_sync(0xffffffffu, a0, 31);
-      b0 = r0 < b0 ? r0 : b0;
-      b1 = r1 < b1 ? r1 : b1;
-      bitonic_stages(b0, b1, lane, 64);  // bitonic -> ascending
+      bitonic_sort64(b0, b1, lane);
+      bound = __shfl_sync(0xffffffffu, b1, 31);
+      continue;
     }
-    bound = __shfl_sync(0xffffffffu, b1, 31);  // largest of the current 64 smallest
+    unsigned m0 = __ballot_sync(0xffffffffu, a0 < bound), m1 = __ballot_sync(0xffffffffu, a1 < bound);
+    int n = __popc(m0) + __popc(m1);
+    if (n == 0) continue;
+    if (cnt + n > 64) {
+      flush();  // tightens the bound: filter this chunk again
+      m0 = __ballot_sync(0xffffffffu, a0 < bound);
+      m1 = __ballot_sync(0xffffffffu, a1 < bound);
+      n = __popc(m0) + __popc(m1);
+      if (n == 0) continue;
+    }
+    if (a0 < bound) buf[cnt + __popc(m0 & lt)] = a0;
+    if (a1 < bound) buf[cnt + __popc(m0) + __popc(m1 & lt)] = a1;
+    cnt += n;
   }
+  if (cnt > 0) flush();
   // exactness check on the sorted head (ranks 0 .. K+2): equal truncated distances -> exact recompute
   {
     const unsigned long long nxt = __shfl_down_sync(0xffffffffu, b0, 1);  // element 2*lane + 2
