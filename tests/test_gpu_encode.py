@@ -203,6 +203,34 @@ def test_graph_replay_matches_eager_and_follows_new_data(built_lib):
     tok.close()
 
 
+@pytest.mark.parametrize("precision,codebook,df,min_agree", [("bf16", 4096, 1, 0.97), ("fp16", 64000, 4, 0.995), ("fp16", 432, 1, 0.995)])
+def test_fused_call_other_modes_agree_with_two_call_path(built_lib, precision, codebook, df, min_agree):
+    """The compact feature hand-off of pst_tokenize in the other tensor-core configurations (bf16 operands, df = 4 with
+    the per-op resampler, the 5-level codebook) against the two-call path of the same precision mode."""
+    import torch
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(codebook, df, precision=precision)
+    tok = StructureTokenizer(cfg, init_params(cfg, 1, "rich"))
+    lengths = [200, 64, 333, 128]
+    atoms, offs = syn.pack_backbones(syn.make_backbones(33, lengths))
+    toff = tok.token_offsets(offs)
+    B, R, T = len(lengths), int(offs[-1]), int(toff[-1])
+    a, o, t = torch.from_numpy(atoms).cuda(), torch.from_numpy(offs).cuda(), torch.from_numpy(toff).cuda()
+    fused = tok.tokenize_device(a, None, o, t, B, R, T).clone()
+    senders, feats = tok.featurize_device(a, None, o, B, R)
+    two_call = tok.quantize_device(tok.encode_graph_device(feats, senders, o, t, B, R, T))
+    torch.cuda.synchronize()
+    assert tok.read_status() == 0
+    assert int(fused.min()) >= 0 and int(fused.max()) < cfg.num_codes
+    agree = float((fused == two_call).float().mean())
+    assert agree >= min_agree, agree
+    tok.close()
+
+
 def test_fused_call_agrees_with_the_two_call_path(built_lib):
     """pst_tokenize hands the features to the embedding kernel in a compact layout and evaluates the 15 RBFs there in
     fp32; pst_featurize_knn + pst_encode_graph + pst_quantize use the reference's 27 fp32 features (fp64 math).  The
