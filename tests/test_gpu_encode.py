@@ -257,3 +257,36 @@ def test_fused_call_agrees_with_the_two_call_path(built_lib):
     agree = float((fused == two_call).float().mean())
     assert agree >= 0.999, agree
     tok.close()
+
+
+def test_graph_cache_eviction_keeps_results(built_lib):
+    """More argument sets than the graph cache holds (8, LRU): entries are evicted and re-captured; every call must
+    still give the eager tokens of its own inputs."""
+    import torch
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(4096, 1, precision="fp16")
+    tok = StructureTokenizer(cfg, init_params(cfg, 1, "rich"))
+    cases = []
+    for i in range(11):
+        lengths = [64 + 8 * i, 90, 70 + i]
+        atoms, offs = syn.pack_backbones(syn.make_backbones(100 + i, lengths))
+        toff = tok.token_offsets(offs)
+        a, o, t = torch.from_numpy(atoms).cuda(), torch.from_numpy(offs).cuda(), torch.from_numpy(toff).cuda()
+        out = torch.empty((int(toff[-1]),), dtype=torch.int32, device="cuda")
+        cases.append((a, o, t, len(lengths), int(offs[-1]), int(toff[-1]), out))
+    tok._workspace(max(c[4] for c in cases), 3)  # one workspace for all: the keys differ by the other arguments
+    tok.graph_cache_enable(False)
+    want = [tok.tokenize_device(a, None, o, t, B, R, T).clone() for a, o, t, B, R, T, _ in cases]
+    tok.graph_cache_enable(True)
+    for rep in range(3):
+        for (a, o, t, B, R, T, out), w in zip(cases, want):
+            out.zero_()
+            tok.tokenize_device(a, None, o, t, B, R, T, out=out)
+            torch.cuda.synchronize()
+            assert torch.equal(out, w), rep
+    assert tok.read_status() == 0
+    tok.close()
