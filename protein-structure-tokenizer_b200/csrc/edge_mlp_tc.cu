@@ -209,20 +209,6 @@ struct Unpack<__nv_bfloat16> {
   static __device__ __forceinline__ float2 two(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
 };
 
-// writes 32 consecutive K-elements [k0, k0+32) of `row` into the group's A image
-template <typename T16>
-__device__ __forceinline__ void store_a_chunk(uint8_t* sA, int row, int k0, const float (&v)[32]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 pk;
-    pk.x = Pack<T16>::two(v[c * 8 + 0], v[c * 8 + 1]);
-    pk.y = Pack<T16>::two(v[c * 8 + 2], v[c * 8 + 3]);
-    pk.z = Pack<T16>::two(v[c * 8 + 4], v[c * 8 + 5]);
-    pk.w = Pack<T16>::two(v[c * 8 + 6], v[c * 8 + 7]);
-    *reinterpret_cast<uint4*>(sA + swz_offset(row, k0 + c * 8)) = pk;
-  }
-}
-
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, uint32_t sA_addr, uint32_t sW_addr, uint32_t idesc,
                                            uint32_t mbar_addr, uint32_t accumulate_first) {
   tc_fence_after();
@@ -434,7 +420,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     //         accumulator row <- (h.W1a)[sender] + (h.W1b + b1)[receiver]  straight from global memory:
     // each thread owns one edge row (the TMEM 32x32b layout), reads its sender's 256-byte row of the fp16 table
     // with eight 32-byte loads (whole sectors: the per-thread access is as efficient as a row-coalesced one) and
-    // the receiver's row (shared by K consecutive edges: L1 broadcast), adds and writes its accumulator row.
+    // the receiver's row (shared by K consecutive edges: the lanes of a warp read one or two addresses, a broadcast load
+    // served by L2: next to 226 KB of shared memory there is no L1 to speak of), adds and writes its accumulator row.
     // No shared-memory staging, no barrier between gather and preload, and the TMA latency hides behind it.
     // (Measured and rejected: dropping the barrier at the top of the loop and deferring the wait for the previous
     // tile's TMA store until after the gather: the exposed latency only moves to the wait for the e tile, 0.2 %.)
@@ -893,23 +880,6 @@ __global__ void abs_senders_kernel(const int32_t* __restrict__ senders, const in
   if (e < E) out[e] = __ldg(row_base + e / K) + __ldg(senders + e);
 }
 
-// tbar[r] = (sum of the partial row sums that cover receiver r) / K
-__global__ void combine_partials_kernel(const float* __restrict__ partial, int K, int R, float* __restrict__ tbar) {
-  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (row >= R) return;
-  const int e0 = row * K, e1 = e0 + K - 1;
-  const int t0 = e0 / kTileM, t1 = e1 / kTileM;
-  float4 s = make_float4(0, 0, 0, 0);
-  for (int t = t0; t <= t1; ++t) {
-    const int seg = row - (t * kTileM) / K;
-    float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)t * 4 + seg) * kD + lane * 4);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-  }
-  const float kf = (float)K;
-  *reinterpret_cast<float4*>(tbar + (size_t)row * kD + lane * 4) = make_float4(s.x / kf, s.y / kf, s.z / kf, s.w / kf);
-}
-
 template <typename T16>
 __global__ void build_weight_image_kernel(const float* __restrict__ w, uint16_t* __restrict__ image, float scale) {
   // w: fp32 [128 (k), 128 (n)] row-major; image element (n, k) at swz_offset(n, k)
@@ -1001,11 +971,11 @@ static int make_edge_state_map(const uint16_t* e, int E, CUtensorMap* out) {
   return rc == CUDA_SUCCESS ? PST_OK : PST_ERR_CUDA;
 }
 
-// mode 0: writes tbar (mean over K of the 2nd hidden layer) into agg_out[R,128]; the caller applies W3, b3.
+// mode 0: writes per-tile partial row sums of the 2nd hidden layer (partial[num_tiles][4][128]); the node kernel forms the
+// per-receiver mean and applies W3, b3.
 // mode 1: e <- LN(e + MLP).
 int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e, const uint16_t* ps,
-                           const uint16_t* pr, const int32_t* senders, const int32_t* row_base, float* partial, int R,
-                           float* agg_out) {
+                           const uint16_t* pr, const int32_t* senders, const int32_t* row_base, float* partial, int R) {
   const int K = m->cfg.num_neighbor;
   const PstLayerW& L = m->w.layer[layer];
   EdgeMlpParams p{};
@@ -1038,9 +1008,7 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   if (mode == 0) {
     if (half) edge_mlp_tc_kernel<__half, 0><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
     else edge_mlp_tc_kernel<__nv_bfloat16, 0><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
-    if (!agg_out) return 1;  // the fused node kernel reads the partial sums directly
-    combine_partials_kernel<<<(R + 7) / 8, 256, 0, st>>>(partial, K, R, agg_out);
-    return 2;
+    return 1;  // the fused node kernel (node_chain_tc.cu) sums the partial rows of each receiver
   }
   if (half) edge_mlp_tc_kernel<__half, 1><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
   else edge_mlp_tc_kernel<__nv_bfloat16, 1><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);

@@ -234,12 +234,6 @@ __global__ void token_embed_kernel(const float* __restrict__ table, const int32_
 // One block per receiver row (K edges); thread = output channel, its 27 weights in registers, the
 // edge's features broadcast from shared memory as float4.  OutT = float (fp32 mode) or a 16-bit
 // type (tensor-core modes keep the edge state in the operand precision of the edge MLPs).
-template <typename OutT>
-__device__ __forceinline__ OutT to_out(float v);
-template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
-template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
-template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
-
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   unsigned long long d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
@@ -250,8 +244,6 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 template <typename OutT>
 __device__ __forceinline__ void store_pair(OutT* p, float2 v);
 template <> __device__ __forceinline__ void store_pair<float>(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
-template <> __device__ __forceinline__ void store_pair<__half>(__half* p, float2 v) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y); }
-template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloat16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
 
 // 128 threads = 2 receiver rows x 64 channel pairs; each thread keeps the 27 x 2 weights of its channel
 // pair in registers and does one packed FFMA2 per feature.
@@ -468,7 +460,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
         // message MLP: returns the per-receiver mean of the 2nd hidden layer; the 3rd linear commutes with
         // that mean (no activation follows it) and is applied by the node kernel
         PstSpan span(m, st, 1);
-        int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, ws.senders_abs, row_base, ws.partial, R, nullptr);  // the node kernel sums the partials itself
+        int n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, ws.senders_abs, row_base, ws.partial, R);  // the node kernel sums the partials itself
         if (n < 0) return n;
         L.count += n;
       }
@@ -480,7 +472,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       }
       if (l == cfg.gnn_layers - 1) break;  // the last layer's edge update is never read (model.py:385)
       PstSpan span(m, st, 2);
-      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), ps2, pr2, ws.senders_abs, row_base, ws.partial, R, nullptr);
+      int n = pst_launch_edge_mlp_tc(m, st, l, 1, reinterpret_cast<uint16_t*>(ws.e), ps2, pr2, ws.senders_abs, row_base, ws.partial, R);
       if (n < 0) return n;
       L.count += n;
     }

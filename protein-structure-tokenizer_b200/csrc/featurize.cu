@@ -267,12 +267,7 @@ __device__ __forceinline__ void bitonic_sort64(unsigned long long& a0, unsigned 
   for (int k = 2; k <= 64; k <<= 1) bitonic_stages(a0, a1, lane, k);
 }
 
-// 1.5**k, k = 0..14 (utils/protein_utils.py:266): exact in fp64
-__constant__ double c_rbf_scale[15] = {1.0, 1.5, 2.25, 3.375, 5.0625, 7.59375, 11.390625, 17.0859375, 25.62890625,
-                                      38.443359375, 57.6650390625, 86.49755859375, 129.746337890625,
-                                      194.6195068359375, 291.92926025390625};
-
-// 1 / 1.5**k: the RBF argument -d*d / 1.5**k (utils/protein_utils.py:266-270) is formed as a product; the one-ulp
+// 1 / 1.5**k, k = 0..14: the RBF argument -d*d / 1.5**k (utils/protein_utils.py:266-270) is formed as a product; the one-ulp
 // (fp64) difference from the reference's division is 1e-14 relative on the result, far below the fp32 rounding.
 __constant__ double c_rbf_inv_scale[15] = {1.0 / 1.0, 1.0 / 1.5, 1.0 / 2.25, 1.0 / 3.375, 1.0 / 5.0625, 1.0 / 7.59375,
                                           1.0 / 11.390625, 1.0 / 17.0859375, 1.0 / 25.62890625, 1.0 / 38.443359375,

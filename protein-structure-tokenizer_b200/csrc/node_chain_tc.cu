@@ -65,11 +65,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(mbar)
-               : "memory");
-}
 __device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint16_t mask) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
@@ -244,12 +239,6 @@ struct Epi {
   uint32_t lane_off;  // TMEM lane field of this thread's warp
   float* red;         // [2 stages][2 halves][128 rows]
 };
-
-// element j (0..31) of a 32-float parameter chunk, fetched as float4 (uniform address: one broadcast transaction)
-__device__ __forceinline__ float ldg4(const float* __restrict__ base, int j) {
-  const float4 t = __ldg(reinterpret_cast<const float4*>(base) + (j >> 2));
-  return (j & 3) == 0 ? t.x : (j & 3) == 1 ? t.y : (j & 3) == 2 ? t.z : t.w;
-}
 
 // LayerNorm over the full 128-wide row (biased variance of the centred row, eps 1e-5: gnn_layers.py:108-120,162-164;
 // hk.LayerNorm is the same formula); x = this thread's 64 columns

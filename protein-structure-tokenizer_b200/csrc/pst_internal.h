@@ -157,7 +157,7 @@ int pst_launch_indexes_to_codes(const pst_model* m, cudaStream_t st, const int32
 // Returns kernels launched, <0 on error.
 int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int mode, uint16_t* e,
                            const uint16_t* ps, const uint16_t* pr, const int32_t* senders,
-                           const int32_t* row_base, float* partial, int R, float* agg_out);
+                           const int32_t* row_base, float* partial, int R);
 size_t pst_tc_partial_floats(int R, int K);
 int pst_launch_abs_senders(const pst_model* m, cudaStream_t st, const int32_t* senders, const int32_t* row_base, int R,
                            int32_t* senders_abs);
