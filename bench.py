@@ -62,27 +62,67 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region.
+
+    NVML is polled in-process every 2 ms (a short timed region still gets tens of samples); when NVML cannot be
+    initialised the recipe's `nvidia-smi --query-gpu` line is used instead (one sample per ~100 ms)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, uuid: str | None = None):
         self.index = index
-        self.samples = []
+        self.samples = []  # [sm_mhz, sm_max_mhz, 4 x bool]
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        self._handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml, self._handle, self.source = pynvml, h, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml, self._handle
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        self.samples.append([sm, self._max] + [bool(r & b) for b in bits])
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")] if out else []
+        if len(f) >= 6 and f[0].replace(".", "").isdigit():
+            self.samples.append([float(f[0]), float(f[1])] + [x.lower().startswith("active") for x in f[2:6]])
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -96,11 +136,10 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "samples": len(self.samples), "source": self.source}
 
 
 def make_batch(workload: str, rank: int):
@@ -302,7 +341,11 @@ def run_ours(args):
         raise SystemExit("device status != 0 after warm-up")
 
     # timed region: the fused call replays its CUDA graph (captured during warm-up: repeated argument set)
-    with ClockSampler(local_rank) as clk:
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local_rank, gpu_uuid) as clk:
         ms_total = timed(step_resident, args.steps)
     launches = tok.launches * args.steps
     # kernel-level pass for the roofline: the same K steps again with the library's event spans around the k-NN and

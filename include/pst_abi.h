@@ -97,8 +97,13 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
                      int device, pst_model** out);
 void pst_model_destroy(pst_model* model);
 
+/* Largest batch one hot call accepts: total_residues * num_neighbor edges.  Kernels index edge rows and
+ * their feature floats with 32-bit integers; beyond this the call returns PST_ERR_BAD_ARGUMENT (split the
+ * batch: pst/tokenizer.py sends chunks of <= 131 072 residues, i.e. 6.5 M edges at K = 50). */
+#define PST_MAX_EDGES_PER_CALL (1 << 26)
+
 /* Bytes of caller-provided scratch needed by any hot call below for a batch of
- * `total_residues` rows in `num_structures` structures. */
+ * `total_residues` rows in `num_structures` structures (0 if the batch exceeds PST_MAX_EDGES_PER_CALL). */
 size_t pst_workspace_bytes(const pst_model* model, int total_residues, int num_structures);
 
 /* Replaces the host featuriser: frames (model/quat_affine.py:406-522), centroid and

@@ -292,6 +292,7 @@ void pst_model_destroy(pst_model* m) {
 
 size_t pst_workspace_bytes(const pst_model* m, int total_residues, int num_structures) {
   if (!m || total_residues < 0 || num_structures < 0) return 0;
+  if ((long long)total_residues * m->cfg.num_neighbor > (long long)PST_MAX_EDGES_PER_CALL) return 0;
   (void)num_structures;
   return pst_carve_workspace(m, nullptr, total_residues, total_residues).bytes;
 }
@@ -332,6 +333,7 @@ int pst_read_status(const pst_model* m, void* stream, void* workspace) {
 
 static int check_batch(const pst_model* m, const void* offsets, int B, int R, void* ws, size_t ws_bytes, int T) {
   if (!m || !offsets || B < 0 || R < 0 || T < 0 || T > R) return PST_ERR_BAD_ARGUMENT;
+  if ((long long)R * m->cfg.num_neighbor > (long long)PST_MAX_EDGES_PER_CALL) return PST_ERR_BAD_ARGUMENT;
   if (!ws) return PST_ERR_BAD_ARGUMENT;
   if (ws_bytes < pst_carve_workspace(m, nullptr, R, R).bytes) return PST_ERR_WORKSPACE_TOO_SMALL;
   return PST_OK;

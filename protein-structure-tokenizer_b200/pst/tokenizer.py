@@ -85,6 +85,8 @@ class StructureTokenizer:
 
     def _workspace(self, R: int, B: int):
         need = self.lib.pst_workspace_bytes(self._h, int(R), int(B))
+        if need == 0:  # include/pst_abi.h: PST_MAX_EDGES_PER_CALL
+            raise ValueError(f"a batch of {R} residues exceeds the per-call limit of the C ABI; use tokenize(), which sends chunks")
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = self.torch.empty(int(need), dtype=self.torch.uint8, device=self.device)

@@ -95,6 +95,15 @@ def test_too_short_structure_raises_status(tok):
         tok.tokenize([bb])
 
 
+def test_oversized_batch_is_refused_by_the_abi(tok):
+    # include/pst_abi.h PST_MAX_EDGES_PER_CALL: kernels index edge rows with 32-bit integers
+    too_many = (1 << 26) // tok.cfg.num_neighbor + 1
+    assert tok.lib.pst_workspace_bytes(tok._h, too_many, 1) == 0
+    assert tok.lib.pst_workspace_bytes(tok._h, too_many - 1, 1) > 0
+    with pytest.raises(ValueError):
+        tok._workspace(too_many, 1)
+
+
 def test_atom37_and_backbone4_layouts_agree(tok):
     from pst import synthetic as syn
 
