@@ -18,7 +18,7 @@ namespace {
 
 // prep record: [0:3] centroid, [3:6] CA, [6:9] n, [9:12] u, [12:15] v
 __global__ void prep_kernel(const float* __restrict__ atoms, const uint8_t* __restrict__ mask,
-                            int apr, int R, double* __restrict__ prep, double4* __restrict__ cen4) {
+                            int apr, int R, double* __restrict__ prep, double* __restrict__ cen) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
   const float* a = atoms + (size_t)i * apr * 3;
@@ -39,7 +39,12 @@ __global__ void prep_kernel(const float* __restrict__ atoms, const uint8_t* __re
   o[0] = sx / c;
   o[1] = sy / c;
   o[2] = sz / c;
-  cen4[i] = make_double4(o[0], o[1], o[2], 0.0);  // compact copy: the k-NN scan streams 32 B per candidate
+  // structure-of-arrays copy (x[R], y[R], z[R]) for the k-NN scan: 32 consecutive candidates of one coordinate are
+  // two 128-byte lines per warp load (an array of 32-byte records, two candidates per lane, cost 16 L1 tag requests
+  // per load instruction and made the scan the largest consumer of the kernel's saturated L1 data pipe)
+  cen[i] = o[0];
+  cen[(size_t)R + i] = o[1];
+  cen[2 * (size_t)R + i] = o[2];
   double nx = (double)a[0], ny_ = (double)a[1], nz_ = (double)a[2];
   double cax = (double)a[3], cay = (double)a[4], caz = (double)a[5];
   double ccx = (double)a[6], ccy = (double)a[7], ccz = (double)a[8];
@@ -300,17 +305,17 @@ __device__ __forceinline__ double exp_neg_for_fp32(double x) {
 constexpr int kKnnWarps = 8;
 constexpr unsigned long long kIdxMask = 0x7FFull;  // 11 bits: L <= 2048
 
-__device__ __forceinline__ unsigned long long packed_key(const double4& ci, const double4* __restrict__ cen4, int base, int j, int L) {
+__device__ __forceinline__ unsigned long long packed_key(const double3& ci, const double* __restrict__ cx, const double* __restrict__ cy,
+                                                         const double* __restrict__ cz, int base, int j, int L) {
   if (j >= L) return 0xFFFFFFFFFFFFFFFFull;
-  const double4 cj = cen4[base + j];
-  const double dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z;
+  const double dx = ci.x - cx[base + j], dy = ci.y - cy[base + j], dz = ci.z - cz[base + j];
   const unsigned long long bits = (unsigned long long)__double_as_longlong(sqrt((dx * dx + dy * dy) + dz * dz));
   return (bits & ~kIdxMask) | (unsigned long long)j;
 }
 
 template <bool COMPACT>
 __global__ void __launch_bounds__(kKnnWarps * 32)
-knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen4, const int32_t* __restrict__ offsets,
+knn_warp_kernel(const double* __restrict__ prep, const double* __restrict__ cen, const int32_t* __restrict__ offsets,
                 int B, int R, int K, int max_len, int32_t* __restrict__ senders, float* __restrict__ feat,
                 int32_t* __restrict__ status, int32_t* __restrict__ redo) {
   __shared__ int s_j[kKnnWarps][64];
@@ -338,7 +343,11 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
       for (int t = lane; t < K * kStride; t += 32) feat[(size_t)row * K * kStride + t] = 0.f;
     return;
   }
-  const double4 ci = cen4[row];
+  const double* pi = prep + (size_t)row * PST_PREP_STRIDE;
+  const double3 ci = make_double3(pi[0], pi[1], pi[2]);
+  const double* cx = cen;
+  const double* cy = cen + (size_t)R;
+  const double* cz = cen + 2 * (size_t)R;
   unsigned long long b0 = 0, b1 = 0;  // running 64 smallest keys, ascending, element e = 2*lane + r
   const int n_chunks = (L + 63) >> 6;
   // Chunks are visited outwards from the one that holds the row itself; a chunk none of whose keys is below
@@ -374,9 +383,9 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
     const int delta = (step + 1) >> 1;
     const int c = (step & 1) ? c_home + delta : c_home - delta;
     if (step > 0 && (c < 0 || c >= n_chunks)) continue;
-    const int j0 = c * 64 + 2 * lane;
-    const unsigned long long a0 = packed_key(ci, cen4, base, j0, L);
-    const unsigned long long a1 = packed_key(ci, cen4, base, j0 + 1, L);
+    const int j0 = c * 64 + lane;  // lanes on consecutive candidates (which lane holds which key does not matter below)
+    const unsigned long long a0 = packed_key(ci, cx, cy, cz, base, j0, L);
+    const unsigned long long a1 = packed_key(ci, cx, cy, cz, base, j0 + 32, L);
     if (step == 0) {  // the home chunk sets the first bound
       b0 = a0;
       b1 = a1;
@@ -418,35 +427,35 @@ knn_warp_kernel(const double* __restrict__ prep, const double4* __restrict__ cen
 
   // ---- features: squared distances once per edge, then the 750 RBF items and the 600 orientation items as two
   // divergence-free loops (item -> lane mapping keeps consecutive lanes on consecutive output floats)
-  const double* pi = prep + (size_t)row * PST_PREP_STRIDE;
   for (int e = lane; e < K; e += 32) {
-    const double4 cj = cen4[base + s_j[warp][first + e]];
-    const double dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z;
+    const double* cj = prep + (size_t)(base + s_j[warp][first + e]) * PST_PREP_STRIDE;  // [0:3] = centroid
+    const double dx = ci.x - cj[0], dy = ci.y - cj[1], dz = ci.z - cj[2];
     const double d = sqrt((dx * dx + dy * dy) + dz * dz);  // the reference squares the rounded distance again
     s_d2[warp][e] = d * d;
   }
   __syncwarp();
   if (COMPACT) {
-    // 16 floats per edge: [d*d, 12 orientation features, 0, 0, 0]; item -> lane keeps consecutive lanes on consecutive floats
+    // 16 floats per edge: [d*d, 12 orientation features, 0, 0, 0]; item -> lane keeps consecutive lanes on consecutive floats.
+    // t = lane + 32 * it, so the slot c = t & 15 is a per-lane constant: the receiver's basis row and (for p) its CA stay in
+    // registers and every iteration loads only the three doubles of the sender's vector (the kernel is bound by L1
+    // data-pipe wavefronts, profiles/r01_kernels_ncu_full.md: the loop used to issue nine scattered loads per item).
     float* out = feat + (size_t)row * K * 16;
-    const double ca_x = pi[3], ca_y = pi[4], ca_z = pi[5];
+    const int c = lane & 15;
+    const bool orient = c >= 1 && c <= 12;
+    const int g = orient ? (c - 1) / 3 : 0, r = orient ? (c - 1) - 3 * g : 0;  // g: 0:p 1:q 2:k 3:t ; r: basis row 0:n 1:u 2:v
+    const double b0 = pi[6 + 3 * r], b1 = pi[7 + 3 * r], b2 = pi[8 + 3 * r];
+    // p = B.(CA_j - CA_i); q, k, t = B.axis_j: subtracting +0.0 leaves every double (and its sign) unchanged
+    const double ox = g == 0 ? pi[3] : 0.0, oy = g == 0 ? pi[4] : 0.0, oz = g == 0 ? pi[5] : 0.0;
+    const int sv_off = 3 + 3 * g;
     for (int t = lane; t < K * 16; t += 32) {
-      const int e = t >> 4, c = t & 15;
+      const int e = t >> 4;
       double val = 0.0;
       if (c == 0) {
         val = s_d2[warp][e];
-      } else if (c <= 12) {
-        const int g = (c - 1) / 3, r = (c - 1) - 3 * g;
-        const double* pj = prep + (size_t)(base + s_j[warp][first + e]) * PST_PREP_STRIDE;
-        double vx, vy, vz;
-        if (g == 0) {
-          vx = pj[3] - ca_x; vy = pj[4] - ca_y; vz = pj[5] - ca_z;
-        } else {
-          const double* sv = pj + 3 + 3 * g;
-          vx = sv[0]; vy = sv[1]; vz = sv[2];
-        }
-        const double* b = pi + 6 + 3 * r;
-        val = b[0] * vx + b[1] * vy + b[2] * vz;
+      } else if (orient) {
+        const double* sv = prep + (size_t)(base + s_j[warp][first + e]) * PST_PREP_STRIDE + sv_off;
+        const double vx = sv[0] - ox, vy = sv[1] - oy, vz = sv[2] - oz;
+        val = b0 * vx + b1 * vy + b2 * vz;
       }
       out[t] = (float)val;
     }
@@ -481,10 +490,10 @@ bool pst_featurize_compact_ok(const pst_model* m) { return m->cfg.num_neighbor <
 
 int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms,
                          const uint8_t* mask, int apr, const int32_t* offsets, int B, int R,
-                         int32_t* senders, float* edge_feat, double* prep, double* cen4, int32_t* status, int32_t* redo,
+                         int32_t* senders, float* edge_feat, double* prep, double* cen, int32_t* status, int32_t* redo,
                          int compact) {
   if (R <= 0) return 0;
-  prep_kernel<<<(R + 127) / 128, 128, 0, st>>>(atoms, mask, apr, R, prep, reinterpret_cast<double4*>(cen4));
+  prep_kernel<<<(R + 127) / 128, 128, 0, st>>>(atoms, mask, apr, R, prep, cen);
   int n_pad = 64;
   while (n_pad < m->cfg.max_len) n_pad <<= 1;
   const size_t smem = (size_t)n_pad * (sizeof(unsigned long long) + sizeof(int));
@@ -495,14 +504,14 @@ int pst_launch_featurize(const pst_model* m, cudaStream_t st, const float* atoms
     cudaMemsetAsync(redo, 0, sizeof(int32_t), st);  // the counter
     const dim3 wg((R + kKnnWarps - 1) / kKnnWarps), rg(min(R, 2 * m->num_sms));
     if (compact) {
-      knn_warp_kernel<true><<<wg, kKnnWarps * 32, 0, st>>>(prep, reinterpret_cast<const double4*>(cen4), offsets, B, R,
+      knn_warp_kernel<true><<<wg, kKnnWarps * 32, 0, st>>>(prep, cen, offsets, B, R,
                                                             m->cfg.num_neighbor, m->cfg.max_len, senders, edge_feat, status, redo);
       // exact recompute of the (normally zero) rows flagged above
       cudaFuncSetAttribute(knn_feature_redo_kernel<kThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       knn_feature_redo_kernel<kThreads, true><<<rg, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,
                                                                            senders, edge_feat, status, redo);
     } else {
-      knn_warp_kernel<false><<<wg, kKnnWarps * 32, 0, st>>>(prep, reinterpret_cast<const double4*>(cen4), offsets, B, R,
+      knn_warp_kernel<false><<<wg, kKnnWarps * 32, 0, st>>>(prep, cen, offsets, B, R,
                                                              m->cfg.num_neighbor, m->cfg.max_len, senders, edge_feat, status, redo);
       cudaFuncSetAttribute(knn_feature_redo_kernel<kThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       knn_feature_redo_kernel<kThreads, false><<<rg, kThreads, smem, st>>>(prep, offsets, B, R, m->cfg.num_neighbor, m->cfg.max_len,

@@ -105,7 +105,7 @@ struct PstWorkspace {
   int32_t* row_base;     // [R]
   int32_t* redo;         // [1 + R] count, then the rows the packed-key k-NN kernel hands to the exact kernel
   double* prep;          // [R,16]
-  double* cen4;          // [R,4] centroid (x,y,z,0): compact copy for the k-NN scan
+  double* cen4;          // centroids as x[R], y[R], z[R] (room for 4R doubles): coalesced copy for the k-NN scan
   int32_t* senders;      // [E]
   float* edge_feat;      // [E,27]
   float* e;              // [E,128] fp32 (fp32 mode) or 16-bit (tensor-core modes: same pointer, half the bytes)

@@ -22,22 +22,39 @@ KEYS = [
 ]
 
 
-def launches(src, dst, steps):
+def launches(src, dst, steps=None):
+    """A pass of the hot call starts at `prep_kernel` and ends at `fsq_quantize_kernel`: only launches inside whole
+    passes are counted (model set-up before the first pass and a pass cut off by `-c` are dropped), and the number
+    of passes is counted from the list itself unless `steps` is given."""
     lines = [l for l in open(src) if not l.startswith("==")]
-    agg = collections.OrderedDict()
-    tot = 0.0
+    rows = []
     for row in csv.DictReader(lines):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
         name = row["Kernel Name"].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
         v = float(row["Metric Value"].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(row["Metric Unit"], 1.0)
+        rows.append((name, v))
+    starts = [i for i, (n, _) in enumerate(rows) if n.startswith("prep_kernel")]
+    ends = [i for i, (n, _) in enumerate(rows) if n.startswith("fsq_quantize_kernel")]
+    dropped = 0
+    if starts and ends and ends[-1] > starts[0]:
+        dropped = starts[0] + len(rows) - 1 - ends[-1]
+        rows = rows[starts[0]:ends[-1] + 1]
+        passes = sum(1 for n, _ in rows if n.startswith("fsq_quantize_kernel"))
+    else:
+        passes = steps or 1
+    steps = steps or passes
+    agg = collections.OrderedDict()
+    tot = 0.0
+    for name, v in rows:
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += v
         tot += v
     with open(dst, "w") as fh:
-        fh.write(f"# ncu launch list ({src}): `--metrics gpu__time_duration.sum --clock-control none`, {steps} timed steps\n\n")
+        fh.write(f"# ncu launch list ({src}): `--metrics gpu__time_duration.sum --clock-control none`; {steps} whole passes of the "
+                 f"hot call ({dropped} launches outside them dropped)\n\n")
         fh.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's live event timing.\n\n")
         fh.write("| kernel | share of step | ms / step | launches / step | avg us |\n|---|---|---|---|---|\n")
         for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -65,6 +82,6 @@ def full(src, dst):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 2)
+        launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else None)
     else:
         full(sys.argv[2], sys.argv[3])
