@@ -103,7 +103,9 @@ void pst_model_destroy(pst_model* model);
 #define PST_MAX_EDGES_PER_CALL (1 << 26)
 
 /* Bytes of caller-provided scratch needed by any hot call below for a batch of
- * `total_residues` rows in `num_structures` structures (0 if the batch exceeds PST_MAX_EDGES_PER_CALL). */
+ * `total_residues` rows in `num_structures` structures (0 if the batch exceeds PST_MAX_EDGES_PER_CALL).
+ * The workspace pointer must be 256-byte aligned (cudaMalloc, torch and XLA allocations are); a misaligned
+ * one is refused with PST_ERR_BAD_ARGUMENT. */
 size_t pst_workspace_bytes(const pst_model* model, int total_residues, int num_structures);
 
 /* Replaces the host featuriser: frames (model/quat_affine.py:406-522), centroid and

@@ -334,7 +334,7 @@ int pst_read_status(const pst_model* m, void* stream, void* workspace) {
 static int check_batch(const pst_model* m, const void* offsets, int B, int R, void* ws, size_t ws_bytes, int T) {
   if (!m || !offsets || B < 0 || R < 0 || T < 0 || T > R) return PST_ERR_BAD_ARGUMENT;
   if ((long long)R * m->cfg.num_neighbor > (long long)PST_MAX_EDGES_PER_CALL) return PST_ERR_BAD_ARGUMENT;
-  if (!ws) return PST_ERR_BAD_ARGUMENT;
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return PST_ERR_BAD_ARGUMENT;  // TMA maps / 32-byte vector loads
   if (ws_bytes < pst_carve_workspace(m, nullptr, R, R).bytes) return PST_ERR_WORKSPACE_TOO_SMALL;
   return PST_OK;
 }

@@ -428,8 +428,9 @@ knn_warp_kernel(const double* __restrict__ prep, const double* __restrict__ cen,
   // ---- features: squared distances once per edge, then the 750 RBF items and the 600 orientation items as two
   // divergence-free loops (item -> lane mapping keeps consecutive lanes on consecutive output floats)
   for (int e = lane; e < K; e += 32) {
-    const double* cj = prep + (size_t)(base + s_j[warp][first + e]) * PST_PREP_STRIDE;  // [0:3] = centroid
-    const double dx = ci.x - cj[0], dy = ci.y - cj[1], dz = ci.z - cj[2];
+    const double* cj = prep + (size_t)(base + s_j[warp][first + e]) * PST_PREP_STRIDE;  // [0:3] = centroid (128-byte records)
+    const double2 cxy = *reinterpret_cast<const double2*>(cj);
+    const double dx = ci.x - cxy.x, dy = ci.y - cxy.y, dz = ci.z - cj[2];
     const double d = sqrt((dx * dx + dy * dy) + dz * dz);  // the reference squares the rounded distance again
     s_d2[warp][e] = d * d;
   }

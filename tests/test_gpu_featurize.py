@@ -104,6 +104,20 @@ def test_oversized_batch_is_refused_by_the_abi(tok):
         tok._workspace(too_many, 1)
 
 
+def test_misaligned_workspace_is_refused(tok):
+    import torch
+
+    R, B, K = 64, 1, tok.cfg.num_neighbor
+    atoms = torch.zeros((R, 4, 3), dtype=torch.float32, device=tok.device)
+    offs = torch.tensor([0, R], dtype=torch.int32, device=tok.device)
+    senders = torch.empty((R * K,), dtype=torch.int32, device=tok.device)
+    ws = tok._workspace(R, B)
+    extra = torch.empty(ws.numel() + 256, dtype=torch.uint8, device=tok.device)
+    rc = tok.lib.pst_featurize_knn(tok._h, tok._stream(), atoms.data_ptr(), None, 4, offs.data_ptr(), B, R,
+                                   senders.data_ptr(), None, extra.data_ptr() + 8, ws.numel())
+    assert rc == -1  # PST_ERR_BAD_ARGUMENT: include/pst_abi.h asks for a 256-byte aligned workspace
+
+
 def test_atom37_and_backbone4_layouts_agree(tok):
     from pst import synthetic as syn
 
