@@ -242,6 +242,20 @@ knn_feature_redo_kernel(const double* __restrict__ prep, const int32_t* __restri
 // the sorted head: if two adjacent entries among ranks 0..K+2 share the truncated distance (this also
 // covers exact ties), the row is flagged and recomputed by the exact (distance, index) block kernel
 // below.  The emitted order is therefore always the stable ascending argsort of the reference contract.
+//
+// The scan orders candidates by the SQUARED distance (no fp64 sqrt per candidate; build with -DPST_KNN_DIST_KEYS for
+// keys made of the rounded distance itself).  sqrt is monotone, so the two orders differ only where two different
+// squares round to the same distance, which the reference then orders by index.  Such squares lie within 4 ulps of
+// each other (sqrt(y) - sqrt(x) <= ulp(r) gives (y - x) / x <= 2^-51), i.e. their truncated keys are equal or
+// ADJACENT: with squared keys the head check therefore flags every adjacent pair whose truncated values differ by
+// at most one (a relative gap below 2^-41: never seen outside constructed cases), and the exact kernel, which does
+// take the square roots, decides those rows.  tests/test_knn_key_model.py states the rule as a NumPy model and
+// checks it on CASP14, on a lattice and on constructed same-sqrt pairs.
+#ifdef PST_KNN_DIST_KEYS
+constexpr bool kKeyIsD2 = false;
+#else
+constexpr bool kKeyIsD2 = true;
+#endif
 __device__ __forceinline__ void ce_remote(unsigned long long& a, int lane_mask, bool keep_min) {
   const unsigned long long o = __shfl_xor_sync(0xffffffffu, a, lane_mask);
   if ((o < a) == keep_min) a = o;
@@ -309,7 +323,8 @@ __device__ __forceinline__ unsigned long long packed_key(const double3& ci, cons
                                                          const double* __restrict__ cz, int base, int j, int L) {
   if (j >= L) return 0xFFFFFFFFFFFFFFFFull;
   const double dx = ci.x - cx[base + j], dy = ci.y - cy[base + j], dz = ci.z - cz[base + j];
-  const unsigned long long bits = (unsigned long long)__double_as_longlong(sqrt((dx * dx + dy * dy) + dz * dz));
+  const double d2 = (dx * dx + dy * dy) + dz * dz;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(kKeyIsD2 ? d2 : sqrt(d2));
   return (bits & ~kIdxMask) | (unsigned long long)j;
 }
 
@@ -408,11 +423,13 @@ knn_warp_kernel(const double* __restrict__ prep, const double* __restrict__ cen,
     cnt += n;
   }
   if (cnt > 0) flush();
-  // exactness check on the sorted head (ranks 0 .. K+2): equal truncated distances -> exact recompute
+  // exactness check on the sorted head (ranks 0 .. K+2): equal (squared keys: equal or adjacent) truncated values ->
+  // exact recompute
   {
+    constexpr unsigned long long kGap = kKeyIsD2 ? 1ull : 0ull;
     const unsigned long long nxt = __shfl_down_sync(0xffffffffu, b0, 1);  // element 2*lane + 2
-    bool clash = (2 * lane + 1 <= K + 2) && ((b0 >> 11) == (b1 >> 11)) && (b1 != 0xFFFFFFFFFFFFFFFFull);
-    clash = clash || ((2 * lane + 2 <= K + 2) && lane < 31 && ((b1 >> 11) == (nxt >> 11)) && (nxt != 0xFFFFFFFFFFFFFFFFull));
+    bool clash = (2 * lane + 1 <= K + 2) && ((b1 >> 11) - (b0 >> 11) <= kGap) && (b1 != 0xFFFFFFFFFFFFFFFFull);
+    clash = clash || ((2 * lane + 2 <= K + 2) && lane < 31 && ((nxt >> 11) - (b1 >> 11) <= kGap) && (nxt != 0xFFFFFFFFFFFFFFFFull));
     if (__any_sync(0xffffffffu, clash)) {
       if (lane == 0) redo[1 + atomicAdd(redo, 1)] = row;
       return;

@@ -151,3 +151,50 @@ def test_exact_distance_ties_follow_stable_argsort(tok):
     u = ulp_diff(f, o["edge_features"].astype(np.float32))
     tiny = np.abs(o["edge_features"].astype(np.float32)) < 1e-30
     assert (u[~tiny] <= 1).all()
+
+
+@pytest.mark.parametrize("straddle", [False, True])
+def test_same_sqrt_pair_is_decided_by_the_exact_kernel(tok, straddle):
+    """Two candidates whose SQUARED distances to row 0 are different doubles that round to the same distance: the
+    reference orders them by index, the scan's squared keys by their squares.  With `straddle` the truncated keys
+    are adjacent rather than equal, the case the head check's "differ by at most one" rule exists for
+    (tests/test_knn_key_model.py is the CPU statement of that rule).  Centroid = CA here (only CA is marked present)."""
+    from oracle import featurize as fz
+
+    rng = np.random.default_rng(11 if straddle else 5)
+    pair = None
+    for _ in range(20000):
+        x, y = rng.uniform(3.0, 6.0, 2).astype(np.float32).astype(np.float64)
+        z0 = np.float32(rng.uniform(5e-5, 4e-4))
+        z = (z0.view(np.int32) + np.arange(1 << 14, dtype=np.int32)).view(np.float32).astype(np.float64)  # successive fp32 values
+        d2 = (x * x + y * y) + z * z
+        nz = np.nonzero(np.diff(d2.view(np.uint64)) > 0)[0]
+        lo, hi = d2[nz], d2[nz + 1]
+        low11 = lo.view(np.uint64) & np.uint64(0x7FF)
+        ok = (np.sqrt(lo) == np.sqrt(hi)) & ((low11 == np.uint64(0x7FF)) if straddle else (low11 < np.uint64(0x700)))
+        if ok.any():
+            i = nz[np.nonzero(ok)[0][0]]
+            pair = (np.array([x, y, z[i]]), np.array([x, y, z[i + 1]]))
+            break
+    assert pair is not None
+    L, K = 58, 50
+    far = rng.uniform(-1.0, 1.0, (L - 1, 3))
+    far = far / np.linalg.norm(far, axis=1, keepdims=True) * rng.uniform(9.0, 30.0, (L - 1, 1))
+    ca = np.concatenate([np.zeros((1, 3)), far]).astype(np.float32)
+    ca[5], ca[9] = pair[1].astype(np.float32), pair[0].astype(np.float32)  # larger square at the smaller index
+    assert np.array_equal(ca[5].astype(np.float64), pair[1]) and np.array_equal(ca[9].astype(np.float64), pair[0])
+    atoms = np.zeros((L, 4, 3), np.float32)
+    atoms[:, 1] = ca
+    atoms[:, 0] = ca + np.float32([-0.5, 1.4, 0.0])
+    atoms[:, 2] = ca + np.float32([1.5, 0.0, 0.0])
+    atoms[:, 3] = ca + np.float32([2.0, 1.0, 0.5])
+    mask = np.zeros((L, 4), np.uint8)
+    mask[:, 1] = 1
+    s, _, _ = _run(tok, [atoms], [mask])
+    assert tok.read_status() == 0
+    cen = ca.astype(np.float64)
+    d = fz.pairwise_distance(cen)
+    assert d[0, 5] == d[0, 9]
+    ref = fz.knn_senders(d, K)
+    assert list(ref[0, :2]) == [5, 9]
+    assert np.array_equal(s.reshape(L, K).astype(np.int64), ref)
