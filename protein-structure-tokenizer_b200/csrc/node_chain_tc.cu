@@ -152,8 +152,19 @@ __device__ __forceinline__ void st256u(void* ptr, const uint32_t* r) {
                : "memory");
 }
 
+#ifdef PST_NODE_GELU_APPROX
+// EXPERIMENT, off by default and not yet measured or tolerance-tested on a GPU: one MUFU.TANH
+// (relative error ~2^-11, what the edge MLP's GELU uses) instead of ex2 + rcp; build with
+// tools/build_variant.sh nodegelu node_chain_tc.cu -DPST_NODE_GELU_APPROX and compare with tools/variant_run.sh
+__device__ __forceinline__ float tanh_fast(float u) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return t;
+}
+#else
 // tanh to ~1e-7 absolute: 1 - 2 / (exp(2u) + 1)   (exp overflow -> +inf -> 1, underflow -> 0 -> -1)
 __device__ __forceinline__ float tanh_fast(float u) { return 1.0f - __fdividef(2.0f, __expf(2.0f * u) + 1.0f); }
+#endif
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
   return 0.5f * x * (1.0f + tanh_fast(u));
