@@ -25,6 +25,36 @@ def test_every_declared_symbol_is_exported(built_lib):
         assert hasattr(lib, n), f"{n} declared in pst_abi.h but not exported"
 
 
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(built_lib, tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (what a cgo / JNI / XLA-FFI shim includes) and a C
+    program using only host-side entry points must link and run against the shared library without a GPU."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "pst_abi.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "abi_probe.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "pst_abi.h"\n'
+        "int main(void) {\n"
+        "  pst_config cfg; pst_model* m = NULL; float blob = 0.f;\n"
+        "  memset(&cfg, 0, sizeof cfg);\n"
+        "  if (pst_abi_version() != PST_ABI_VERSION) return 1;\n"
+        "  if (pst_model_create(&cfg, &blob, 1, 0, &m) != PST_ERR_UNSUPPORTED_CONFIG || m != NULL) return 2;\n"
+        "  if (pst_workspace_bytes(NULL, 1, 1) != 0) return 3;\n"
+        "  if (strlen(pst_status_string(PST_ERR_WORKSPACE_TOO_SMALL)) == 0) return 4;\n"
+        '  puts("ok");\n  return 0;\n}\n')
+    exe = tmp_path / "abi_probe"
+    libdir = os.path.dirname(built_lib)
+    subprocess.run([gcc, "-std=c99", "-I", os.path.dirname(hdr), str(src), "-o", str(exe), "-L", libdir,
+                    "-l:" + os.path.basename(built_lib), "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
+
+
 def test_python_binding_covers_the_header(built_lib):
     from pst import _lib
 
