@@ -485,7 +485,11 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
 #pragma unroll
       for (int q = 0; q < 2; ++q)
 #pragma unroll
+#ifdef PST_NODE_RECIP_MUL  // EXPERIMENT (off, not yet run on a GPU): reciprocal multiply instead of IEEE division
+        for (int j = 0; j < 32; ++j) x[q][j] = x[q][j] * (1.0f / kf);
+#else
         for (int j = 0; j < 32; ++j) x[q][j] = x[q][j] / kf;
+#endif
     }
     split_store_half(e, X, x);
     publish();
@@ -690,7 +694,11 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
       for (int q = 0; q < 2; ++q)
 #pragma unroll 8
         for (int j = 0; j < 32; ++j) {
+#ifdef PST_NODE_RECIP_MUL
+          const float r = x[q][j] * (1.0f / d);
+#else
           const float r = x[q][j] / d;
+#endif
           const float4* wr = reinterpret_cast<const float4*>(p.down_w + (size_t)(e.half * 64 + q * 32 + j) * PST_C8);
           const float4 w0 = __ldg(wr), w1 = __ldg(wr + 1);
           zc[0] = fmaf(r, w0.x, zc[0]); zc[1] = fmaf(r, w0.y, zc[1]); zc[2] = fmaf(r, w0.z, zc[2]); zc[3] = fmaf(r, w0.w, zc[3]);
