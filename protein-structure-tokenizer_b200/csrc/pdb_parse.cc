@@ -18,7 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "pst_abi.h"
@@ -56,22 +56,57 @@ const ResType kResTypes[20] = {
     {"VAL", "C CA CB CG1 CG2 N O"},
 };
 
-int atom_slot(const std::string& name) {
-  for (int i = 0; i < 37; ++i)
-    if (name == kAtomTypes[i]) return i;
-  return -1;
-}
-// the same for a fixed-column field, without allocating
-int atom_slot_field(const char* s, size_t n) {
+// A stripped field of at most three characters packed into 32 bits (character i in byte i): atom and residue names
+// are compared as integers in the per-line loop (no std::string, no strlen).  Returns 0 for an empty field and
+// 0xFFFFFFFF for one that is longer than three characters after stripping.
+inline uint32_t pack_field(const char* s, size_t n) {
   size_t a = 0, b = n;
   while (a < b && s[a] == ' ') ++a;
   while (b > a && s[b - 1] == ' ') --b;
   const size_t m = b - a;
-  if (m == 0 || m > 3) return -1;
-  for (int i = 0; i < 37; ++i) {
-    const char* t = kAtomTypes[i];
-    if (strlen(t) == m && memcmp(t, s + a, m) == 0) return i;
+  if (m > 3) return 0xFFFFFFFFu;
+  uint32_t code = 0;
+  for (size_t i = 0; i < m; ++i) code |= static_cast<uint32_t>(static_cast<unsigned char>(s[a + i])) << (8 * i);
+  return code;
+}
+inline uint32_t pack_cstr(const char* s) { return pack_field(s, strlen(s)); }
+
+struct Tables {
+  uint32_t atom_code[37];
+  uint32_t res_code[20];
+  uint8_t exists[21][37];  // atom37_atom_exists per residue type (20 = UNK: N, CA, C, CB)
+  Tables() {
+    for (int i = 0; i < 37; ++i) atom_code[i] = pack_cstr(kAtomTypes[i]);
+    memset(exists, 0, sizeof(exists));
+    for (int t = 0; t < 20; ++t) {
+      res_code[t] = pack_cstr(kResTypes[t].name);
+      const char* q = kResTypes[t].atoms;
+      while (*q) {
+        const char* sp = strchr(q, ' ');
+        const size_t m = sp ? static_cast<size_t>(sp - q) : strlen(q);
+        const uint32_t code = pack_field(q, m);
+        for (int i = 0; i < 37; ++i)
+          if (atom_code[i] == code) exists[t][i] = 1;
+        q += m + (sp ? 1 : 0);
+      }
+    }
+    exists[20][0] = exists[20][1] = exists[20][2] = exists[20][3] = 1;
   }
+};
+const Tables& tables() {
+  static const Tables t;
+  return t;
+}
+
+// the same for a fixed-column field, without allocating: atom37 names start with N, C, O or S, which rejects the
+// hydrogens (about half of the records of an all-atom file) on one character
+int atom_slot_field(const char* s, size_t n) {
+  const uint32_t code = pack_field(s, n);
+  const char c0 = static_cast<char>(code & 0xFF);
+  if (c0 != 'C' && c0 != 'N' && c0 != 'O' && c0 != 'S') return -1;
+  const uint32_t* t = tables().atom_code;
+  for (int i = 0; i < 37; ++i)
+    if (t[i] == code) return i;
   return -1;
 }
 
@@ -121,6 +156,44 @@ bool parse_float(const char* s, size_t n, float* out) {
   return true;
 }
 
+// residue id -> position in the residue list: open addressing in one allocation (an unordered_map costs a heap node per
+// residue, which is also where parser threads running side by side meet in the allocator)
+struct FlatIndex {
+  std::vector<unsigned long long> keys;
+  std::vector<int> vals;
+  size_t mask = 0, used = 0;
+  explicit FlatIndex(size_t expected) {
+    size_t cap = 64;
+    while (cap < expected * 2) cap <<= 1;
+    keys.assign(cap, ~0ull);  // ~0 is never a valid id (the hetero-kind field is at most 2)
+    vals.assign(cap, -1);
+    mask = cap - 1;
+  }
+  static size_t hash(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33;
+    return static_cast<size_t>(k);
+  }
+  int find(unsigned long long k) const {
+    for (size_t i = hash(k) & mask;; i = (i + 1) & mask) {
+      if (keys[i] == k) return vals[i];
+      if (keys[i] == ~0ull) return -1;
+    }
+  }
+  void insert(unsigned long long k, int v) {
+    if ((used + 1) * 2 > keys.size()) {
+      FlatIndex bigger(keys.size());
+      for (size_t i = 0; i < keys.size(); ++i)
+        if (keys[i] != ~0ull) bigger.insert(keys[i], vals[i]);
+      *this = std::move(bigger);
+    }
+    size_t i = hash(k) & mask;
+    while (keys[i] != ~0ull) i = (i + 1) & mask;
+    keys[i] = k;
+    vals[i] = v;
+    ++used;
+  }
+};
+
 struct Atom {
   float xyz[3];
   float occ;
@@ -128,7 +201,7 @@ struct Atom {
   bool set;
 };
 struct Residue {
-  std::string resname;
+  uint32_t resname;  // pack_field of columns [17:20]
   char chain, icode;
   int resseq;
   int chain_rank;
@@ -142,7 +215,8 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
   if (!text || !n_residues_out) return PST_ERR_BAD_ARGUMENT;
   *n_residues_out = 0;
   std::vector<Residue> residues;
-  std::unordered_map<unsigned long long, int> index;  // residue id -> position in `residues`
+  residues.reserve(len / 640 + 16);  // ~8 records of 81 bytes per residue in an all-atom file: no regrowth copies of the 750-byte entries
+  FlatIndex index(len / 640 + 16);   // residue id -> position in `residues`
   unsigned long long last_key = ~0ull;
   int last_idx = -1;
   std::string chain_order;
@@ -161,36 +235,43 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
     if (!is_atom && !is_het) continue;
     if (n < 54) return PST_ERR_PDB_MALFORMED;
     if (!in_model) loose_atoms = true;
-    const std::string resname = strip(line + 17, 3);
+    const uint32_t resname = pack_field(line + 17, 3);
     const char chain = line[21];
-    const std::string resseq_s = strip(line + 22, 4);
-    char* end = nullptr;
-    const long resseq = std::strtol(resseq_s.c_str(), &end, 10);
-    if (resseq_s.empty() || *end != '\0') return PST_ERR_PDB_MALFORMED;
+    long resseq = 0;
+    {  // int(line[22:26]): optional sign and decimal digits between blanks
+      size_t a = 22, b = 26;
+      while (a < b && line[a] == ' ') ++a;
+      while (b > a && line[b - 1] == ' ') --b;
+      bool neg = false;
+      if (a < b && (line[a] == '-' || line[a] == '+')) { neg = line[a] == '-'; ++a; }
+      if (a == b) return PST_ERR_PDB_MALFORMED;
+      for (; a < b; ++a) {
+        if (line[a] < '0' || line[a] > '9') return PST_ERR_PDB_MALFORMED;
+        resseq = resseq * 10 + (line[a] - '0');
+      }
+      if (neg) resseq = -resseq;
+    }
     const char icode = line[26];
     // residue id (chain, hetero flag, resseq, icode) packed into 64 bits: chain 8 | icode 8 | resseq + 2^15 16 |
     // hetero kind 2 (0 ATOM, 1 water, 2 other HETATM) | the 3 resname characters 24 (other HETATM only)
     unsigned long long key = ((unsigned long long)(unsigned char)chain << 56) | ((unsigned long long)(unsigned char)icode << 48) |
                              ((unsigned long long)(unsigned)(resseq + 32768) << 32);
     if (!is_atom) {
-      if (resname == "HOH" || resname == "WAT") key |= 1ull << 30;
-      else {
-        key |= 2ull << 30;
-        for (size_t i = 0; i < resname.size() && i < 3; ++i) key |= (unsigned long long)(unsigned char)resname[i] << (8 * i);
-      }
+      static const uint32_t kHoh = pack_cstr("HOH"), kWat = pack_cstr("WAT");
+      if (resname == kHoh || resname == kWat) key |= 1ull << 30;
+      else key |= (2ull << 30) | (resname & 0xFFFFFFu);
     }
     Residue* res;
     int found = -1;
     if (key == last_key) found = last_idx;
     else {
-      auto it = index.find(key);
-      if (it != index.end()) found = it->second;
+      found = index.find(key);
     }
     if (found < 0) {
       size_t rank = chain_order.find(chain);
       if (rank == std::string::npos) { rank = chain_order.size(); chain_order.push_back(chain); }
       found = static_cast<int>(residues.size());
-      index.emplace(key, found);
+      index.insert(key, found);
       residues.emplace_back();
       res = &residues.back();
       res->resname = resname;
@@ -206,10 +287,10 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
     last_idx = found;
     const int slot = atom_slot_field(line + 12, 4);
     if (slot < 0) continue;  // hydrogens and names outside atom37 are dropped
-    float occ = 1.0f;
-    if (n < 60 || !parse_float(line + 54, 6, &occ)) occ = 1.0f;
     const char altloc = line[16];
     Atom& a = res->atoms[slot];
+    float occ = 1.0f;  // only ever compared between two records that both carry an altloc
+    if (altloc != ' ' && (n < 60 || !parse_float(line + 54, 6, &occ))) occ = 1.0f;
     if (!a.set || (altloc != ' ' && a.altloc != ' ' && occ > a.occ)) {
       float x, y, z;
       if (!parse_float(line + 30, 8, &x) || !parse_float(line + 38, 8, &y) || !parse_float(line + 46, 8, &z)) return PST_ERR_PDB_MALFORMED;
@@ -232,9 +313,10 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
       for (int s = 0; s < 37; ++s) any = any || res.atoms[s].set;
       if (!any) continue;
       if (n_out < max_residues && atom37_positions && gt_exists && atom_exists && aatype) {
+        const Tables& T = tables();
         int rt = 20;
         for (int t = 0; t < 20; ++t)
-          if (res.resname == kResTypes[t].name) { rt = t; break; }
+          if (res.resname == T.res_code[t]) { rt = t; break; }
         float* p = atom37_positions + static_cast<size_t>(n_out) * 37 * 3;
         uint8_t* g = gt_exists + static_cast<size_t>(n_out) * 37;
         uint8_t* e = atom_exists + static_cast<size_t>(n_out) * 37;
@@ -244,20 +326,8 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
           p[s * 3 + 1] = a.set ? a.xyz[1] : 0.f;
           p[s * 3 + 2] = a.set ? a.xyz[2] : 0.f;
           g[s] = a.set ? 1 : 0;
-          e[s] = 0;
         }
-        if (rt == 20) {
-          e[0] = e[1] = e[2] = e[3] = 1;  // UNK: N, CA, C, CB
-        } else {
-          const char* q = kResTypes[rt].atoms;
-          while (*q) {
-            const char* sp = strchr(q, ' ');
-            const size_t m = sp ? static_cast<size_t>(sp - q) : strlen(q);
-            const int s = atom_slot(std::string(q, m));
-            if (s >= 0) e[s] = 1;
-            q += m + (sp ? 1 : 0);
-          }
-        }
+        memcpy(e, T.exists[rt], 37);
         aatype[n_out] = rt;
       }
       ++n_out;

@@ -155,16 +155,23 @@ class InferenceRunner:
         # Host pipeline around the device call: the next batch is read and parsed (C++ parser, the GIL is released
         # inside the ctypes call) and the previous batch's files are written while the GPU works on the current one.
         # Errors keep the reference's order: a batch's parse error is raised when that batch's turn comes.
+        # The files of one batch are parsed side by side (one C++ call per file, no GIL inside): a single parser thread
+        # delivers ~0.8 M residues/s, a B200 tokenizes 16 M/s.  `map` keeps the list order, so the first bad file of a
+        # batch, in list order, is still the one that raises.
+        n_parse = max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1),
+                             effective_batch_size))
+
         def load(it: int):
             files = pdbs[it * effective_batch_size : (it + 1) * effective_batch_size]
-            return files, [load_structure(f, data_config.graph_max_neighbor, data_config.seq_max_size) for f in files]
+            one = lambda f: load_structure(f, data_config.graph_max_neighbor, data_config.seq_max_size)  # noqa: E731
+            return files, list(parse_pool.map(one, files))
 
         def save(files, tokens):
             for f, tok in zip(files, tokens):
                 name = os.path.basename(f).split(".pdb")[0]
                 np.save(os.path.join(token_save_path, name + "_tokens"), np.asarray(tok, np.uint32).reshape(1, -1))
 
-        with ThreadPoolExecutor(max_workers=2) as pool:
+        with ThreadPoolExecutor(max_workers=2) as pool, ThreadPoolExecutor(max_workers=n_parse) as parse_pool:
             nxt = pool.submit(load, 0) if num_iteration else None
             pending_save = None
             for it in range(num_iteration):

@@ -97,3 +97,48 @@ def test_load_and_build_batch_pads_and_truncates(tmp_path):
     assert out.dtype == np.int32 and out.shape == (2, 7)
     assert out[0].tolist() == [0, 1, 2, 3, 4, 4097, 4097]
     assert out[1].tolist() == [100, 101, 102, 103, 104, 105, 106]
+
+
+def test_runner_host_pipeline_with_a_stand_in_callable(built_lib, tmp_path):
+    """InferenceRunner.tokenize's host side without a GPU: files are parsed side by side through the C ABI parser,
+    batches reach the callable in list order (the last one padded by cycling the list, scripts/inference_runner.py:
+    268-275), every structure's tokens land in `<stem>_tokens.npy` as uint32 (1, n), and the first bad file of a
+    batch, in list order, raises the reference's error."""
+    import types
+
+    import pytest
+    from pst import synthetic as syn
+    from pst.inference_runner import InferenceRunner
+    from test_pdb import _pdb_from_backbone
+
+    lengths = [60, 75, 52, 90, 66]
+    bbs = syn.make_backbones(17, lengths)
+    files = []
+    for i, bb in enumerate(bbs):
+        f = tmp_path / f"P{i}.pdb"
+        f.write_text(_pdb_from_backbone(bb))
+        files.append(str(f))
+    seen = []
+
+    def quantize(params, rng, batch):  # stands in for the device call: token t of a structure = its CA count + t
+        seen.append([a.shape[0] for a, _ in batch])
+        for a, m in batch:
+            assert a.shape[1:] == (37, 3) and a.dtype == np.float32 and m.shape == a.shape[:2]
+        return {"tokens": [np.arange(a.shape[0], dtype=np.int32) + a.shape[0] for a, _ in batch]}
+
+    data_cfg = types.SimpleNamespace(graph_max_neighbor=50, seq_max_size=512)
+    out = tmp_path / "tokens"
+    InferenceRunner.tokenize(None, quantize, None, files, str(out), 1, data_cfg, batch_size_per_device=2)
+    assert seen == [[60, 75], [52, 90], [66, 60]]  # 5 files, batches of 2: the list is cycled to fill the last batch
+    for i, n in enumerate(lengths):
+        t = np.load(out / f"P{i}_tokens.npy")
+        assert t.dtype == np.uint32 and t.shape == (1, n) and t[0, 0] == n and t[0, -1] == 2 * n - 1
+    # a too-short structure and an insertion code in the same batch: the one that comes first in the list raises
+    short = tmp_path / "short.pdb"
+    short.write_text(_pdb_from_backbone(bbs[0][:20]))
+    bad = tmp_path / "bad.pdb"
+    bad.write_text(_pdb_from_backbone(bbs[1]).replace(" A   7 ", " A   7B"))
+    with pytest.raises(NotImplementedError):
+        InferenceRunner.tokenize(None, quantize, None, [str(short), str(bad)], str(tmp_path / "o2"), 1, data_cfg, batch_size_per_device=2)
+    with pytest.raises(ValueError):
+        InferenceRunner.tokenize(None, quantize, None, [str(bad), str(short)], str(tmp_path / "o3"), 1, data_cfg, batch_size_per_device=2)
