@@ -176,6 +176,16 @@ int pst_graph_cache_enable(const pst_model* model, int enable);
 int pst_parse_pdb(const char* text, size_t text_bytes, int max_residues, float* atom37_positions,
                   uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out);
 
+/* HOST function: n_files PDB texts parsed side by side on up to n_threads host threads (<= 0: all hardware threads),
+ * the feeder in front of pst_tokenize (the reference parses one file at a time in Python,
+ * scripts/inference_runner.py:40-74 called from :288-296).  The output arrays are shared: file i's residues are rows
+ * residue_offsets_out[i] .. residue_offsets_out[i+1] (n_files + 1 entries); status_out[i] is PST_OK or that file's
+ * PST_ERR_PDB_* (it then contributes no rows).  Call with the array pointers NULL to get the offsets only.
+ * Returns PST_OK, PST_ERR_BAD_ARGUMENT or PST_ERR_WORKSPACE_TOO_SMALL (residue_offsets_out[n_files] rows are needed). */
+int pst_parse_pdb_batch(const char* const* texts, const size_t* text_bytes, int n_files, int n_threads,
+                        int max_residues_total, float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists,
+                        int32_t* aatype, int32_t* residue_offsets_out, int32_t* status_out);
+
 /* Device status word raised by kernels (0 = fine, PST_ERR_LENGTH_OUT_OF_RANGE ...).
  * Synchronises `stream`; not part of the hot path. */
 int pst_read_status(const pst_model* model, void* stream, void* workspace);

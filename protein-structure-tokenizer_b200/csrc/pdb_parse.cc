@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -208,13 +210,11 @@ struct Residue {
   Atom atoms[37];
 };
 
-}  // namespace
-
-extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, float* atom37_positions, uint8_t* gt_exists,
-                             uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out) {
-  if (!text || !n_residues_out) return PST_ERR_BAD_ARGUMENT;
-  *n_residues_out = 0;
-  std::vector<Residue> residues;
+// Phase 1: the records of one file -> `residues` (order of first appearance) and `order`, the positions of the residues
+// that are emitted, in output order (chains by first appearance, residues without a kept atom skipped).
+int parse_text(const char* text, size_t len, std::vector<Residue>& residues, std::vector<int>& order) {
+  residues.clear();
+  order.clear();
   residues.reserve(len / 640 + 16);  // ~8 records of 81 bytes per residue in an all-atom file: no regrowth copies of the 750-byte entries
   FlatIndex index(len / 640 + 16);   // residue id -> position in `residues`
   unsigned long long last_key = ~0ull;
@@ -302,38 +302,97 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
   }
   const int n_models = models > 0 ? models : (loose_atoms ? 1 : 0);
   if (n_models != 1) return PST_ERR_PDB_MODEL_COUNT;
-
-  int n_out = 0;
   const int n_chains = static_cast<int>(chain_order.size());
   for (int c = 0; c < n_chains; ++c) {
-    for (const Residue& res : residues) {
+    for (size_t r = 0; r < residues.size(); ++r) {
+      const Residue& res = residues[r];
       if (res.chain_rank != c) continue;
       if (res.icode != ' ') return PST_ERR_PDB_INSERTION_CODE;
       bool any = false;
       for (int s = 0; s < 37; ++s) any = any || res.atoms[s].set;
-      if (!any) continue;
-      if (n_out < max_residues && atom37_positions && gt_exists && atom_exists && aatype) {
-        const Tables& T = tables();
-        int rt = 20;
-        for (int t = 0; t < 20; ++t)
-          if (res.resname == T.res_code[t]) { rt = t; break; }
-        float* p = atom37_positions + static_cast<size_t>(n_out) * 37 * 3;
-        uint8_t* g = gt_exists + static_cast<size_t>(n_out) * 37;
-        uint8_t* e = atom_exists + static_cast<size_t>(n_out) * 37;
-        for (int s = 0; s < 37; ++s) {
-          const Atom& a = res.atoms[s];
-          p[s * 3] = a.set ? a.xyz[0] : 0.f;
-          p[s * 3 + 1] = a.set ? a.xyz[1] : 0.f;
-          p[s * 3 + 2] = a.set ? a.xyz[2] : 0.f;
-          g[s] = a.set ? 1 : 0;
-        }
-        memcpy(e, T.exists[rt], 37);
-        aatype[n_out] = rt;
-      }
-      ++n_out;
+      if (any) order.push_back(static_cast<int>(r));
     }
   }
+  return PST_OK;
+}
+
+// Phase 2: one residue -> row `row` of the caller's arrays
+void emit_residue(const Residue& res, size_t row, float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype) {
+  const Tables& T = tables();
+  int rt = 20;
+  for (int t = 0; t < 20; ++t)
+    if (res.resname == T.res_code[t]) { rt = t; break; }
+  float* p = atom37_positions + row * 37 * 3;
+  uint8_t* g = gt_exists + row * 37;
+  for (int s = 0; s < 37; ++s) {
+    const Atom& a = res.atoms[s];
+    p[s * 3] = a.set ? a.xyz[0] : 0.f;
+    p[s * 3 + 1] = a.set ? a.xyz[1] : 0.f;
+    p[s * 3 + 2] = a.set ? a.xyz[2] : 0.f;
+    g[s] = a.set ? 1 : 0;
+  }
+  memcpy(atom_exists + row * 37, T.exists[rt], 37);
+  aatype[row] = rt;
+}
+
+}  // namespace
+
+extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, float* atom37_positions, uint8_t* gt_exists,
+                             uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out) {
+  if (!text || !n_residues_out) return PST_ERR_BAD_ARGUMENT;
+  *n_residues_out = 0;
+  std::vector<Residue> residues;
+  std::vector<int> order;
+  const int rc = parse_text(text, len, residues, order);
+  if (rc != PST_OK) return rc;
+  const int n_out = static_cast<int>(order.size());
   *n_residues_out = n_out;
-  if (atom37_positions && n_out > max_residues) return PST_ERR_WORKSPACE_TOO_SMALL;
+  if (!(atom37_positions && gt_exists && atom_exists && aatype)) return PST_OK;
+  const int n_emit = n_out < max_residues ? n_out : (max_residues > 0 ? max_residues : 0);
+  for (int i = 0; i < n_emit; ++i) emit_residue(residues[order[i]], static_cast<size_t>(i), atom37_positions, gt_exists, atom_exists, aatype);
+  return n_out > max_residues ? PST_ERR_WORKSPACE_TOO_SMALL : PST_OK;
+}
+
+// Many files side by side on host threads (the feeder).  Each worker parses whole files into
+// its own residue lists (phase 1), the residue counts are prefix-summed, then the workers write the rows (phase 2).
+extern "C" int pst_parse_pdb_batch(const char* const* texts, const size_t* text_bytes, int n_files, int n_threads,
+                                   int max_residues_total, float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists,
+                                   int32_t* aatype, int32_t* residue_offsets_out, int32_t* status_out) {
+  if (n_files < 0 || !residue_offsets_out || !status_out || (n_files > 0 && (!texts || !text_bytes))) return PST_ERR_BAD_ARGUMENT;
+  residue_offsets_out[0] = 0;
+  if (n_files == 0) return PST_OK;
+  if (n_threads <= 0) n_threads = static_cast<int>(std::thread::hardware_concurrency());
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n_files) n_threads = n_files;
+  std::vector<std::vector<Residue>> residues(n_files);
+  std::vector<std::vector<int>> order(n_files);
+  std::atomic<int> next{0};
+  auto run = [&](auto&& body) {
+    next.store(0);
+    auto worker = [&]() {
+      for (int i = next.fetch_add(1); i < n_files; i = next.fetch_add(1)) body(i);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread& t : pool) t.join();
+  };
+  run([&](int i) {
+    status_out[i] = texts[i] ? parse_text(texts[i], text_bytes[i], residues[i], order[i]) : static_cast<int>(PST_ERR_BAD_ARGUMENT);
+    if (status_out[i] != PST_OK) order[i].clear();
+  });
+  long long total = 0;
+  for (int i = 0; i < n_files; ++i) {
+    total += static_cast<long long>(order[i].size());
+    if (total > 0x7fffffffLL) return PST_ERR_BAD_ARGUMENT;
+    residue_offsets_out[i + 1] = static_cast<int32_t>(total);
+  }
+  if (!(atom37_positions && gt_exists && atom_exists && aatype)) return PST_OK;  // counts only
+  if (total > max_residues_total) return PST_ERR_WORKSPACE_TOO_SMALL;
+  run([&](int i) {
+    const size_t base = static_cast<size_t>(residue_offsets_out[i]);
+    for (size_t k = 0; k < order[i].size(); ++k)
+      emit_residue(residues[i][order[i][k]], base + k, atom37_positions, gt_exists, atom_exists, aatype);
+  });
   return PST_OK;
 }

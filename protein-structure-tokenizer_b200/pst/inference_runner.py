@@ -30,6 +30,7 @@ import numpy as np
 
 from .config import TokenizerConfig
 from .pdb import structure_from_pdb_file_native as structure_from_pdb_file  # C++ parser behind the C ABI (pst_parse_pdb)
+from .pdb import structures_from_pdb_files_native as structures_from_pdb_files  # pst_parse_pdb_batch
 from .weights import init_params, load_params_npz
 
 
@@ -37,7 +38,22 @@ def load_structure(pdb_file_path: str, num_neighbor: int, padding_num_residue: i
     """Counterpart of make_graph_from_pdb's host part: parse + length guards.  Note the reference checks
     nb_residues *before* dropping incomplete residues (scripts/inference_runner.py:52-62); the device path
     additionally needs n_valid >= num_neighbor, which the tokenizer re-checks."""
-    sample = structure_from_pdb_file(pdb_file_path)
+    return _guard_lengths(structure_from_pdb_file(pdb_file_path), num_neighbor, padding_num_residue)
+
+
+def load_structures(pdb_file_paths: Sequence[str], num_neighbor: int, padding_num_residue: int, n_threads: int = 0):
+    """`load_structure` for a batch of files: ONE call into the library parses them side by side on host threads
+    (`pst_parse_pdb_batch`: no GIL, no Python work per file while it runs).  The first bad file in list order raises,
+    as a loop over `load_structure` would."""
+    out = []
+    for sample in structures_from_pdb_files(pdb_file_paths, n_threads):
+        if isinstance(sample, Exception):
+            raise sample
+        out.append(_guard_lengths(sample, num_neighbor, padding_num_residue))
+    return out
+
+
+def _guard_lengths(sample, num_neighbor: int, padding_num_residue: int):
     if sample.nb_residues > padding_num_residue:
         raise NotImplementedError(
             f"We currently don't support protein with more than {padding_num_residue} residues"
@@ -155,23 +171,22 @@ class InferenceRunner:
         # Host pipeline around the device call: the next batch is read and parsed (C++ parser, the GIL is released
         # inside the ctypes call) and the previous batch's files are written while the GPU works on the current one.
         # Errors keep the reference's order: a batch's parse error is raised when that batch's turn comes.
-        # The files of one batch are parsed side by side (one C++ call per file, no GIL inside): a single parser thread
-        # delivers ~0.8 M residues/s, a B200 tokenizes 16 M/s.  `map` keeps the list order, so the first bad file of a
+        # The files of one batch are parsed side by side inside ONE library call (pst_parse_pdb_batch, host threads, no
+        # GIL): a single parser thread delivers ~0.8 M residues/s, a B200 tokenizes 16 M/s.  The first bad file of a
         # batch, in list order, is still the one that raises.
         n_parse = max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1),
                              effective_batch_size))
 
         def load(it: int):
             files = pdbs[it * effective_batch_size : (it + 1) * effective_batch_size]
-            one = lambda f: load_structure(f, data_config.graph_max_neighbor, data_config.seq_max_size)  # noqa: E731
-            return files, list(parse_pool.map(one, files))
+            return files, load_structures(files, data_config.graph_max_neighbor, data_config.seq_max_size, n_parse)
 
         def save(files, tokens):
             for f, tok in zip(files, tokens):
                 name = os.path.basename(f).split(".pdb")[0]
                 np.save(os.path.join(token_save_path, name + "_tokens"), np.asarray(tok, np.uint32).reshape(1, -1))
 
-        with ThreadPoolExecutor(max_workers=2) as pool, ThreadPoolExecutor(max_workers=n_parse) as parse_pool:
+        with ThreadPoolExecutor(max_workers=2) as pool:
             nxt = pool.submit(load, 0) if num_iteration else None
             pending_save = None
             for it in range(num_iteration):

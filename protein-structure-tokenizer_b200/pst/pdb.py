@@ -10,6 +10,7 @@ Also the residue filter of data/preprocessing.py:72,99-117 (`valid_backbone`).
 """
 from __future__ import annotations
 
+import threading
 from typing import Dict, List, NamedTuple, Tuple
 
 import numpy as np
@@ -147,6 +148,9 @@ def structure_from_pdb_file(path: str) -> StructureSample:
         return structure_from_pdb_string(fh.read())
 
 
+_scratch = threading.local()
+
+
 def structure_from_pdb_bytes_native(data: bytes) -> StructureSample:
     """The same result through the C++ parser of the C ABI (`pst_parse_pdb`, csrc/pdb_parse.cc): ~100x faster than
     the pure-Python loop above, which is kept as an independent restatement for the tests.  Raises ValueError where
@@ -157,13 +161,20 @@ def structure_from_pdb_bytes_native(data: bytes) -> StructureSample:
 
     lib = _lib.load()
     n = C.c_int32(0)
-    cap = max(1, data.count(b" CA ") + 8)  # one CA per residue, plus slack for CA-less residues
+    # Per-thread scratch arrays, grown on demand and reused from file to file (the runner parses files side by side:
+    # fresh multi-hundred-KB arrays per file are mmap'ed and page-faulted every time, which serialises the threads in the
+    # kernel), no scan of the text in Python (the GIL is only released inside the C call): capacity guess = one
+    # residue per four 81-byte records, the exact count on the rare retry.
+    cap = len(data) // 324 + 16
     while True:
-        pos = np.zeros((cap, 37, 3), np.float32)
-        gt = np.zeros((cap, 37), np.uint8)
-        ex = np.zeros((cap, 37), np.uint8)
-        aa = np.zeros((cap,), np.int32)
-        rc = lib.pst_parse_pdb(data, len(data), cap, pos.ctypes.data, gt.ctypes.data, ex.ctypes.data, aa.ctypes.data, C.byref(n))
+        sc = getattr(_scratch, "arrays", None)
+        if sc is None or sc[0].shape[0] < cap:
+            grow = max(cap, 1024)
+            sc = _scratch.arrays = (np.empty((grow, 37, 3), np.float32), np.empty((grow, 37), np.uint8),
+                                    np.empty((grow, 37), np.uint8), np.empty((grow,), np.int32))
+        pos, gt, ex, aa = sc
+        rc = lib.pst_parse_pdb(data, len(data), pos.shape[0], pos.ctypes.data, gt.ctypes.data, ex.ctypes.data, aa.ctypes.data,
+                               C.byref(n))
         if rc == _lib.PST_ERR_WORKSPACE_TOO_SMALL:
             cap = int(n.value)
             continue
@@ -173,9 +184,60 @@ def structure_from_pdb_bytes_native(data: bytes) -> StructureSample:
     _lib.check(rc, "pst_parse_pdb")
     k = int(n.value)
     return StructureSample(nb_residues=k, aatype=aa[:k].copy(), atom37_positions=pos[:k].copy(),
-                           atom37_gt_exists=gt[:k].astype(bool), atom37_atom_exists=ex[:k].astype(bool))
+                           atom37_gt_exists=gt[:k].astype(np.bool_), atom37_atom_exists=ex[:k].astype(np.bool_))
 
 
 def structure_from_pdb_file_native(path: str) -> StructureSample:
     with open(path, "rb") as fh:
         return structure_from_pdb_bytes_native(fh.read())
+
+
+def structures_from_pdb_bytes_batch_native(datas, n_threads: int = 0):
+    """Many PDB texts through ONE C call (`pst_parse_pdb_batch`: host threads inside the library, no GIL, no Python
+    work per file while they run).  Returns a list with a StructureSample per text, or the ValueError the reference
+    would raise for that file (not raised here: the caller decides which file's error comes first)."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    nf = len(datas)
+    if nf == 0:
+        return []
+    texts = (C.c_char_p * nf)(*datas)
+    sizes = (C.c_size_t * nf)(*[len(d) for d in datas])
+    offs = np.zeros(nf + 1, np.int32)
+    status = np.zeros(nf, np.int32)
+    cap = sum(len(d) for d in datas) // 324 + 16 * nf
+    while True:
+        pos = np.empty((cap, 37, 3), np.float32)
+        gt = np.empty((cap, 37), np.uint8)
+        ex = np.empty((cap, 37), np.uint8)
+        aa = np.empty((cap,), np.int32)
+        rc = lib.pst_parse_pdb_batch(texts, sizes, nf, int(n_threads), cap, pos.ctypes.data, gt.ctypes.data, ex.ctypes.data,
+                                     aa.ctypes.data, offs.ctypes.data, status.ctypes.data)
+        if rc == _lib.PST_ERR_WORKSPACE_TOO_SMALL:
+            cap = int(offs[nf])
+            continue
+        break
+    _lib.check(rc, "pst_parse_pdb_batch")
+    gtb, exb = gt.view(np.bool_), ex.view(np.bool_)
+    out = []
+    for i in range(nf):
+        st = int(status[i])
+        if st in (_lib.PST_ERR_PDB_MODEL_COUNT, _lib.PST_ERR_PDB_INSERTION_CODE, _lib.PST_ERR_PDB_MALFORMED):
+            out.append(ValueError(lib.pst_status_string(st).decode()))
+            continue
+        _lib.check(st, "pst_parse_pdb_batch")
+        a, b = int(offs[i]), int(offs[i + 1])
+        out.append(StructureSample(nb_residues=b - a, aatype=aa[a:b], atom37_positions=pos[a:b],
+                                   atom37_gt_exists=gtb[a:b], atom37_atom_exists=exb[a:b]))
+    return out
+
+
+def structures_from_pdb_files_native(paths, n_threads: int = 0):
+    datas = []
+    for path in paths:
+        with open(path, "rb") as fh:
+            datas.append(fh.read())
+    return structures_from_pdb_bytes_batch_native(datas, n_threads)

@@ -175,3 +175,55 @@ def test_native_parser_on_the_bundled_pdb_files(built_lib):
         with open(f, "rb") as fh:
             data = fh.read()
         _same_samples(ppdb.structure_from_pdb_bytes_native(data), ppdb.structure_from_pdb_string(data.decode()))
+
+
+def test_batch_parser_equals_the_single_file_parser(built_lib, tmp_path):
+    """pst_parse_pdb_batch (host threads inside the library): every file's rows equal the single-file call, a bad file
+    reports its own status without disturbing its neighbours, and the capacity retry / counts-only modes work."""
+    import ctypes as C
+
+    from pst import _lib
+    from pst import synthetic as syn
+
+    bbs = syn.make_backbones(23, [60, 131, 77, 52, 300, 64, 90])
+    texts = [_pdb_from_backbone(bb, resname=rn) for bb, rn in zip(bbs, ("GLY", "ALA", "TRP", "XYZ", "SER", "LYS", "VAL"))]
+    texts.insert(2, _tricky_text())
+    ok = [_atom(1, "N", "GLY", "A", 1, (0, 0, 0)), _atom(2, "CA", "GLY", "A", 1, (1, 0, 0))]
+    texts.insert(4, "\n".join(ok + [_atom(3, "N", "GLY", "A", 2, (3, 0, 0), icode="A")]))  # insertion code
+    texts.insert(6, "REMARK nothing here\nEND\n")                                            # no model
+    datas = [t.encode() for t in texts]
+    for n_threads in (1, 4, 0):
+        out = ppdb.structures_from_pdb_bytes_batch_native(datas, n_threads)
+        assert len(out) == len(datas)
+        for i, (d, o) in enumerate(zip(datas, out)):
+            if i in (4, 6):
+                assert isinstance(o, ValueError) and ("insertion code" in str(o) if i == 4 else "single model" in str(o))
+            else:
+                _same_samples(o, ppdb.structure_from_pdb_bytes_native(d))
+    # the C entry point itself: counts only, then a capacity that is too small
+    lib = _lib.load()
+    nf = len(datas)
+    arr = (C.c_char_p * nf)(*datas)
+    sizes = (C.c_size_t * nf)(*[len(d) for d in datas])
+    offs = np.zeros(nf + 1, np.int32)
+    status = np.zeros(nf, np.int32)
+    assert lib.pst_parse_pdb_batch(arr, sizes, nf, 3, 0, None, None, None, None, offs.ctypes.data, status.ctypes.data) == 0
+    good = [o for o in ppdb.structures_from_pdb_bytes_batch_native(datas, 2) if not isinstance(o, Exception)]
+    assert offs[-1] == sum(o.nb_residues for o in good) and list(status[[4, 6]]) == [-9, -8]
+    total = int(offs[-1])
+    pos = np.empty((total - 1, 37, 3), np.float32)
+    gt = np.empty((total - 1, 37), np.uint8)
+    ex = np.empty((total - 1, 37), np.uint8)
+    aa = np.empty((total - 1,), np.int32)
+    rc = lib.pst_parse_pdb_batch(arr, sizes, nf, 3, total - 1, pos.ctypes.data, gt.ctypes.data, ex.ctypes.data, aa.ctypes.data,
+                                 offs.ctypes.data, status.ctypes.data)
+    assert rc == -4 and offs[-1] == total  # PST_ERR_WORKSPACE_TOO_SMALL, rows needed
+    assert ppdb.structures_from_pdb_bytes_batch_native([], 4) == []
+    # files on disk through the runner's helper
+    paths = []
+    for i in (0, 1, 3):
+        f = tmp_path / f"f{i}.pdb"
+        f.write_bytes(datas[i])
+        paths.append(str(f))
+    for o, i in zip(ppdb.structures_from_pdb_files_native(paths, 2), (0, 1, 3)):
+        _same_samples(o, ppdb.structure_from_pdb_bytes_native(datas[i]))
