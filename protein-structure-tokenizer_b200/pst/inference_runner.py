@@ -30,6 +30,7 @@ import numpy as np
 
 from .config import TokenizerConfig
 from .pdb import structure_from_pdb_file_native as structure_from_pdb_file  # C++ parser behind the C ABI (pst_parse_pdb)
+from .pdb import structure_from_sample_file
 from .pdb import structures_from_pdb_files_native as structures_from_pdb_files  # pst_parse_pdb_batch
 from .weights import init_params, load_params_npz
 
@@ -44,9 +45,14 @@ def load_structure(pdb_file_path: str, num_neighbor: int, padding_num_residue: i
 def load_structures(pdb_file_paths: Sequence[str], num_neighbor: int, padding_num_residue: int, n_threads: int = 0):
     """`load_structure` for a batch of files: ONE call into the library parses them side by side on host threads
     (`pst_parse_pdb_batch`: no GIL, no Python work per file while it runs).  The first bad file in list order raises,
-    as a loop over `load_structure` would."""
+    as a loop over `load_structure` would.  Paths ending in .npy are read as the reference's preprocessed
+    `ProteinStructureSample` files (data/protein_structure_sample.py:46-54) instead of being parsed."""
+    paths = list(pdb_file_paths)
+    is_npy = [p.endswith(".npy") for p in paths]  # preprocessed ProteinStructureSample files need no parsing
+    parsed = iter(structures_from_pdb_files([p for p, s in zip(paths, is_npy) if not s], n_threads))
     out = []
-    for sample in structures_from_pdb_files(pdb_file_paths, n_threads):
+    for path, npy in zip(paths, is_npy):
+        sample = structure_from_sample_file(path) if npy else next(parsed)
         if isinstance(sample, Exception):
             raise sample
         out.append(_guard_lengths(sample, num_neighbor, padding_num_residue))
@@ -183,7 +189,9 @@ class InferenceRunner:
 
         def save(files, tokens):
             for f, tok in zip(files, tokens):
-                name = os.path.basename(f).split(".pdb")[0]
+                name = os.path.basename(f).split(".pdb")[0]  # scripts/inference_runner.py:316
+                if name.endswith(".npy"):
+                    name = name[: -len(".npy")]
                 np.save(os.path.join(token_save_path, name + "_tokens"), np.asarray(tok, np.uint32).reshape(1, -1))
 
         with ThreadPoolExecutor(max_workers=2) as pool:

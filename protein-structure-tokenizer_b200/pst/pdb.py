@@ -241,3 +241,40 @@ def structures_from_pdb_files_native(paths, n_threads: int = 0):
         with open(path, "rb") as fh:
             datas.append(fh.read())
     return structures_from_pdb_bytes_batch_native(datas, n_threads)
+
+
+def structure_from_sample_file(path: str) -> StructureSample:
+    """The reference's preprocessed sample format: `ProteinStructureSample.to_file` / `.from_file`
+    (structure_tokenizer/data/protein_structure_sample.py:46-62), an .npy holding the pickled dict of the NamedTuple
+    (chain_id, nb_residues, aatype one-hot bool [n, 21], atom37_positions f32 [n, 37, 3], atom37_gt_exists /
+    atom37_atom_exists bool [n, 37], resolution, pdb_cluster_size).  444 bytes per residue instead of ~700 bytes of PDB
+    text and no parsing: the ingest format for large runs (data/test_data/cif_raw_data.npy is the bundled example)."""
+    import os
+
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"{path} does not exist")
+    with open(path, "rb") as fh:
+        d = np.load(fh, allow_pickle=True)[()]
+    n = int(d["nb_residues"])
+    aatype = np.asarray(d["aatype"])
+    if aatype.ndim == 2:  # one-hot over the 20 residue types + unknown
+        aatype = aatype.argmax(axis=-1)
+    pos = np.ascontiguousarray(d["atom37_positions"], np.float32)
+    gt = np.ascontiguousarray(d["atom37_gt_exists"], np.bool_)
+    ex = np.ascontiguousarray(d["atom37_atom_exists"], np.bool_)
+    if pos.shape != (n, 37, 3) or gt.shape != (n, 37) or ex.shape != (n, 37) or aatype.shape != (n,):
+        raise ValueError(f"{path}: arrays do not match nb_residues = {n}")
+    return StructureSample(nb_residues=n, aatype=aatype.astype(np.int32), atom37_positions=pos, atom37_gt_exists=gt,
+                           atom37_atom_exists=ex)
+
+
+def structure_to_sample_file(sample: StructureSample, path: str, chain_id: str = "", resolution: float = 0.0,
+                             pdb_cluster_size: int = 1) -> None:
+    """Writes what `ProteinStructureSample.from_file` of the reference reads back (protein_structure_sample.py:46-62)."""
+    onehot = np.zeros((sample.nb_residues, 21), np.bool_)
+    onehot[np.arange(sample.nb_residues), np.asarray(sample.aatype, np.int64)] = True
+    np.save(path, {"chain_id": chain_id, "nb_residues": int(sample.nb_residues), "aatype": onehot,
+                   "atom37_positions": np.asarray(sample.atom37_positions, np.float32),
+                   "atom37_gt_exists": np.asarray(sample.atom37_gt_exists, np.bool_),
+                   "atom37_atom_exists": np.asarray(sample.atom37_atom_exists, np.bool_),
+                   "resolution": float(resolution), "pdb_cluster_size": int(pdb_cluster_size)})

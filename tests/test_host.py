@@ -142,3 +142,53 @@ def test_runner_host_pipeline_with_a_stand_in_callable(built_lib, tmp_path):
         InferenceRunner.tokenize(None, quantize, None, [str(short), str(bad)], str(tmp_path / "o2"), 1, data_cfg, batch_size_per_device=2)
     with pytest.raises(ValueError):
         InferenceRunner.tokenize(None, quantize, None, [str(bad), str(short)], str(tmp_path / "o3"), 1, data_cfg, batch_size_per_device=2)
+
+
+def test_preprocessed_sample_files_round_trip_and_feed_the_runner(built_lib, tmp_path):
+    """ProteinStructureSample .npy files (structure_tokenizer/data/protein_structure_sample.py:46-62): written and read
+    back bit for bit, equal to what the PDB parser produces for the same structure, accepted by the runner next to PDB
+    files, and the reference's bundled example parses when the checkout is there."""
+    import os
+    import types
+
+    from pst import pdb as ppdb
+    from pst import synthetic as syn
+    from pst.inference_runner import InferenceRunner, load_structures
+    from test_pdb import _pdb_from_backbone
+
+    bbs = syn.make_backbones(29, [64, 80])
+    texts = [_pdb_from_backbone(bb, resname=rn) for bb, rn in zip(bbs, ("ALA", "XYZ"))]
+    paths = []
+    for i, t in enumerate(texts):
+        s = ppdb.structure_from_pdb_bytes_native(t.encode())
+        f = str(tmp_path / f"S{i}.npy")
+        ppdb.structure_to_sample_file(s, f, chain_id=f"S{i}")
+        r = ppdb.structure_from_sample_file(f)
+        assert r.nb_residues == s.nb_residues and np.array_equal(r.aatype, s.aatype)
+        assert np.array_equal(r.atom37_positions, s.atom37_positions)
+        assert np.array_equal(r.atom37_gt_exists, s.atom37_gt_exists) and np.array_equal(r.atom37_atom_exists, s.atom37_atom_exists)
+        d = np.load(f, allow_pickle=True)[()]  # the reference's `cls(**dict_representation)` needs exactly these keys
+        assert sorted(d) == sorted(["chain_id", "nb_residues", "aatype", "atom37_positions", "atom37_gt_exists",
+                                    "atom37_atom_exists", "resolution", "pdb_cluster_size"])
+        assert d["aatype"].shape == (s.nb_residues, 21) and d["aatype"].dtype == np.bool_
+        paths.append(f)
+    pdb_path = tmp_path / "S1.pdb"
+    pdb_path.write_text(texts[1])
+    mixed = load_structures([paths[0], str(pdb_path), paths[1]], 50, 512, 2)
+    assert np.array_equal(mixed[1][0], mixed[2][0]) and np.array_equal(mixed[1][1], mixed[2][1])
+    seen = []
+
+    def quantize(params, rng, batch):
+        seen.append([a.shape[0] for a, _ in batch])
+        return {"tokens": [np.zeros(a.shape[0], np.int32) for a, _ in batch]}
+
+    out = tmp_path / "tok"
+    InferenceRunner.tokenize(None, quantize, None, [paths[0], str(pdb_path)], str(out), 1,
+                             types.SimpleNamespace(graph_max_neighbor=50, seq_max_size=512), batch_size_per_device=2)
+    assert seen == [[64, 80]] and sorted(os.listdir(out)) == ["S0_tokens.npy", "S1_tokens.npy"]
+    with pytest.raises(FileNotFoundError):
+        ppdb.structure_from_sample_file(str(tmp_path / "missing.npy"))
+    ref = "/root/reference/structure_tokenizer/data/test_data/cif_raw_data.npy"
+    if os.path.isfile(ref):
+        s = ppdb.structure_from_sample_file(ref)
+        assert s.nb_residues == 123 and s.atom37_positions.shape == (123, 37, 3) and s.valid_backbone().sum() >= 50
