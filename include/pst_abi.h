@@ -55,7 +55,8 @@ typedef enum pst_status {
   PST_ERR_BAD_WEIGHTS = -7,
   PST_ERR_PDB_MODEL_COUNT = -8,     /* the file does not hold exactly one model */
   PST_ERR_PDB_INSERTION_CODE = -9,  /* a residue carries an insertion code */
-  PST_ERR_PDB_MALFORMED = -10       /* an ATOM / HETATM record is too short or has non-numeric fields */
+  PST_ERR_PDB_MALFORMED = -10,      /* an ATOM / HETATM record is too short or has non-numeric fields */
+  PST_ERR_FILE_NOT_FOUND = -11      /* pst_parse_pdb_files: the path could not be opened */
 } pst_status;
 
 /* GEMM operand precision of the edge-level MLPs (accumulation is always fp32;
@@ -185,6 +186,12 @@ int pst_parse_pdb(const char* text, size_t text_bytes, int max_residues, float* 
 int pst_parse_pdb_batch(const char* const* texts, const size_t* text_bytes, int n_files, int n_threads,
                         int max_residues_total, float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists,
                         int32_t* aatype, int32_t* residue_offsets_out, int32_t* status_out);
+
+/* The same over files: the worker threads read paths[i] themselves (a PST_ERR_WORKSPACE_TOO_SMALL retry reads
+ * and parses the files again).  status_out[i] may also be PST_ERR_FILE_NOT_FOUND. */
+int pst_parse_pdb_files(const char* const* paths, int n_files, int n_threads, int max_residues_total,
+                        float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype,
+                        int32_t* residue_offsets_out, int32_t* status_out);
 
 /* Device status word raised by kernels (0 = fine, PST_ERR_LENGTH_OUT_OF_RANGE ...).
  * Synchronises `stream`; not part of the hot path. */

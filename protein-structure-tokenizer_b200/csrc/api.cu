@@ -195,6 +195,7 @@ const char* pst_status_string(int status) {
     case PST_ERR_PDB_MODEL_COUNT: return "Only single model PDBs are supported";
     case PST_ERR_PDB_INSERTION_CODE: return "PDB contains an insertion code; these are not supported";
     case PST_ERR_PDB_MALFORMED: return "malformed ATOM / HETATM record";
+    case PST_ERR_FILE_NOT_FOUND: return "file could not be opened";
     default: return "unknown status";
   }
 }

@@ -15,6 +15,7 @@
 //     selected child), a blank-altloc duplicate keeps the first record;
 //   * unknown residue names -> UNK (aatype 20; expected atoms N, CA, C, CB) (:211-215, residue_constants.py:733-737);
 //   * residues without any kept atom are skipped (:228-230); coordinates are float32 (:216).
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -355,10 +356,14 @@ extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, flo
 
 // Many files side by side on host threads (the feeder).  Each worker parses whole files into
 // its own residue lists (phase 1), the residue counts are prefix-summed, then the workers write the rows (phase 2).
-extern "C" int pst_parse_pdb_batch(const char* const* texts, const size_t* text_bytes, int n_files, int n_threads,
-                                   int max_residues_total, float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists,
-                                   int32_t* aatype, int32_t* residue_offsets_out, int32_t* status_out) {
-  if (n_files < 0 || !residue_offsets_out || !status_out || (n_files > 0 && (!texts || !text_bytes))) return PST_ERR_BAD_ARGUMENT;
+// `paths` != nullptr: the workers also read the files (one fread per file), texts / text_bytes are ignored.
+namespace {
+
+int parse_batch(const char* const* texts, const size_t* text_bytes, const char* const* paths, int n_files, int n_threads,
+                int max_residues_total, float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype,
+                int32_t* residue_offsets_out, int32_t* status_out) {
+  if (n_files < 0 || !residue_offsets_out || !status_out) return PST_ERR_BAD_ARGUMENT;
+  if (n_files > 0 && !paths && (!texts || !text_bytes)) return PST_ERR_BAD_ARGUMENT;
   residue_offsets_out[0] = 0;
   if (n_files == 0) return PST_OK;
   if (n_threads <= 0) n_threads = static_cast<int>(std::thread::hardware_concurrency());
@@ -370,15 +375,37 @@ extern "C" int pst_parse_pdb_batch(const char* const* texts, const size_t* text_
   auto run = [&](auto&& body) {
     next.store(0);
     auto worker = [&]() {
-      for (int i = next.fetch_add(1); i < n_files; i = next.fetch_add(1)) body(i);
+      std::string file;  // reused from file to file by this worker
+      for (int i = next.fetch_add(1); i < n_files; i = next.fetch_add(1)) body(i, file);
     };
     std::vector<std::thread> pool;
     for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
     worker();
     for (std::thread& t : pool) t.join();
   };
-  run([&](int i) {
-    status_out[i] = texts[i] ? parse_text(texts[i], text_bytes[i], residues[i], order[i]) : static_cast<int>(PST_ERR_BAD_ARGUMENT);
+  run([&](int i, std::string& file) {
+    const char* text = nullptr;
+    size_t len = 0;
+    int rc = PST_OK;
+    if (paths) {
+      FILE* fh = paths[i] ? fopen(paths[i], "rb") : nullptr;
+      if (!fh) rc = PST_ERR_FILE_NOT_FOUND;
+      else {
+        file.clear();
+        char buf[1 << 16];
+        size_t got;
+        while ((got = fread(buf, 1, sizeof buf, fh)) > 0) file.append(buf, got);
+        fclose(fh);
+        text = file.data();
+        len = file.size();
+      }
+    } else if (!texts[i]) {
+      rc = PST_ERR_BAD_ARGUMENT;
+    } else {
+      text = texts[i];
+      len = text_bytes[i];
+    }
+    status_out[i] = rc == PST_OK ? parse_text(text, len, residues[i], order[i]) : rc;
     if (status_out[i] != PST_OK) order[i].clear();
   });
   long long total = 0;
@@ -389,10 +416,27 @@ extern "C" int pst_parse_pdb_batch(const char* const* texts, const size_t* text_
   }
   if (!(atom37_positions && gt_exists && atom_exists && aatype)) return PST_OK;  // counts only
   if (total > max_residues_total) return PST_ERR_WORKSPACE_TOO_SMALL;
-  run([&](int i) {
+  run([&](int i, std::string&) {
     const size_t base = static_cast<size_t>(residue_offsets_out[i]);
     for (size_t k = 0; k < order[i].size(); ++k)
       emit_residue(residues[i][order[i][k]], base + k, atom37_positions, gt_exists, atom_exists, aatype);
   });
   return PST_OK;
+}
+
+}  // namespace
+
+extern "C" int pst_parse_pdb_batch(const char* const* texts, const size_t* text_bytes, int n_files, int n_threads,
+                                   int max_residues_total, float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists,
+                                   int32_t* aatype, int32_t* residue_offsets_out, int32_t* status_out) {
+  return parse_batch(texts, text_bytes, nullptr, n_files, n_threads, max_residues_total, atom37_positions, gt_exists, atom_exists,
+                     aatype, residue_offsets_out, status_out);
+}
+
+extern "C" int pst_parse_pdb_files(const char* const* paths, int n_files, int n_threads, int max_residues_total,
+                                   float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype,
+                                   int32_t* residue_offsets_out, int32_t* status_out) {
+  if (n_files > 0 && !paths) return PST_ERR_BAD_ARGUMENT;
+  return parse_batch(nullptr, nullptr, paths, n_files, n_threads, max_residues_total, atom37_positions, gt_exists, atom_exists,
+                     aatype, residue_offsets_out, status_out);
 }

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("PST_LIB_PATH") or os.path.join(os.path.dirname(os.pat
 PST_ABI_VERSION = 1
 PST_ERR_WORKSPACE_TOO_SMALL = -4
 PST_ERR_PDB_MODEL_COUNT, PST_ERR_PDB_INSERTION_CODE, PST_ERR_PDB_MALFORMED = -8, -9, -10
+PST_ERR_FILE_NOT_FOUND = -11
 PST_MAX_LEVELS = 8
 
 
@@ -51,6 +52,8 @@ SIGNATURES = {
     "pst_parse_pdb": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "pst_parse_pdb_batch": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pst_parse_pdb_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "pst_read_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pst_last_launch_count": (C.c_int, [C.c_void_p]),
     "pst_graph_cache_enable": (C.c_int, [C.c_void_p, C.c_int]),

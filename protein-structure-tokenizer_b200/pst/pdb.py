@@ -192,41 +192,34 @@ def structure_from_pdb_file_native(path: str) -> StructureSample:
         return structure_from_pdb_bytes_native(fh.read())
 
 
-def structures_from_pdb_bytes_batch_native(datas, n_threads: int = 0):
-    """Many PDB texts through ONE C call (`pst_parse_pdb_batch`: host threads inside the library, no GIL, no Python
-    work per file while they run).  Returns a list with a StructureSample per text, or the ValueError the reference
-    would raise for that file (not raised here: the caller decides which file's error comes first)."""
-    import ctypes as C
-
+def _parse_batch_native(n_files: int, guess_rows: int, call, names):
+    """Shared driver of the two batch entry points: capacity retry, per-file status -> sample or exception."""
     from . import _lib
 
     lib = _lib.load()
-    nf = len(datas)
-    if nf == 0:
-        return []
-    texts = (C.c_char_p * nf)(*datas)
-    sizes = (C.c_size_t * nf)(*[len(d) for d in datas])
-    offs = np.zeros(nf + 1, np.int32)
-    status = np.zeros(nf, np.int32)
-    cap = sum(len(d) for d in datas) // 324 + 16 * nf
+    offs = np.zeros(n_files + 1, np.int32)
+    status = np.zeros(n_files, np.int32)
+    cap = guess_rows
     while True:
         pos = np.empty((cap, 37, 3), np.float32)
         gt = np.empty((cap, 37), np.uint8)
         ex = np.empty((cap, 37), np.uint8)
         aa = np.empty((cap,), np.int32)
-        rc = lib.pst_parse_pdb_batch(texts, sizes, nf, int(n_threads), cap, pos.ctypes.data, gt.ctypes.data, ex.ctypes.data,
-                                     aa.ctypes.data, offs.ctypes.data, status.ctypes.data)
+        rc = call(lib, cap, pos, gt, ex, aa, offs, status)
         if rc == _lib.PST_ERR_WORKSPACE_TOO_SMALL:
-            cap = int(offs[nf])
+            cap = int(offs[n_files])
             continue
         break
     _lib.check(rc, "pst_parse_pdb_batch")
     gtb, exb = gt.view(np.bool_), ex.view(np.bool_)
     out = []
-    for i in range(nf):
+    for i in range(n_files):
         st = int(status[i])
         if st in (_lib.PST_ERR_PDB_MODEL_COUNT, _lib.PST_ERR_PDB_INSERTION_CODE, _lib.PST_ERR_PDB_MALFORMED):
             out.append(ValueError(lib.pst_status_string(st).decode()))
+            continue
+        if st == _lib.PST_ERR_FILE_NOT_FOUND:
+            out.append(FileNotFoundError(f"{names[i]} does not exist or cannot be read"))
             continue
         _lib.check(st, "pst_parse_pdb_batch")
         a, b = int(offs[i]), int(offs[i + 1])
@@ -235,12 +228,48 @@ def structures_from_pdb_bytes_batch_native(datas, n_threads: int = 0):
     return out
 
 
+def structures_from_pdb_bytes_batch_native(datas, n_threads: int = 0):
+    """Many PDB texts through ONE C call (`pst_parse_pdb_batch`: host threads inside the library, no GIL, no Python
+    work per file while they run).  Returns a list with a StructureSample per text, or the ValueError the reference
+    would raise for that file (not raised here: the caller decides which file's error comes first)."""
+    import ctypes as C
+
+    nf = len(datas)
+    if nf == 0:
+        return []
+    texts = (C.c_char_p * nf)(*datas)
+    sizes = (C.c_size_t * nf)(*[len(d) for d in datas])
+
+    def call(lib, cap, pos, gt, ex, aa, offs, status):
+        return lib.pst_parse_pdb_batch(texts, sizes, nf, int(n_threads), cap, pos.ctypes.data, gt.ctypes.data, ex.ctypes.data,
+                                       aa.ctypes.data, offs.ctypes.data, status.ctypes.data)
+
+    return _parse_batch_native(nf, sum(len(d) for d in datas) // 324 + 16 * nf, call, [f"text {i}" for i in range(nf)])
+
+
 def structures_from_pdb_files_native(paths, n_threads: int = 0):
-    datas = []
-    for path in paths:
-        with open(path, "rb") as fh:
-            datas.append(fh.read())
-    return structures_from_pdb_bytes_batch_native(datas, n_threads)
+    """The same over files (`pst_parse_pdb_files`): the library's worker threads read the files too, so nothing per file
+    happens in Python until the arrays are sliced.  A missing file yields a FileNotFoundError in its slot."""
+    import ctypes as C
+    import os
+
+    paths = [os.fspath(p) for p in paths]
+    nf = len(paths)
+    if nf == 0:
+        return []
+    arr = (C.c_char_p * nf)(*[os.fsencode(p) for p in paths])
+    guess = 0
+    for p in paths:
+        try:
+            guess += os.path.getsize(p) // 324 + 16
+        except OSError:
+            guess += 16
+
+    def call(lib, cap, pos, gt, ex, aa, offs, status):
+        return lib.pst_parse_pdb_files(arr, nf, int(n_threads), cap, pos.ctypes.data, gt.ctypes.data, ex.ctypes.data,
+                                       aa.ctypes.data, offs.ctypes.data, status.ctypes.data)
+
+    return _parse_batch_native(nf, guess, call, paths)
 
 
 def structure_from_sample_file(path: str) -> StructureSample:

@@ -227,3 +227,8 @@ def test_batch_parser_equals_the_single_file_parser(built_lib, tmp_path):
         paths.append(str(f))
     for o, i in zip(ppdb.structures_from_pdb_files_native(paths, 2), (0, 1, 3)):
         _same_samples(o, ppdb.structure_from_pdb_bytes_native(datas[i]))
+    # a missing file takes its own slot and leaves the neighbours alone (pst_parse_pdb_files reads inside the library)
+    out = ppdb.structures_from_pdb_files_native([paths[0], str(tmp_path / "missing.pdb"), paths[2]], 3)
+    assert isinstance(out[1], FileNotFoundError)
+    _same_samples(out[0], ppdb.structure_from_pdb_bytes_native(datas[0]))
+    _same_samples(out[2], ppdb.structure_from_pdb_bytes_native(datas[3]))
