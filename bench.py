@@ -5,8 +5,11 @@
   python bench.py --impl reference --steps K --warmup W    the CPU restatement of the reference path (oracle/)
 
 Workload at N=1: BASELINE.json configs[1] -- 256 synthetic 512-residue backbones, codebook 4096,
-df=1 (131 072 valid residues per step per GPU; weak scaling: every rank owns its own 256).
-A step = one pass of the fused B2 call (atoms -> token ids) over that batch.
+df=1 (131 072 valid residues per step).  A step = one pass of the fused B2 call (atoms -> token ids) over that batch.
+Workload at N>1: BASELINE.json configs[4] -- ONE pool of length-bucketed structures (64..2048 residues, multiples of 64,
+log-uniform; 1 024*N unique structures tiled cyclically 8x to 8 192*N: 65 536 structures / ~37 M residues at N=8),
+partitioned over the ranks by LPT (pst/distributed.py), every rank streaming its shard through the chunk pipeline,
+token ids gathered to rank 0 over NCCL INSIDE the timed region.  Weak scaling (work per GPU fixed).
 `value`  : inputs resident in HBM, CUDA events on the launching stream, max over ranks.
 `e2e`    : the same batch through the host API from pinned HOST buffers, H2D and D2H inside the timed region.
 `roofline`: the dominant kernel group (the edge-level MLPs), timed live with CUDA events inside the hot call.
@@ -50,6 +53,8 @@ HW_FLOP_UPD = 2 * 3 * 128 * 128
 # edge features handed from the k-NN kernel to the embedding: 50 edges x 27 fp32 (reference layout) or x 16 fp32 (compact)
 K_FEAT_BYTES_FULL, K_FEAT_BYTES_COMPACT = 50 * 27 * 4, 50 * 16 * 4
 NCU_DRAM_BYTES = {"msg": 1.877e9, "upd": 3.415e9, "residues": 131072}
+PORT_DETAIL = ("vectorised NumPy / torch-CPU restatement of the reference path (oracle/): it has none of the reference's per-edge "
+               "Python loops, so it is FASTER than the reference's own code and the GPU/CPU ratio is conservative")
 
 
 def load_peaks():
@@ -204,14 +209,24 @@ def run_reference(args):
     if rank != 0:
         return
     workload = args.workload
-    idx, n_struct, length, codebook, df, seq_max = WORKLOADS[workload]
     from pst import synthetic as syn
 
     import torch
 
     torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))  # torchrun exports OMP_NUM_THREADS=1: use every core we may run on
-    n_sample = max(2, min(n_struct, args.cpu_sample))
-    bbs = syn.make_backbones(SEED + idx, [length] * n_sample, group=n_sample)
+    if workload == "sharded":
+        # the N > 1 arm's workload (BASELINE configs[4]): the first structures of the same length-bucketed pool
+        idx, codebook, df, seq_max = 5, 64000, 1, 2048
+        n_sample = max(2, min(8, args.cpu_sample))
+        lens = [int(v) for v in syn.bucketed_lengths(SEED + 5, POOL_UNIQUE_PER_RANK * max(1, args.gpus))[:n_sample]]
+        bbs = syn.make_backbones(SEED + 5, lens, group=n_sample)
+        what = f"cfg5 (BASELINE configs[4]): length-bucketed 64..2048-residue synthetic backbones, codebook {codebook}, df={df}"
+    else:
+        idx, n_struct, length, codebook, df, seq_max = WORKLOADS[workload]
+        n_sample = max(2, min(n_struct, args.cpu_sample))
+        lens = [length] * n_sample if length is not None else [int(v) for v in syn.bucketed_lengths(SEED + idx, n_sample)]
+        bbs = syn.make_backbones(SEED + idx, lens, group=n_sample)
+        what = f"{workload}: {n_struct}x{length}-residue synthetic backbones, codebook {codebook}, df={df}"
     vals = []
     total_steps = args.warmup + args.steps
     desc, cores = "", 1
@@ -225,9 +240,9 @@ def run_reference(args):
         "impl": "reference", "metric": "residues/sec tokenized", "value": value, "unit": "residues/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload}: {n_struct}x{length}-residue synthetic backbones, codebook {codebook}, df={df} "
-                               f"(each step = a bounded sample of {n_sample} structures)"},
-        "cpu_baseline": {"value": value, "unit": "residues/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": {"workload": f"{what} (each step = a bounded sample of {n_sample} structures, lengths {min(lens)}..{max(lens)})"},
+        "cpu_baseline": {"value": value, "unit": "residues/s", "cores": cores, "kind": "port", "sample": desc,
+                         "port_detail": PORT_DETAIL},
         "e2e": {"value": value, "unit": "residues/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference path (oracle/), not JAX: jax/haiku are not installable in this image",
     }
@@ -477,20 +492,259 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------ GPU arm, N > 1 (BASELINE configs[4])
+POOL_UNIQUE_PER_RANK = 1024   # unique structures generated per rank (the pool holds 1 024 * N)
+POOL_TILE = 8                 # the pool is tiled cyclically this many times: 8 192 * N structures in all
+
+
+def build_sharded_pool(rank: int, world: int, dev, unique_per_rank: int, tile: int):
+    """The configs[4] pool: lengths log-uniform on [64, 2048] snapped to multiples of 64.  Every rank
+    generates the unique structures u with u % world == rank (the generator is a sequential Python random walk), the
+    ranks exchange them once (all_gather, outside any timed region), and the tiled list of tile * unique structures is
+    partitioned by LPT.  Returns (this rank's global indices, their structures, all lengths of the tiled list)."""
+    import torch
+    import torch.distributed as dist
+    from pst import synthetic as syn
+    from pst.distributed import lpt_partition
+
+    n_unique = unique_per_rank * world
+    lens_u = syn.bucketed_lengths(SEED + 5, n_unique).astype(np.int64)
+    mine_u = list(range(rank, n_unique, world))
+    bbs = syn.make_backbones(SEED + 5 + 1000 * rank, [int(lens_u[u]) for u in mine_u], group=64)
+    pool = [None] * n_unique
+    if world > 1:
+        flat = np.concatenate(bbs, axis=0).astype(np.float32).reshape(-1)  # [sum L * 12]
+        sizes = [int(lens_u[r::world].sum()) * 12 for r in range(world)]
+        cap = max(sizes)
+        send = torch.zeros(cap, dtype=torch.float32, device=dev)
+        send[: flat.size] = torch.from_numpy(flat).to(dev)
+        recv = [torch.empty(cap, dtype=torch.float32, device=dev) for _ in range(world)]
+        dist.all_gather(recv, send)
+        for r in range(world):
+            buf = recv[r][: sizes[r]].cpu().numpy().reshape(-1, 4, 3)
+            pos = 0
+            for u in range(r, n_unique, world):
+                pool[u] = buf[pos : pos + int(lens_u[u])]
+                pos += int(lens_u[u])
+        del recv, send
+    else:
+        for u, bb in zip(mine_u, bbs):
+            pool[u] = bb
+    n_total = n_unique * tile
+    lens_all = np.tile(lens_u, tile)
+    shard = lpt_partition(lens_all.tolist(), world)[rank]
+    structures = [pool[i % n_unique] for i in shard]
+    return shard, structures, lens_all, n_unique
+
+
+def run_sharded(args):
+    import torch
+    import torch.distributed as dist
+
+    from pst.config import TokenizerConfig
+    from pst.distributed import gather_tokens_flat, structure_cost
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    codebook, df, seq_max = 64000, 1, 2048
+    t0 = time.time()
+    shard, structures, lens_all, n_unique = build_sharded_pool(rank, world, dev, args.pool_per_rank, args.pool_tile)
+    gen_s = time.time() - t0
+    n_total = int(lens_all.size)
+    cfg = TokenizerConfig.named(codebook, df, seq_max_size=seq_max, precision=args.precision)
+    params = init_params(cfg, 0, "spread")
+    tok = StructureTokenizer(cfg, params, device=local_rank)
+    K = cfg.num_neighbor
+    R_local = int(sum(s.shape[0] for s in structures))
+    R_total = int(lens_all.sum())
+
+    # ---- resident form of this rank's shard: the chunks the host pipeline would send, already on the device
+    lengths = [int(s.shape[0]) for s in structures]
+    chunks = tok._chunks(lengths)
+    offs_all = np.zeros(len(lengths) + 1, np.int64)
+    offs_all[1:] = np.cumsum(lengths)
+    T_local = R_local // df
+    tokens_dev = torch.empty((T_local,), dtype=torch.int32, device=dev)
+    resident = []
+    for a, b in chunks:
+        offs = (offs_all[a : b + 1] - offs_all[a]).astype(np.int32)
+        toff = tok.token_offsets(offs)
+        atoms = np.concatenate(structures[a:b], axis=0)
+        resident.append((torch.from_numpy(atoms).to(dev), torch.from_numpy(offs).to(dev), torch.from_numpy(toff).to(dev),
+                         b - a, int(offs[-1]), int(toff[-1]), int(offs_all[a]) // df))
+    counts = np.asarray(lengths, np.int64) // df
+    busy = {"ms": 0.0}
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    last = {}
+
+    def step_resident():
+        ev_a.record()
+        for atoms, offs, toff, B, R, T, t0_ in resident:
+            tok.tokenize_device(atoms, None, offs, toff, B, R, T, out=tokens_dev[t0_ : t0_ + T])
+        ev_b.record()
+        last["g"] = gather_tokens_flat(shard, counts, tokens_dev, n_total, rank, world, device=dev)
+        ev_b.synchronize()
+        busy["ms"] += ev_a.elapsed_time(ev_b)
+
+    def step_e2e():
+        t_a = time.perf_counter()
+        flat, cnt = tok.tokenize(structures, flat=True)  # host arrays -> pinned staging -> GPU -> host tokens
+        busy["ms"] += (time.perf_counter() - t_a) * 1e3
+        last["g"] = gather_tokens_flat(shard, cnt, flat, n_total, rank, world, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        busy["ms"] = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, busy["ms"]], device=dev, dtype=torch.float64)
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allv, t)
+        else:
+            allv = [t]
+        allv = torch.stack(allv).cpu().numpy()
+        return float(allv[:, 0].max()), (allv[:, 1] / steps).tolist()
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_resident()
+    torch.cuda.synchronize()
+    if tok.read_status() != 0:
+        raise SystemExit("device status != 0 after warm-up")
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local_rank, gpu_uuid) as clk:
+        ms_total, busy_res = timed(step_resident, args.steps)
+    launches = tok.launches * len(resident) * args.steps
+    g_res = last.get("g")
+    res_flat = [f.copy() for f in g_res.flat] if g_res is not None else None
+
+    # kernel-level pass (one step, event spans, eager launches) for the roofline of the dominant kernel group
+    tok.profile_enable(True)
+    barrier()
+    for atoms, offs, toff, B, R, T, t0_ in resident:
+        tok.tokenize_device(atoms, None, offs, toff, B, R, T, out=tokens_dev[t0_ : t0_ + T])
+    torch.cuda.synchronize()
+    prof_ms, prof_cnt = tok.profile_collect()
+    tok.profile_enable(False)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, busy_e2e = timed(step_e2e, args.steps)
+    g_e2e = last.get("g")
+
+    if rank == 0:
+        # correctness inside the bench: (1) the host path and the resident path return the same ids, (2) the tiled copies of
+        # one structure get identical ids whichever rank / chunk they ran in, (3) ids are in range
+        for a, b in zip(res_flat, g_e2e.flat):
+            assert np.array_equal(a, b), "end-to-end pass and resident pass disagree"
+        toks = g_e2e.to_list()
+        assert len(toks) == n_total and all(t.size == int(lens_all[i]) // df for i, t in enumerate(toks))
+        for i in range(0, n_unique, max(1, n_unique // 997)):
+            for rep in range(1, args.pool_tile):
+                assert np.array_equal(toks[i], toks[i + rep * n_unique]), "tiled copies of one structure disagree"
+        mx = max(int(f.max()) for f in g_e2e.flat if f.size)
+        assert mx < cfg.num_codes
+        peaks = load_peaks()
+        clocks = clk.summary()
+        ms_step = ms_total / args.steps
+        ms_step_e2e = ms_e2e / args.steps
+        value = R_total / (ms_step * 1e-3)
+        e2e_val = R_total / (ms_step_e2e * 1e-3)
+        burst = clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"]
+        peak = peaks["bf16_tflops"] if burst else peaks["bf16_tflops_sustained"]
+        mlp_groups, mlp_ms = prof_cnt[1] + prof_cnt[2], prof_ms[1] + prof_ms[2]
+        roof = None
+        if mlp_groups > 0 and mlp_ms > 0:
+            E_local = R_local * K
+            # every chunk runs 3 message + 2 edge-update MLP launch groups over its own edges
+            achieved = E_local * (2 * cfg.gnn_layers - 1) * FLOP_PER_EDGE_MLP / (mlp_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "edge-level MLP (message + edge-update), rank 0's shard, all chunks",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": f"{peaks['source']} ({'bf16_tflops (burst: SM clock at max during the timed region)' if burst else 'bf16_tflops_sustained'}, MEASURED_PEAKS.json)",
+                    "avg_launch_ms": mlp_ms / mlp_groups, "launch_groups": mlp_groups,
+                    "kernel_ms_per_step_rank0": {"featurize_knn": prof_ms[0], "input_embeddings": prof_ms[4], "message_mlp": prof_ms[1],
+                                                 "node_update": prof_ms[3], "edge_update_mlp": prof_ms[2], "resampler_head_df1": prof_ms[5],
+                                                 "fsq": prof_ms[6]},
+                    "end_to_end_frac": value / world * FLOP_PER_RESIDUE[df] / 1e12 / peak}
+        costs = structure_cost(lens_all)
+        line = {
+            "metric": "residues/sec tokenized", "value": value, "unit": "residues/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp16": "f16 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate", "fp32": "f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": f"cfg5 (BASELINE configs[4]): {n_total} structures = {n_unique} unique synthetic backbones tiled "
+                                   f"{args.pool_tile}x, {R_total} residues, lengths {int(lens_all.min())}..{int(lens_all.max())} "
+                                   f"(log-uniform, multiples of 64), codebook {codebook}, df={df}, K=50, LPT-sharded over {world} "
+                                   f"GPUs ({len(shard)} structures / {R_local} residues / {len(resident)} chunks on rank 0), NCCL token "
+                                   f"gather to rank 0 inside the timed region; random-init 'spread' weights",
+                       "precision": args.precision, "gen_seconds": round(gen_s, 1),
+                       "l2": "working set per chunk (edge state up to 1.7 GB) far exceeds the 126 MB L2; no explicit flush",
+                       "lpt_cost_imbalance": None,
+                       "launch": "one pst_tokenize per chunk of <= 131 072 residues"},
+            "clocks": clocks, "gpu_launches": launches,
+            "per_rank_busy_ms": {"resident": busy_res, "e2e_host_pipeline": busy_e2e,
+                                 "note": "per step, before the gather; value and e2e divide by the slowest rank's wall incl. the gather"},
+            "gather": {"bytes_per_step": int(R_total // df * 4), "collective": "NCCL gather of a padded int32 payload + two small size/table collectives"},
+            "e2e": {"value": e2e_val, "unit": "residues/s", "ms_per_step": ms_step_e2e,
+                    "h2d_bytes_per_step": int(R_total * 48 + (n_total + len(resident) * world) * 8),
+                    "d2h_bytes_per_step": int(R_total // df * 4) * 2,
+                    "pipeline": "StructureTokenizer.tokenize per rank: host arrays -> two pinned staging slots -> chunk calls -> host tokens; "
+                                "then the NCCL gather (host -> device -> rank 0 -> host)"},
+            "roofline": roof,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["sharded"],
+                    help="default: cfg2 at N=1, the LPT-sharded configs[4] pool ('sharded') at N>1")
+    ap.add_argument("--pool-per-rank", type=int, default=POOL_UNIQUE_PER_RANK)
+    ap.add_argument("--pool-tile", type=int, default=POOL_TILE)
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="structures timed by the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-agreement", action="store_true", help="skip the full-batch fp32-mode agreement pass")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "cfg2" if world == 1 else "sharded"
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sharded":
+        run_sharded(args)
     else:
         run_ours(args)
 

@@ -6,7 +6,9 @@
 // (`PstEncodeGraph`: the ProteinGraph leaves the callable reads) or, together with make_graph_from_pdb's
 // featurisation (:40-74), at boundary B2 (`PstTokenize`: atoms in, token ids out).
 //
-// NOT BUILT IN THIS IMAGE: it needs the headers of a JAX >= 0.4.31 (`python -c "import jax.ffi;
+// A compile check against a stand-in for the XLA header (tests/ffi_stub/xla/ffi/api/ffi.h: the API surface used here,
+// nothing more) runs in tests/test_abi.py; the real build is
+// NOT POSSIBLE IN THIS IMAGE: it needs the headers of a JAX >= 0.4.31 (`python -c "import jax.ffi;
 // print(jax.ffi.include_dir())"`), and neither jax nor jaxlib is installed here (the reference pins jax==0.4.23,
 // which predates jax.ffi).  pst/jax_ffi.py compiles and registers it when `import jax` works:
 //   g++ -std=c++17 -shared -fPIC -I$(jax.ffi.include_dir()) -I include -I /usr/local/cuda/include \
@@ -29,15 +31,24 @@ static inline pst_model* as_model(int64_t handle) { return reinterpret_cast<pst_
 
 static ffi::Error fail(int rc) { return ffi::Error(ffi::ErrorCode::kInternal, pst_status_string(rc)); }
 
-// B2: atoms f32[R, A, 3] (A = 4 or 37), offsets i32[B+1], token_offsets i32[B+1] -> tokens i32[T]
-static ffi::Error TokenizeImpl(cudaStream_t stream, int64_t model, ffi::Buffer<ffi::F32> atoms, ffi::Buffer<ffi::S32> offsets,
-                               ffi::Buffer<ffi::S32> token_offsets, ffi::ResultBuffer<ffi::S32> tokens,
-                               ffi::ResultBuffer<ffi::U8> workspace) {
+// B2: atoms f32[R, A, 3] (A = 4 or 37), atom_mask u8[R, A] (gt_exists & atom_exists, data/preprocessing.py:72; an EMPTY
+// buffer, u8[0], means "every atom slot present": backbone-only input), offsets i32[B+1], token_offsets i32[B+1]
+// -> tokens i32[T].  With atom37 input from real PDB files the mask is REQUIRED: the k-NN anchor is the mean of the
+// present heavy atoms (utils/protein_utils.py:373-378) and zero-filled absent slots must not enter it.
+static ffi::Error TokenizeImpl(cudaStream_t stream, int64_t model, ffi::Buffer<ffi::F32> atoms, ffi::Buffer<ffi::U8> atom_mask,
+                               ffi::Buffer<ffi::S32> offsets, ffi::Buffer<ffi::S32> token_offsets,
+                               ffi::ResultBuffer<ffi::S32> tokens, ffi::ResultBuffer<ffi::U8> workspace) {
   const int B = static_cast<int>(offsets.dimensions()[0]) - 1;
   const int R = static_cast<int>(atoms.dimensions()[0]);
   const int A = static_cast<int>(atoms.dimensions()[1]);
   const int T = static_cast<int>(tokens->dimensions()[0]);
-  const int rc = pst_tokenize(as_model(model), stream, atoms.typed_data(), /*atom_mask=*/nullptr, A, offsets.typed_data(),
+  const uint8_t* mask = nullptr;
+  if (atom_mask.element_count() != 0) {
+    if (atom_mask.element_count() != static_cast<size_t>(R) * static_cast<size_t>(A))
+      return ffi::Error(ffi::ErrorCode::kInvalidArgument, "atom_mask must be u8[R, A] or empty");
+    mask = atom_mask.typed_data();
+  }
+  const int rc = pst_tokenize(as_model(model), stream, atoms.typed_data(), mask, A, offsets.typed_data(),
                               token_offsets.typed_data(), B, R, T, tokens->typed_data(), workspace->typed_data(),
                               workspace->size_bytes());
   return rc == PST_OK ? ffi::Error::Success() : fail(rc);
@@ -63,6 +74,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(PstTokenize, TokenizeImpl,
                                   .Ctx<ffi::PlatformStream<cudaStream_t>>()
                                   .Attr<int64_t>("model")
                                   .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
                                   .Arg<ffi::Buffer<ffi::S32>>()
                                   .Arg<ffi::Buffer<ffi::S32>>()
                                   .Ret<ffi::Buffer<ffi::S32>>()

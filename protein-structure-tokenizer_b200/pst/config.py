@@ -141,6 +141,10 @@ class TokenizerConfig:
             raise NotImplementedError("codebook.renorm=true is not used by any released config")
         if not model.down_sampler.use_local_attn or model.down_sampler.get("use_global_node", 0):
             raise NotImplementedError("only local-attention down-samplers without a global node are supported")
+        if not data.get("graph_residue_loc_is_alphac", True):
+            # data/preprocessing.py:147-165: the alternative places the orientation features' positions on the side-chain
+            # centroid; the kernels take them from CA (every released data config sets true)
+            raise NotImplementedError("graph_residue_loc_is_alphac=false is not supported (all released configs use CA)")
         return cls(
             seq_max_size=int(data.seq_max_size),
             max_out_len=int(model.down_sampler.max_out_len),

@@ -5,70 +5,118 @@ end (4 B per token).  Replaces the reference's `jax.pmap` data parallelism
 
 The partition is a greedy longest-processing-time assignment on the cost model
 c(L) = L * (alpha + beta * L)  (O(L*K) encoder work + O(L^2) k-NN work), so ragged batches balance.
+
+Callers: `InferenceRunner.tokenize` under torchrun (files sharded over ranks, rank 0 writes the token files),
+`_TokenizeFn` (LPT over the devices of one process) and `bench.py --gpus N` (the BASELINE configs[4] workload).
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence
+import heapq
+from typing import Callable, List, NamedTuple, Optional, Sequence
 
 import numpy as np
 
 
-def structure_cost(length: int, alpha: float = 1.0, beta: float = 1.0 / 4096.0) -> float:
-    return float(length) * (alpha + beta * float(length))
+def structure_cost(length, alpha: float = 1.0, beta: float = 1.0 / 4096.0):
+    """Relative cost of one structure (scalar or array of lengths)."""
+    L = np.asarray(length, np.float64)
+    c = L * (alpha + beta * L)
+    return float(c) if c.ndim == 0 else c
 
 
 def lpt_partition(lengths: Sequence[int], world: int, alpha: float = 1.0, beta: float = 1.0 / 4096.0) -> List[List[int]]:
-    """Indices of the structures each rank owns; deterministic (ties broken by index)."""
-    order = sorted(range(len(lengths)), key=lambda i: (-structure_cost(lengths[i], alpha, beta), i))
-    load = [0.0] * world
+    """Indices of the structures each rank owns; deterministic (ties broken by index, then by rank)."""
+    n = len(lengths)
+    cost = np.asarray(structure_cost(np.asarray(lengths, np.int64), alpha, beta), np.float64).reshape(-1)
+    order = np.lexsort((np.arange(n), -cost))  # descending cost, ascending index
+    heap = [(0.0, r) for r in range(world)]
     shards: List[List[int]] = [[] for _ in range(world)]
-    for i in order:
-        r = min(range(world), key=lambda k: (load[k], k))
+    for i in order.tolist():
+        load, r = heapq.heappop(heap)
         shards[r].append(i)
-        load[r] += structure_cost(lengths[i], alpha, beta)
+        heapq.heappush(heap, (load + float(cost[i]), r))
     for s in shards:
         s.sort()
     return shards
 
 
-def gather_tokens(local_indices: Sequence[int], local_tokens: Sequence[np.ndarray], n_total: int, rank: int, world: int,
-                  device=None, group=None) -> Optional[List[np.ndarray]]:
-    """Collects every rank's token arrays on rank 0 (returns None elsewhere).  One size exchange
-    (all_gather of int64 counts) and one `gather` of a padded int32 payload [index, length, tokens...]."""
+class GatheredTokens(NamedTuple):
+    """Rank 0's view of a gather: `flat[r]` holds rank r's tokens back to back in the order of `index[r]`."""
+
+    flat: List[np.ndarray]     # per rank, int32 [sum of that rank's token counts]
+    index: List[np.ndarray]    # per rank, int64 [n_r] global structure indices
+    counts: List[np.ndarray]   # per rank, int64 [n_r] tokens per structure
+    n_total: int
+
+    def to_list(self) -> List[np.ndarray]:
+        """One uint32 array per structure, in global input order (views into the gathered buffers)."""
+        out: List[Optional[np.ndarray]] = [None] * self.n_total
+        for flat, idx, cnt in zip(self.flat, self.index, self.counts):
+            ends = np.cumsum(cnt)
+            u = flat.view(np.uint32)
+            for i, a, b in zip(idx.tolist(), (ends - cnt).tolist(), ends.tolist()):
+                out[i] = u[a:b]
+        assert all(o is not None for o in out), "a structure's tokens never arrived"
+        return out  # type: ignore[return-value]
+
+    def total_tokens(self) -> int:
+        return int(sum(int(c.sum()) for c in self.counts))
+
+
+def gather_tokens_flat(local_indices: Sequence[int], local_counts: Sequence[int], local_flat, n_total: int, rank: int,
+                       world: int, device=None, group=None) -> Optional[GatheredTokens]:
+    """Collects every rank's tokens on rank 0 (None elsewhere).  `local_flat` is this rank's tokens back to back
+    (int32; a NumPy array, or a torch tensor already on `device`, which then goes over NCCL without a host hop).
+    Two small collectives (all_gather of the sizes, gather of the (index, count) tables) and ONE gather of the padded
+    int32 payload: the only data-path collective of the whole tokenize job."""
     import torch
     import torch.distributed as dist
 
+    idx = np.asarray(local_indices, np.int64)
+    cnt = np.asarray(local_counts, np.int64)
     if world == 1:
-        out: List[Optional[np.ndarray]] = [None] * n_total
-        for i, t in zip(local_indices, local_tokens):
-            out[i] = np.asarray(t, np.uint32)
-        return out  # type: ignore
+        flat = local_flat.cpu().numpy() if isinstance(local_flat, torch.Tensor) else np.asarray(local_flat)
+        return GatheredTokens([flat.astype(np.int32, copy=False)], [idx], [cnt], n_total)
     dev = device if device is not None else torch.device("cpu")
-    parts = []
-    for i, t in zip(local_indices, local_tokens):
-        t = np.asarray(t).astype(np.int64)
-        parts.append(np.concatenate([[i, t.size], t]))
-    flat = np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
-    n = torch.tensor([flat.size], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    cap = int(max(int(s.item()) for s in sizes))
-    payload = torch.zeros(max(cap, 1), dtype=torch.int32, device=dev)
-    payload[: flat.size] = torch.from_numpy(flat).to(dev)
+    if isinstance(local_flat, torch.Tensor):
+        payload_local = local_flat.to(device=dev, dtype=torch.int32)
+    else:
+        payload_local = torch.from_numpy(np.ascontiguousarray(local_flat, np.int32)).to(dev)
+    sizes_t = torch.tensor([idx.size, int(payload_local.numel())], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes_t) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes_t, group=group)
+    sizes = np.stack([s.cpu().numpy() for s in all_sizes])  # [world, 2]
+    cap_n, cap_t = int(sizes[:, 0].max()), int(sizes[:, 1].max())
+    table = torch.zeros((2, max(cap_n, 1)), dtype=torch.int64, device=dev)
+    if idx.size:
+        table[0, : idx.size] = torch.from_numpy(idx).to(dev)
+        table[1, : idx.size] = torch.from_numpy(cnt).to(dev)
+    payload = torch.zeros(max(cap_t, 1), dtype=torch.int32, device=dev)
+    payload[: payload_local.numel()] = payload_local
+    tables = [torch.zeros_like(table) for _ in range(world)] if rank == 0 else None
     bufs = [torch.zeros_like(payload) for _ in range(world)] if rank == 0 else None
+    dist.gather(table, tables, dst=0, group=group)
     dist.gather(payload, bufs, dst=0, group=group)
     if rank != 0:
         return None
-    out = [None] * n_total
+    flats, idxs, cnts = [], [], []
     for r in range(world):
-        buf = bufs[r][: int(sizes[r].item())].cpu().numpy()
-        pos = 0
-        while pos < buf.size:
-            i, m = int(buf[pos]), int(buf[pos + 1])
-            out[i] = buf[pos + 2 : pos + 2 + m].astype(np.uint32)
-            pos += 2 + m
-    assert all(o is not None for o in out), "a structure's tokens never arrived"
-    return out  # type: ignore
+        n_r, t_r = int(sizes[r, 0]), int(sizes[r, 1])
+        tb = tables[r].cpu().numpy()
+        idxs.append(tb[0, :n_r].copy())
+        cnts.append(tb[1, :n_r].copy())
+        flats.append(bufs[r][:t_r].cpu().numpy())
+    return GatheredTokens(flats, idxs, cnts, n_total)
+
+
+def gather_tokens(local_indices: Sequence[int], local_tokens: Sequence[np.ndarray], n_total: int, rank: int, world: int,
+                  device=None, group=None) -> Optional[List[np.ndarray]]:
+    """List form of `gather_tokens_flat`: rank 0 gets one uint32 array per structure in input order."""
+    counts = [int(np.asarray(t).size) for t in local_tokens]
+    flat = (np.concatenate([np.asarray(t).reshape(-1) for t in local_tokens]).astype(np.int32)
+            if local_tokens else np.zeros(0, np.int32))
+    g = gather_tokens_flat(local_indices, counts, flat, n_total, rank, world, device=device, group=group)
+    return None if g is None else g.to_list()
 
 
 def tokenize_sharded(lengths: Sequence[int], tokenize_local: Callable[[List[int]], List[np.ndarray]], rank: int, world: int,
@@ -78,3 +126,17 @@ def tokenize_sharded(lengths: Sequence[int], tokenize_local: Callable[[List[int]
     mine = shards[rank]
     toks = tokenize_local(mine) if mine else []
     return gather_tokens(mine, toks, len(lengths), rank, world, device=device, group=group)
+
+
+def dist_env():
+    """(rank, world, local_rank) of this process: the torch.distributed group when one is initialised, else 0, 1, 0."""
+    import os
+
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", "0"))
+    except Exception:
+        pass
+    return 0, 1, 0

@@ -51,15 +51,18 @@ def register() -> None:
 
 def make_tokenize_fn(tok):
     """tok: pst.tokenizer.StructureTokenizer (owns the pst_model handle).  Returns
-    f(atoms f32[R, A, 3], offsets i32[B+1], token_offsets i32[B+1], total_tokens: int) -> i32[total_tokens]."""
+    f(atoms f32[R, A, 3], offsets i32[B+1], token_offsets i32[B+1], total_tokens: int, atom_mask=None) -> i32[total_tokens].
+    `atom_mask` u8[R, A] = gt_exists & atom_exists (data/preprocessing.py:72) is required with atom37 input from real
+    files (absent atom slots are zero-filled and must not enter the centroid); None = every slot present."""
     register()
     handle = np.int64(tok._h.value)
 
-    def f(atoms, offsets, token_offsets, total_tokens: int):
+    def f(atoms, offsets, token_offsets, total_tokens: int, atom_mask=None):
         R, B = atoms.shape[0], offsets.shape[0] - 1
         ws = int(tok.lib.pst_workspace_bytes(tok._h, int(R), int(B)))
+        mask = jnp.zeros((0,), jnp.uint8) if atom_mask is None else jnp.asarray(atom_mask, jnp.uint8)
         out = jax.ffi.ffi_call("PstTokenize", (jax.ShapeDtypeStruct((total_tokens,), jnp.int32),
-                                               jax.ShapeDtypeStruct((ws,), jnp.uint8)))(atoms, offsets, token_offsets, model=handle)
+                                               jax.ShapeDtypeStruct((ws,), jnp.uint8)))(atoms, mask, offsets, token_offsets, model=handle)
         return out[0]
 
     return f

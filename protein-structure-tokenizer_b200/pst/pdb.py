@@ -10,6 +10,7 @@ Also the residue filter of data/preprocessing.py:72,99-117 (`valid_backbone`).
 """
 from __future__ import annotations
 
+import pickle
 import threading
 from typing import Dict, List, NamedTuple, Tuple
 
@@ -272,6 +273,45 @@ def structures_from_pdb_files_native(paths, n_threads: int = 0):
     return _parse_batch_native(nf, guess, call, paths)
 
 
+class _SampleUnpickler(pickle.Unpickler):
+    """Unpickler for `ProteinStructureSample.to_file` payloads: a dict of str / int / float / NumPy arrays.  Only the
+    NumPy reconstruction helpers those need may be resolved; any other global (what a hostile pickle would use to run
+    code) is refused, so a stray .npy in --pdb_dir cannot execute anything (np.load(allow_pickle=True) would)."""
+
+    _ALLOWED = {
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+        ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+        ("numpy", "ndarray"), ("numpy", "dtype"),
+    }
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"refusing to resolve {module}.{name} while reading a structure sample file")
+
+
+def _load_sample_dict(path: str) -> dict:
+    """Reads the 0-d object .npy that `np.save(path, dict)` writes without np.load's unrestricted unpickling."""
+    with open(path, "rb") as fh:
+        version = np.lib.format.read_magic(fh)
+        if version == (1, 0):
+            shape, _, dtype = np.lib.format.read_array_header_1_0(fh)
+        elif version in ((2, 0), (3, 0)):
+            shape, _, dtype = np.lib.format.read_array_header_2_0(fh)
+        else:
+            raise ValueError(f"{path}: unsupported .npy version {version}")
+        if not dtype.hasobject or shape != ():
+            raise ValueError(f"{path}: not a ProteinStructureSample file (expected a 0-d object array holding a dict)")
+        obj = _SampleUnpickler(fh).load()
+    if isinstance(obj, np.ndarray) and obj.shape == ():
+        obj = obj[()]
+    if not isinstance(obj, dict):
+        raise ValueError(f"{path}: not a ProteinStructureSample file (payload is {type(obj).__name__}, expected dict)")
+    return obj
+
+
+
 def structure_from_sample_file(path: str) -> StructureSample:
     """The reference's preprocessed sample format: `ProteinStructureSample.to_file` / `.from_file`
     (structure_tokenizer/data/protein_structure_sample.py:46-62), an .npy holding the pickled dict of the NamedTuple
@@ -282,8 +322,7 @@ def structure_from_sample_file(path: str) -> StructureSample:
 
     if not os.path.isfile(path):
         raise FileNotFoundError(f"{path} does not exist")
-    with open(path, "rb") as fh:
-        d = np.load(fh, allow_pickle=True)[()]
+    d = _load_sample_dict(path)
     n = int(d["nb_residues"])
     aatype = np.asarray(d["aatype"])
     if aatype.ndim == 2:  # one-hot over the 20 residue types + unknown

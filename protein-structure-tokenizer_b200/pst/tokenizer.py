@@ -173,6 +173,41 @@ class StructureTokenizer:
         self.launches = self.lib.pst_last_launch_count(self._h)
         return tokens
 
+    def masked_token_code(self) -> int:
+        """Token id the reference emits at padded positions: the bounded latent is multiplied by the mask before
+        rounding (model/quantize.py:188-209), so every digit is 0 + floor(L/2) (2 730 for 4 096
+        codes, 32 036 for 64 000)."""
+        code, basis = 0, 1
+        for L in self.cfg.levels:
+            code += (int(L) // 2) * basis
+            basis *= int(L)
+        return code
+
+    def encode_graph(self, edge_features: np.ndarray, senders: np.ndarray, offsets: np.ndarray) -> List[np.ndarray]:
+        """Boundary B1 on host arrays: ragged `edge_features` f32 [sum n*K, 27], `senders` i32 [sum n*K] (indices local
+        to their structure, as in `ProteinGraph.senders`), `offsets` i32 [B+1] -> one uint32 token array per structure.
+        Sent in chunks of at most `max_rows_per_call` residues (pst_encode_graph + pst_quantize per chunk)."""
+        t = self.torch
+        K = self.cfg.num_neighbor
+        offsets = np.asarray(offsets, np.int64)
+        self.check_lengths(offsets)
+        lengths = np.diff(offsets).tolist()
+        out: List[np.ndarray] = []
+        for a, b in self._chunks(lengths):
+            offs = (offsets[a : b + 1] - offsets[a]).astype(np.int32)
+            toff = self.token_offsets(offs)
+            R, T, B = int(offs[-1]), int(toff[-1]), b - a
+            e0, e1 = int(offsets[a]) * K, int(offsets[b]) * K
+            f = t.from_numpy(np.ascontiguousarray(edge_features[e0:e1], np.float32)).to(self.device)
+            s = t.from_numpy(np.ascontiguousarray(senders[e0:e1], np.int32)).to(self.device)
+            z = self.encode_graph_device(f, s, t.from_numpy(offs).to(self.device), t.from_numpy(toff).to(self.device), B, R, T)
+            tokens = self.quantize_device(z).cpu().numpy()
+            st = self.read_status()
+            if st != 0:
+                raise _lib.PstError(st, "pst_encode_graph (device status)")
+            out.extend(tokens[toff[i] : toff[i + 1]].astype(np.uint32) for i in range(B))
+        return out
+
     def graph_cache_enable(self, on: bool = True) -> None:
         """CUDA-graph replay of repeated pst_tokenize calls (on by default; see include/pst_abi.h)."""
         _lib.check(self.lib.pst_graph_cache_enable(self._h, int(on)), "pst_graph_cache_enable")
@@ -203,11 +238,13 @@ class StructureTokenizer:
             out.append((start, len(lengths)))
         return out
 
-    def tokenize(self, structures: Sequence[np.ndarray], masks: Optional[Sequence[Optional[np.ndarray]]] = None) -> List[np.ndarray]:
+    def tokenize(self, structures: Sequence[np.ndarray], masks: Optional[Sequence[Optional[np.ndarray]]] = None,
+                 flat: bool = False):
         """structures: one fp32 array [L, A, 3] per protein (A = 4: N,CA,C,O; A = 37: atom37),
         only valid residues; masks: optional u8/bool [L, A].  Returns one uint32 token
         array [floor(L/df)] per protein (the dtype the reference saves,
-        scripts/inference_runner.py:315-321).
+        scripts/inference_runner.py:315-321); with `flat=True` the same tokens as ONE int32 array (structures back
+        to back) plus the per-structure counts, which is what the multi-GPU gather sends (pst/distributed.py).
 
         The structures are processed in chunks of at most `max_rows_per_call` residues through a two-slot pipeline:
         while the GPU works on chunk i, the host packs chunk i + 1 into pinned staging buffers and its H2D copy runs on
@@ -217,8 +254,13 @@ class StructureTokenizer:
         offs_all = np.zeros(len(lengths) + 1, np.int64)
         offs_all[1:] = np.cumsum(lengths)
         self.check_lengths(offs_all)
+        df = self.cfg.downsampling_ratio
+        counts = np.asarray(lengths, np.int64) // df
+        tok_all = np.zeros(len(lengths) + 1, np.int64)
+        tok_all[1:] = np.cumsum(counts)
+        out_flat = np.empty(int(tok_all[-1]), np.int32)
         if not lengths:
-            return []
+            return (out_flat, counts) if flat else []
         chunks = self._chunks(lengths)
         A = int(structures[0].shape[1])
         use_mask = masks is not None and any(m is not None for m in masks)
@@ -227,17 +269,14 @@ class StructureTokenizer:
         slots = self._pipeline_slots(min(2, len(chunks)), cap_rows, cap_b, A, use_mask)
         self._workspace(cap_rows, cap_b)  # sized for the largest chunk up front: no reallocation inside the pipeline
         main = t.cuda.current_stream(self.device)
-        results: List[Optional[np.ndarray]] = [None] * len(lengths)
 
         def finish(sl):
-            a, b, tok_off = sl["job"]
+            a, b, T = sl["job"]
             sl["done"].synchronize()
             st = int(sl["status_pin"][0])
             if st != 0:
                 raise _lib.PstError(st, "pst_tokenize (device status)")
-            tokens = sl["tokens_pin"].numpy()
-            for i in range(b - a):
-                results[a + i] = tokens[tok_off[i] : tok_off[i + 1]].astype(np.uint32)
+            out_flat[tok_all[a] : tok_all[a] + T] = sl["tokens_pin"].numpy()[:T]
             sl["job"] = None
 
         for ci, (a, b) in enumerate(chunks):
@@ -245,11 +284,13 @@ class StructureTokenizer:
             if sl["job"] is not None:
                 finish(sl)
             offsets = (offs_all[a : b + 1] - offs_all[a]).astype(np.int32)
-            tok_off = self.token_offsets(offsets)
+            tok_off = (tok_all[a : b + 1] - tok_all[a]).astype(np.int32)
             R, T, B = int(offsets[-1]), int(tok_off[-1]), b - a
             atoms_np = sl["atoms_pin"].numpy()
-            for i in range(a, b):
-                atoms_np[offsets[i - a] : offsets[i - a + 1]] = structures[i]
+            if B == 1:
+                atoms_np[:R] = structures[a]
+            else:
+                np.concatenate(structures[a:b], axis=0, out=atoms_np[:R])
             if use_mask:
                 mask_np = sl["mask_pin"].numpy()
                 for i in range(a, b):
@@ -274,11 +315,14 @@ class StructureTokenizer:
                 self._copy.wait_event(sl["computed"])
                 sl["tokens_pin"][:T].copy_(sl["tokens"][:T], non_blocking=True)
                 sl["done"].record(self._copy)
-            sl["job"] = (a, b, tok_off)
+            sl["job"] = (a, b, T)
         order = sorted((sl for sl in slots if sl["job"] is not None), key=lambda sl: sl["job"][0])
         for sl in order:
             finish(sl)
-        return results  # type: ignore[return-value]
+        if flat:
+            return out_flat, counts
+        u = out_flat.view(np.uint32)
+        return [u[a:b] for a, b in zip(tok_all[:-1].tolist(), tok_all[1:].tolist())]
 
     def _pipeline_slots(self, n: int, rows: int, nb: int, A: int, use_mask: bool):
         """Pinned host + device staging buffers of the chunk pipeline (grow-only, kept between calls)."""

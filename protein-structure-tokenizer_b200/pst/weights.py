@@ -196,7 +196,9 @@ def pack_weights(params: Dict[str, np.ndarray], cfg: TokenizerConfig) -> np.ndar
         put(_find(params, f"{pre}/norm_msg_2/scale"), (D,))
         put(_find(params, f"{pre}/norm_msg_2/offset"), (D,))
     put(pe_table(np.arange(cfg.max_out_len), cfg.max_out_len), (cfg.max_out_len, D))
-    it = "cross_attn_scaler_iteration"
+    # the parent scope matters: a full released checkpoint also holds the decoder's
+    # `cross_attn_upsampling/cross_attn_scaler_iteration/...` with identical inner names (model/model.py:70-98)
+    it = "cross_attn_downsampling/cross_attn_scaler_iteration"
     att = f"{it}/cross_attention/attention"
     for b in range(cfg.num_blocks):
         put(_find(params, f"{it}/cross_attention/query_norm/scale")[b], (D,))

@@ -45,7 +45,11 @@ CASES = [  # (codebook, df, structures, weight seed)
     (64000, 4, ["T1024", "T1046s1"], 12),
     (432, 1, ["T1046s1"], 13),
     (4096, 2, ["T1030"], 14),
+    # larger samples (>= 2 000 tokens each) for the default-mode agreement gate: tokens + bounded latents only
+    (64000, 1, ["T1079", "T1037", "T1042", "T1025", "T1041", "T1067", "T1038", "T1090"], 15),
+    (1728, 1, ["T1024", "T1030", "T1099", "T1032", "T1056", "T1027", "T1039", "T1043", "T1026", "T1054", "T1046s2", "T1049"], 16),
 ]
+LARGE = {(64000, 1), (1728, 1)}  # no pre-projection embeddings stored (128 floats per token)
 
 
 def deep_merge(a, b):
@@ -101,8 +105,12 @@ def main():
             atom37_atom_exists=np.unpackbits(a37["atom37_atom_exists"][sl], axis=1)[:, :37].astype(bool),
             resolution=0.0, pdb_cluster_size=1)
 
-    name_fixture = {}
+    only = {tuple(int(v) for v in a.split("_df")) for a in sys.argv[1:]}  # e.g. `64000_df1 1728_df1`: just these cases
+    names_path = os.path.join(HERE, "model_ref_param_names.json")
+    name_fixture = json.load(open(names_path)) if only and os.path.exists(names_path) else {}
     for codebook, df, structs, seed in CASES:
+        if only and (codebook, df) not in only:
+            continue
         cfg = compose_config(codebook, df)
         dc = cfg.data.data
         assert dc.downsampling_ratio == df
@@ -159,7 +167,8 @@ def main():
             tok = np.asarray(q["tokens"])[0]
             out[f"{s}/tokens"] = tok.astype(np.uint32)
             out[f"{s}/bounded"] = np.asarray(q["continuous_embedding"])[0, :nt].astype(np.float32)
-            out[f"{s}/pre_proj"] = np.asarray(q["continuous_embedding_pre_proj"])[0, :nt].astype(np.float32)
+            if (codebook, df) not in LARGE:
+                out[f"{s}/pre_proj"] = np.asarray(q["continuous_embedding_pre_proj"])[0, :nt].astype(np.float32)
             out[f"{s}/n_valid"] = nv
             print(f"  {s}: n_valid={nv} tokens={nt} distinct={len(np.unique(tok[:nt]))} "
                   f"perplexity={float(np.asarray(q['perplexity'])):.1f} {time.time() - t0:.1f}s")

@@ -3,6 +3,7 @@ No compute call is made here (there is no GPU); host-only entry points are exerc
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -132,3 +133,20 @@ def test_jax_ffi_binding_is_gated_on_jax_and_uses_only_abi_symbols():
     except ImportError:
         with pytest.raises(ImportError):
             import pst.jax_ffi  # noqa: F401
+
+
+def test_jax_ffi_handlers_compile_against_the_header_stand_in():
+    """g++ -fsyntax-only of ffi/pst_xla_ffi.cc against tests/ffi_stub (the slice of xla/ffi/api/ffi.h the handlers
+    use): the handler parameter lists match their bindings (static_assert in the stand-in), PstTokenize carries the
+    atom mask, and every C-ABI call type-checks against include/pst_abi.h."""
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("CUDA headers not found")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-comment", "-Werror", "-I", os.path.join(ROOT, "tests", "ffi_stub"),
+                        "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, os.path.join(ROOT, "ffi", "pst_xla_ffi.cc")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    with open(os.path.join(ROOT, "ffi", "pst_xla_ffi.cc")) as fh:
+        src = fh.read()
+    tok = src[src.index("static ffi::Error TokenizeImpl"):src.index("// B1:")]
+    assert "atom_mask" in tok and "/*atom_mask=*/nullptr" not in tok

@@ -119,3 +119,90 @@ def test_chunk_pipeline_matches_single_call(built_lib):
     for a, b in zip(whole, parts):
         assert np.array_equal(a, b)
     assert small.tokenize([]) == []
+
+
+def test_flat_token_output_equals_the_list_form(built_lib):
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(64000, 4, precision="fp16")
+    tok = StructureTokenizer(cfg, init_params(cfg, 0, "spread"), max_rows_per_call=300)
+    lengths = [64, 201, 90, 150, 77]
+    bbs = syn.make_backbones(12, lengths)
+    parts = tok.tokenize(bbs)
+    flat, counts = tok.tokenize(bbs, flat=True)
+    assert counts.tolist() == [L // 4 for L in lengths] and flat.dtype == np.int32
+    assert np.array_equal(flat.view(np.uint32), np.concatenate(parts))
+
+
+@pytest.mark.parametrize("codebook,df", [(4096, 1), (64000, 4), (4096, 2)])
+def test_reference_padded_graph_batch_through_the_callable(built_lib, casp14, codebook, df):
+    """The reference's own batch object — ProteinGraph leaves padded to seq_max_size and stacked to [Dev, B, ...]
+    (data/preprocessing.py:191-283, scripts/inference_runner.py:77-83) — goes through the runner's callable (boundary
+    B1) and comes back as uint32 [Dev, B, T] INCLUDING the padded tail (code 2 730 / 32 036), compared with the tokens
+    the reference's model source produced for the same padded graphs (tests/golden/model_ref_*.npz, all T rows)."""
+    import types
+
+    from oracle import featurize as fz
+    from pst.config import TokenizerConfig
+    from pst.inference_runner import InferenceRunner
+    from test_golden_model import load_case
+    from test_host import _pad_like_the_reference
+
+    f, cfg, params = load_case(codebook, df)
+    cfg = TokenizerConfig(seq_max_size=cfg.seq_max_size, max_out_len=cfg.max_out_len, downsampling_ratio=df,
+                          levels=list(cfg.levels), precision="fp32")
+    names = [str(n) for n in f["names"]]
+    padded = []
+    for n in names:
+        e = casp14[n]
+        g = fz.featurize(e["pos"].astype(np.float64), e["gt"], e["exists"], cfg.num_neighbor)
+        padded.append(_pad_like_the_reference(g, cfg.num_neighbor, cfg.seq_max_size, df))
+    batch = types.SimpleNamespace(**{k: np.stack([p[k] for p in padded])[None] for k in padded[0]})  # [Dev=1, B, ...]
+    fn = InferenceRunner.prepare_tokenize_fn(cfg, [0])
+    out = fn(params, None, types.SimpleNamespace(graph=batch, features={}))["tokens"]
+    T = cfg.seq_max_size // df
+    assert out.shape == (1, len(names), T) and out.dtype == np.uint32
+    for b, n in enumerate(names):
+        ref_t, ref_b = f[f"{n}/tokens"], f[f"{n}/bounded"]
+        nt = int(f[f"{n}/n_valid"]) // df
+        amb = (np.abs(ref_b - np.floor(ref_b) - 0.5) < 5e-4).any(-1)
+        assert np.array_equal(out[0, b, :nt][~amb], ref_t[:nt][~amb]), n
+        assert np.array_equal(out[0, b, nt:], ref_t[nt:]), n  # the masked-token code of the padded tail
+        # what the reference's save loop keeps (scripts/inference_runner.py:307-317)
+        kept = out[0, b, : int(batch.tokens_mask[0, b].sum())]
+        assert kept.shape == (nt,)
+
+
+def test_runner_under_torchrun_shards_files_and_gathers_on_rank0(built_lib, tmp_path):
+    """scripts/tokenize_pdb.py under torchrun with 2 ranks: files sharded by LPT, tokens gathered over NCCL, rank 0
+    writes every file; the files equal a single-process run."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from conftest import ROOT
+    from pst import synthetic as syn
+    from test_pdb import _pdb_from_backbone
+
+    pdb_dir = tmp_path / "pdbs"
+    pdb_dir.mkdir()
+    bbs = syn.make_backbones(41, [70, 120, 55, 200, 64])
+    for i, bb in enumerate(bbs):
+        (pdb_dir / f"S{i}.pdb").write_text(_pdb_from_backbone(bb))
+    cli = os.path.join(ROOT, "scripts", "tokenize_pdb.py")
+    common = ["--pdb_dir", str(pdb_dir), "--random_init", "--batch_size_per_device", "2"]
+    one = subprocess.run([sys.executable, cli, "--token_save_path", str(tmp_path / "one"), *common], capture_output=True, text=True)
+    assert one.returncode == 0, one.stderr[-2000:]
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29731", cli, "--token_save_path", str(tmp_path / "two"), *common], capture_output=True, text=True)
+    assert two.returncode == 0, two.stderr[-2000:]
+    names = sorted(os.listdir(tmp_path / "one"))
+    assert names == sorted(os.listdir(tmp_path / "two")) == [f"S{i}_tokens.npy" for i in range(5)]
+    for n in names:
+        assert np.array_equal(np.load(tmp_path / "one" / n), np.load(tmp_path / "two" / n))

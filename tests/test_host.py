@@ -192,3 +192,97 @@ def test_preprocessed_sample_files_round_trip_and_feed_the_runner(built_lib, tmp
     if os.path.isfile(ref):
         s = ppdb.structure_from_sample_file(ref)
         assert s.nb_residues == 123 and s.atom37_positions.shape == (123, 37, 3) and s.valid_backbone().sum() >= 50
+
+
+def _pad_like_the_reference(g, K, N, df):
+    """data/preprocessing.py:191-283 on an oracle graph: zero features and K self loops per padded residue."""
+    n = g["n_node"]
+    feats = np.zeros((N * K, 27), np.float32)
+    feats[: n * K] = g["edge_features"]
+    send = np.repeat(np.arange(N), K)
+    send[: n * K] = g["senders"]
+    recv = np.repeat(np.arange(N), K)
+    nodes_mask = (np.arange(N) < n)[:, None]
+    tokens_mask = (np.arange(N // df) < n // df)[:, None]
+    return {"n_node": np.array([n]), "n_edge": np.array([n * K]), "nodes_mask": nodes_mask, "edge_features": feats,
+            "tokens_mask": tokens_mask, "senders": send, "receivers": recv}
+
+
+def test_padded_protein_graph_batches_convert_to_the_ragged_call(casp14):
+    """The reference's own batch (ProteinGraph leaves stacked to [Dev, B, ...] by batch_collate,
+    scripts/inference_runner.py:77-83; or a BatchDataVQ3D wrapping one, types.py:78-87) -> ragged B1 inputs."""
+    import types
+
+    from oracle import featurize as fz
+    from pst.inference_runner import is_padded_graph, padded_graph_to_ragged
+
+    K, N = 50, 512
+    names = ["T1046s1", "T1031", "T1073", "T1082"]
+    gs = []
+    for n in names:
+        e = casp14[n]
+        gs.append(fz.featurize(e["pos"].astype(np.float64), e["gt"], e["exists"], K))
+    padded = [_pad_like_the_reference(g, K, N, 1) for g in gs]
+    batch = {k: np.stack([p[k] for p in padded]).reshape(2, 2, *padded[0][k].shape) for k in padded[0]}  # [Dev=2, B=2, ...]
+    graph = types.SimpleNamespace(**batch)
+    wrapped = types.SimpleNamespace(graph=graph, features={})
+    assert is_padded_graph(batch) and is_padded_graph(graph) and is_padded_graph(wrapped)
+    assert not is_padded_graph([(np.zeros((64, 4, 3), np.float32), None)])
+    for b in (batch, graph, wrapped):
+        lead, n_valid, feats, send, offsets, n_pad = padded_graph_to_ragged(b, K)
+        assert lead == (2, 2) and n_pad == N and n_valid.tolist() == [g["n_node"] for g in gs]
+        assert offsets.tolist() == np.concatenate([[0], np.cumsum(n_valid)]).tolist()
+        assert np.array_equal(feats, np.concatenate([g["edge_features"] for g in gs]).astype(np.float32))
+        assert np.array_equal(send, np.concatenate([g["senders"] for g in gs]))
+    with pytest.raises(ValueError):
+        padded_graph_to_ragged({**batch, "edge_features": batch["edge_features"][..., :26]}, K)
+
+
+def test_sample_file_reader_refuses_foreign_pickles(tmp_path):
+    """A stray .npy in --pdb_dir must not be able to run code: only NumPy's own reconstruction helpers resolve."""
+    import os
+    import pickle
+
+    from pst import pdb as ppdb
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("echo pwned > " + str(tmp_path / "pwned"),))
+
+    bad = tmp_path / "evil.npy"
+    np.save(bad, {"nb_residues": 1, "x": Evil()}, allow_pickle=True)
+    with pytest.raises(pickle.UnpicklingError):
+        ppdb.structure_from_sample_file(str(bad))
+    assert not (tmp_path / "pwned").exists()
+    plain = tmp_path / "plain.npy"
+    np.save(plain, np.zeros((4, 3), np.float32))
+    with pytest.raises(ValueError):
+        ppdb.structure_from_sample_file(str(plain))
+
+
+def test_load_params_names_the_conversion_step_for_released_checkpoints(tmp_path):
+    from pst.config import TokenizerConfig
+    from pst.inference_runner import InferenceRunner
+    from pst.weights import init_params, save_params
+
+    cfg = TokenizerConfig.named(4096, 1)
+    params = init_params(cfg, 0, "spread")
+    released = tmp_path / "released"
+    released.mkdir()
+    np.savez(released / "params.npz", *[params[k] for k in sorted(params)])  # positional leaves arr_0, arr_1, ...
+    with pytest.raises(ValueError, match="params_named.npz"):
+        InferenceRunner.load_params(str(released))
+    save_params(str(released / "params_named.npz"), params)  # what INTEGRATION.md's recipe writes: found first
+    got = InferenceRunner.load_params(str(released))
+    assert sorted(got) == sorted(params) and all(np.array_equal(got[k], params[k]) for k in params)
+    with pytest.raises(FileNotFoundError):
+        InferenceRunner.load_params(str(tmp_path / "nowhere"))
+
+
+def test_alpha_carbon_flag_is_checked():
+    from pst.config import TokenizerConfig, load_config
+
+    cfg = load_config(overrides=["model=gnn/ablation_4k_df_1.yaml", "data=ablation_df_1.yaml"])
+    cfg.data.data["graph_residue_loc_is_alphac"] = False
+    with pytest.raises(NotImplementedError):
+        TokenizerConfig.from_reference_cfg(cfg)
