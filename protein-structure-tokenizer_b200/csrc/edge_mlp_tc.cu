@@ -13,13 +13,14 @@
 //
 // Structure: persistent CTAs (one per SM, 512 threads).  The three 128x128 16-bit weight matrices of
 // the MLP stay resident in shared memory (96 KB, canonical K-major SWIZZLE_128B UMMA layout, image
-// built once at model load).  Four independent "tile groups" of 4 warps each own a 128-edge tile, a
-// 32 KB A-operand buffer and a 128-column fp32 accumulator in TMEM (4 x 128 = all 512 columns); a
-// group runs   [TMA load of e  ||  gather ps[s] + pr[r] -> accumulator]  -> MMA1 -> epilogue1 (GELU, fp32 regs ->
-// 16-bit smem) -> MMA2 -> epilogue2 -> {MMA3 -> TMA re-read of e -> residual + LayerNorm -> TMA store  |
-// row-sum MMA -> partial sums}   serially, and the four groups interleave on the SM so one group's MMA and
-// memory waits overlap the others' epilogues.  In the 32x32b TMEM load layout each thread owns one accumulator
-// row (= one edge), so the LayerNorm and the gathers are thread-local.
+// built once at model load).  A 128-edge tile lives in one of four SLOTS: a 32 KB A-operand buffer and a
+// 128-column fp32 accumulator in TMEM (4 x 128 = all 512 columns).  A PRODUCER warpgroup prepares slots in
+// sequence order   [TMA load of e  ||  gather ps[s] + pr[r] -> accumulator]  -> MMA1,   and three WORK GROUPS of
+// 4 epilogue warps each pick the prepared tiles up round robin and run   epilogue1 (GELU, fp32 regs -> 16-bit
+// smem) -> MMA2 -> epilogue2 -> {MMA3 -> TMA re-read of e -> residual + LayerNorm -> TMA store  |  row-sum MMA ->
+// partial sums}:   with four slots for three groups the load, the gather and the first product of the next tile
+// overlap the epilogues of the three tiles in flight.  In the 32x32b TMEM load layout each thread owns one
+// accumulator row (= one edge), so the LayerNorm and the gathers are thread-local.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -31,13 +32,23 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kD = 128;
 constexpr int kGroups = 4;
-constexpr int kThreads = kGroups * 128;
+constexpr int kThreads = kGroups * 128;      // threads of the tile groups (edge MLP: epilogue warps; embedding kernel: all)
+// edge MLP kernel: four tile SLOTS (A buffer + 128-column accumulator each), three work groups of epilogue warps and one
+// producer warpgroup (warps 12..15, one per TMEM lane quarter)
+constexpr int kSlots = 4;
+constexpr int kWorkGroups = 3;
+constexpr int kMlpThreads = (kWorkGroups + 1) * 128;
+// register split (setmaxnreg): 512 threads launch with 128 registers each; the work groups shrink to 120, the producer
+// warpgroup grows to 152 (3 * 128 * 120 + 128 * 152 = 65 536)
+constexpr int kRegsEpilogue = 120;
+constexpr int kRegsGather = 152;
+static_assert(kSlots == kGroups, "the A buffers and the selection-matrix slots are sized by kGroups");
 constexpr uint32_t kMatBytes = 128 * 128 * 2;  // one 16-bit 128x128 operand image
 constexpr uint32_t kKBlockBytes = 128 * 128;    // 128 rows x 64 elements x 2 B
 constexpr uint32_t kSmemW = 3 * kMatBytes;
 constexpr uint32_t kSmemA = kGroups * kMatBytes;
 constexpr uint32_t kSmemVec = 4 * 128 * sizeof(float) + 64;  // b2, b3, ln scale, ln offset; per-group segment bases
-constexpr uint32_t kSmemMisc = 128;  // MMA mbarriers, TMA mbarriers, TMEM slot
+constexpr uint32_t kSmemMisc = 384;  // MMA, TMA, addend-ready and accumulator-free mbarriers, TMEM slot
 constexpr uint32_t kSmemTotal = kSmemW + kSmemA + kSmemVec + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 
@@ -71,18 +82,28 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
 }
+// Every failed poll of an mbarrier is a shared-memory-class operation on the L1 data pipe (ncu: ~800-1000 SYNCS per tile
+// showed up as that many data-pipe wavefronts, a sixth of the pipe that bounds the edge MLP kernel), so a waiting warp
+// asks the hardware to suspend it (suspend-time hint, ns) and backs off between polls.
+#ifndef PST_MBAR_HINT_NS
+#define PST_MBAR_HINT_NS 2000
+#endif
+#ifndef PST_MBAR_SLEEP_NS
+#define PST_MBAR_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
   uint32_t done;
   do {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"((uint32_t)PST_MBAR_HINT_NS)
         : "memory");
+    if (PST_MBAR_SLEEP_NS > 0 && !done) __nanosleep(PST_MBAR_SLEEP_NS);
   } while (!done);
 }
 // ---- TMA (cp.async.bulk.tensor): the 128 x 128 16-bit edge-state tile moves between HBM and the A buffer as two
@@ -209,8 +230,10 @@ struct Unpack<__nv_bfloat16> {
   static __device__ __forceinline__ float2 two(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
 };
 
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, uint32_t sA_addr, uint32_t sW_addr, uint32_t idesc,
-                                           uint32_t mbar_addr, uint32_t accumulate_first) {
+// Not inlined on purpose: one thread per tile group issues, and inlining lets the compiler hoist the ~60 loop-invariant
+// descriptor words of the three GEMMs into registers of ALL threads (the epilogue warps run with 80 registers).
+__device__ __noinline__ void issue_gemm(uint32_t tmem_acc, uint32_t sA_addr, uint32_t sW_addr, uint32_t idesc,
+                                        uint32_t mbar_addr, uint32_t accumulate_first) {
   tc_fence_after();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {  // K = 128 = 8 x UMMA_K(16); 4 steps per 64-element swizzle block
@@ -245,6 +268,9 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 // matrix are scaled by 0.5 at build time: exact in fp16 / bf16), which saves one packed op per pair.
 constexpr float kActScale = 0.5f;   // what the consumer of G(x) multiplies by
 __device__ __forceinline__ float2 gelu2(float2 x) {
+#ifdef PST_ABL_NOGELU  // timing experiment: no activation math
+  return x;
+#endif
   const float2 x2 = mul2(x, x);
   const float2 p = fma2(x2, make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f));
   const float2 u = mul2(x, p);  // sqrt(2/pi) (x + 0.044715 x^3)
@@ -259,16 +285,24 @@ __device__ __forceinline__ void ldg256(const uint32_t* ptr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "l"(ptr));
 }
-__device__ __forceinline__ uint32_t hadd2u(uint32_t a, uint32_t b) {
-  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
 __device__ __forceinline__ void tmem_ld32v(uint32_t taddr, float2 (&v)[16]) { tmem_ld32(taddr, *reinterpret_cast<float (*)[32]>(&v)); }
 __device__ __forceinline__ void tmem_st32v(uint32_t taddr, const float2 (&v)[16]) { tmem_st32(taddr, *reinterpret_cast<const float (*)[32]>(&v)); }
 
 // 32 consecutive K-elements [k0, k0+32) of `row` -> the group's 16-bit A image (4 x 16 B, swizzled)
 template <typename T16>
 __device__ __forceinline__ void store_a_chunk2(uint8_t* sA, int row, int k0, const float2 (&v)[16]) {
+#ifdef PST_ABL_NOSTS  // timing experiment: one of the four 16-byte stores only
+#pragma unroll
+  for (int c = 0; c < 1; ++c) {
+    uint4 pk;
+    pk.x = Pack<T16>::two(v[0].x + v[4].x + v[8].x + v[12].x, v[0].y + v[4].y + v[8].y + v[12].y);
+    pk.y = Pack<T16>::two(v[1].x + v[5].x + v[9].x + v[13].x, v[1].y + v[5].y + v[9].y + v[13].y);
+    pk.z = Pack<T16>::two(v[2].x + v[6].x + v[10].x + v[14].x, v[2].y + v[6].y + v[10].y + v[14].y);
+    pk.w = Pack<T16>::two(v[3].x + v[7].x + v[11].x + v[15].x, v[3].y + v[7].y + v[11].y + v[15].y);
+    *reinterpret_cast<uint4*>(sA + swz_offset(row, k0 + c * 8)) = pk;
+  }
+  return;
+#endif
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 pk;
@@ -304,6 +338,12 @@ __device__ __forceinline__ void gelu_epilogue(uint32_t tmem_row, uint8_t* sA, in
 #pragma unroll 1
   for (int q = 0; q < 4; ++q) {
     float2 v[16];
+#ifdef PST_ABL_NOLDTM  // timing experiment: one accumulator load per epilogue instead of four
+    if (q > 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = make_float2((float)(gt + c + q) * 0.001f, (float)(gt - c) * 0.002f);
+    } else
+#endif
     tmem_ld32v(tmem_row + q * 32, v);
     gelu_chunk<T16, BIAS>(sA, gt, q, sBias, v);
   }
@@ -331,31 +371,34 @@ __device__ unsigned long long g_edge_prof[2][16];
 #endif
 
 template <typename T16, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams p, const __grid_constant__ CUtensorMap tmap_e) {
+__global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams p, const __grid_constant__ CUtensorMap tmap_e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sAall = smem + kSmemW;
   float* sVec = reinterpret_cast<float*>(smem + kSmemW + kSmemA);                 // b2, b3, ln_s, ln_o [128] each
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemW + kSmemA + 2048 + 64);
-  uint64_t* tbar = mbar + kGroups;  // per group: completion of the TMA loads of the edge-state tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbar + kGroups);
+  uint64_t* tbar = mbar + kSlots;  // per slot: completion of the TMA loads of the edge-state tile
+  uint64_t* abar = tbar + kSlots;  // per slot: the gather warps have preloaded the accumulator (4 arrivals)
+  uint64_t* gbar = abar + kSlots;  // per slot: GEMM 1 (issued by the producer) has completed
+  uint64_t* fbar = gbar + kSlots;  // per slot x lane quarter: the epilogue warp has read its accumulator rows for the last time
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fbar + 4 * kSlots);
+  // Phase parities.  Every barrier completes a fixed number of times per tile of its slot, and a waiter can never be
+  // more than one completion behind: gbar / abar / fbar / (message mode) tbar once, mbar twice (GEMM 2, then GEMM 3 or
+  // the row sums; only the tile's own work group waits on it), (update mode) tbar twice (load, re-read).  GEMM 1 has
+  // its own barrier because a work group may arrive at a slot while the slot's previous tile, owned by another
+  // group, is still between its second and third product: on a shared barrier that phase has the parity it waits for.
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int g = warp >> 2;          // tile group
-  const int gt = tid & 127;         // thread within the group == accumulator row
-  const int wq = warp & 3;          // TMEM lane quarter this warp may access
-  uint8_t* sA = sAall + g * kMatBytes;
-  uint8_t* sSel = sW + 2 * kMatBytes + g * 4096;  // message mode only: the W3 slot is not loaded
   // ---- one-time setup -------------------------------------------------------------------------
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_image);
     uint4* dst = reinterpret_cast<uint4*>(sW);
     const int n16 = (MODE == 0 ? 2 : 3) * (int)(kMatBytes / 16);
-    for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
+    for (int i = tid; i < n16; i += kMlpThreads) dst[i] = src[i];
     if (MODE == 0) {
       uint4* z = reinterpret_cast<uint4*>(sW + 2 * kMatBytes);
-      for (int i = tid; i < (int)(kGroups * 4096 / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < (int)(kSlots * 4096 / 16); i += kMlpThreads) z[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid < 128) {
       sVec[tid] = p.b2[tid];
@@ -365,8 +408,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < kGroups; ++i) mbar_init(smem_u32(&mbar[i]), 1);
-    for (int i = 0; i < kGroups; ++i) mbar_init(smem_u32(&tbar[i]), 1);
+    for (int i = 0; i < kSlots; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+    for (int i = 0; i < kSlots; ++i) mbar_init(smem_u32(&tbar[i]), 1);
+    for (int i = 0; i < kSlots; ++i) mbar_init(smem_u32(&abar[i]), 4);
+    for (int i = 0; i < kSlots; ++i) mbar_init(smem_u32(&gbar[i]), 1);
+    for (int i = 0; i < 4 * kSlots; ++i) mbar_init(smem_u32(&fbar[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -379,237 +425,245 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_acc = tmem_base + (uint32_t)(g * 128);                 // column offset of this group
-  const uint32_t tmem_row = tmem_acc + ((uint32_t)(wq * 32) << 16);          // + lane quarter of this warp
-  const uint32_t sA_addr = smem_u32(sA);
   const uint32_t sW_addr = smem_u32(sW);
-  const uint32_t mbar_addr = smem_u32(&mbar[g]);
-  const uint32_t tbar_addr = smem_u32(&tbar[g]);
-  uint32_t parity = 0, tparity = 0;
-#ifdef PST_EDGE_PROFILE
-  unsigned long long prof_acc[16] = {0};
-  long long prof_last = clock64();
-#endif
-  // this thread's sender row (absolute) for its edge row of the first tile; fetched one tile ahead afterwards
-  int my_sender = 0;
-  {
-    const int t0 = blockIdx.x * kGroups + g;
-    if (t0 < p.num_tiles) my_sender = __ldg(p.senders + min(t0 * kTileM + gt, p.E - 1));
-  }
-  // The sender's row of the fp16 table (256 B, eight 32-byte loads) is fetched ONE TILE AHEAD into registers: the
-  // loads are issued at the end of the previous tile (registers are free there) and their L2 latency (there is no L1
-  // to speak of next to 226 KB of shared memory) hides behind that tile's last MMA / TMA store.
-  uint32_t a[64];
-  {
-    const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)my_sender * kD);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ldg256(psr + i * 8, &a[i * 8]);
-  }
+  // The CTA's tile sequence j = 0, 1, 2, ...: four consecutive tiles per round.  Tile j lives in slot j & 3 (A buffer +
+  // accumulator) and is finished by work group j % 3; validity is monotone in j.
+  const int round_stride = (int)gridDim.x * kSlots;
+  auto tile_of = [&](int j) { return (int)blockIdx.x * kSlots + (j & 3) + (j >> 2) * round_stride; };
 
-  for (int tile = blockIdx.x * kGroups + g; tile < p.num_tiles; tile += gridDim.x * kGroups) {
-    const int row0 = tile * kTileM;
-    const int er = row0 + gt;
-    const int first_recv = row0 / p.K;
-    const int last_row = min(p.E - row0, kTileM);  // valid rows in this tile
+  if (warp >= 4 * kWorkGroups) {
+    // ================================ producer warpgroup =============================================
+    // Warp 12 + q owns TMEM lane quarter q of EVERY slot.  For each tile, in sequence order, each lane reads its
+    // edge's sender row of the fp16 table (h.W1a) and the receiver's row of (h.W1b + b1) (256 B each, eight 32-byte
+    // loads, issued BEFORE the slot's accumulator is free: their L2 latency -- there is no L1 next to 226 KB of shared
+    // memory -- overlaps the slot's previous tile), sums them in fp32 and writes its accumulator row with
+    // tcgen05.st.  Warp 12 then issues GEMM 1 (acc += e . W1[256:384]) as soon as the slot's TMA load has landed, so a
+    // work group that picks the tile up finds the first product done: the load, the gather and GEMM 1 of tile j + 3
+    // overlap the epilogues of tiles j .. j + 2.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsGather));
+    const int q = warp - 4 * kWorkGroups;
+    const int lane = tid & 31;
     const int last_recv = (p.E - 1) / p.K;
-    tc_fence_before();
-    group_sync(g);
-    tc_fence_after();
-    PHASE(0);
-    // ---- 0. The edge-state tile starts moving into the (free) A buffer by TMA; meanwhile
-    //         accumulator row <- (h.W1a)[sender] + (h.W1b + b1)[receiver]  straight from global memory:
-    // each thread owns one edge row (the TMEM 32x32b layout), reads its sender's 256-byte row of the fp16 table
-    // with eight 32-byte loads (whole sectors: the per-thread access is as efficient as a row-coalesced one) and
-    // the receiver's row (shared by K consecutive edges: the lanes of a warp read one or two addresses, a broadcast load
-    // served by L2: next to 226 KB of shared memory there is no L1 to speak of), adds and writes its accumulator row.
-    // No shared-memory staging, no barrier between gather and preload, and the TMA latency hides behind it.
-    // (Measured and rejected: dropping the barrier at the top of the loop and deferring the wait for the previous
-    // tile's TMA store until after the gather: the exposed latency only moves to the wait for the e tile, 0.2 %.)
-    if (gt == 0) {
-      tma_tile_load(sA_addr, &tmap_e, row0, tbar_addr);
-      const int nt = tile + gridDim.x * kGroups;
-      if (nt < p.num_tiles) {  // warm L2 with the next tile's rows
-        tma_prefetch_2d(&tmap_e, 0, nt * kTileM);
-        tma_prefetch_2d(&tmap_e, 64, nt * kTileM);
-      }
+    if (q == 0 && lane == 0) {
+#pragma unroll
+      for (int j = 0; j < kSlots; ++j)
+        if (tile_of(j) < p.num_tiles) tma_tile_load(smem_u32(sAall + j * kMatBytes), &tmap_e, tile_of(j) * kTileM, smem_u32(&tbar[j]));
     }
-    {
-      const uint32_t* prr = reinterpret_cast<const uint32_t*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
+    int tile = tile_of(0);
+    int sender = tile < p.num_tiles ? __ldg(p.senders + min(tile * kTileM + q * 32 + lane, p.E - 1)) : 0;
+    for (int j = 0; tile < p.num_tiles; ++j) {
+      const int s = j & 3;
+      const uint32_t par = (uint32_t)(j >> 2) & 1u;
+      const int er = min(tile * kTileM + q * 32 + lane, p.E - 1);
+      uint32_t a[64], b[64];
       {
-        const int nt = tile + gridDim.x * kGroups;
-        my_sender = nt < p.num_tiles ? __ldg(p.senders + min(nt * kTileM + gt, p.E - 1)) : 0;
-      }
+        const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)sender * kD);
+        const uint32_t* prr = reinterpret_cast<const uint32_t*>(p.pr + (size_t)min(er / p.K, last_recv) * kD);
+#if defined(PST_ABL_NOGATHER_PS)  // timing experiment: one 32-byte load of the sender row instead of eight
+        ldg256(psr, &a[0]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t b[16];
-        ldg256(prr + q * 16, &b[0]);
-        ldg256(prr + q * 16 + 8, &b[8]);
-        float2 v[16];
+        for (int i = 8; i < 64; ++i) a[i] = a[i & 7];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = Unpack<__half>::two(hadd2u(a[q * 16 + c], b[c]));
-        tmem_st32v(tmem_row + q * 32, v);
-      }
-    }
-    tc_fence_before();
-    group_sync(g);
-    PHASE(2);
-    // ---- 1./2. GEMM 1: acc += e . W1[256:384] once the TMA copy of the e tile has landed (rows beyond E are
-    // zero-filled).  Only the issuing thread waits for the copy: the others go straight to the GEMM's barrier.
-    if (gt == 0) {
-      mbar_wait(tbar_addr, tparity);
-      issue_gemm(tmem_acc, sA_addr, sW_addr, p.idesc, mbar_addr, /*accumulate_first=*/1u);
-    }
-    tparity ^= 1;
-    PHASE(3);
-    mbar_wait(mbar_addr, parity);
-    parity ^= 1;
-    tc_fence_after();
-    PHASE(4);
-    // ---- 3. epilogue 1: GELU -> A image ------------------------------------------------------------------
-    gelu_epilogue<T16, false>(tmem_row, sA, gt, sVec);
-    fence_proxy_async();
-    tc_fence_before();
-    group_sync(g);
-    PHASE(5);
-    // ---- 4. GEMM 2 ----------------------------------------------------------------------------------
-    if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + kMatBytes, p.idesc, mbar_addr, 0u);
-    mbar_wait(mbar_addr, parity);
-    parity ^= 1;
-    tc_fence_after();
-    PHASE(6);
-    if (MODE == 1) {
-      // ---- 5a. epilogue 2: + b2, GELU -> A image; GEMM 3; epilogue 3: residual + LayerNorm -------------
-      gelu_epilogue<T16, true>(tmem_row, sA, gt, sVec);
-      fence_proxy_async();
-      tc_fence_before();
-      group_sync(g);
-      PHASE(7);
-      if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + 2 * kMatBytes, p.idesc, mbar_addr, 0u);
-      mbar_wait(mbar_addr, parity);
-      parity ^= 1;
-      tc_fence_after();
-      PHASE(8);
-      // pass 1: x = acc + b3 + e.  The tile is re-read (an L2 hit) by TMA into the free A buffer, in the operand
-      // image layout, so each thread finds its own row conflict-free; statistics; x -> TMEM.
-      if (gt == 0) tma_tile_load(sA_addr, &tmap_e, row0, tbar_addr);
-      mbar_wait(tbar_addr, tparity);
-      tparity ^= 1;
-      PHASE(9);
-      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float2 v[16];
-        tmem_ld32v(tmem_row + q * 32, v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 pk = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
-          const float4 ba = *reinterpret_cast<const float4*>(sVec + 128 + q * 32 + j * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(sVec + 128 + q * 32 + j * 8 + 4);
-          v[j * 4 + 0] = add2(v[j * 4 + 0], add2(Unpack<T16>::two(pk.x), make_float2(ba.x, ba.y)));
-          v[j * 4 + 1] = add2(v[j * 4 + 1], add2(Unpack<T16>::two(pk.y), make_float2(ba.z, ba.w)));
-          v[j * 4 + 2] = add2(v[j * 4 + 2], add2(Unpack<T16>::two(pk.z), make_float2(bb.x, bb.y)));
-          v[j * 4 + 3] = add2(v[j * 4 + 3], add2(Unpack<T16>::two(pk.w), make_float2(bb.z, bb.w)));
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          sum2 = add2(sum2, v[c]);
-          sq2 = fma2(v[c], v[c], sq2);
-        }
-        tmem_st32v(tmem_row + q * 32, v);
-      }
-      PHASE(10);
-      const float mean = (sum2.x + sum2.y) * (1.0f / kD);
-      const float var = fmaxf((sq2.x + sq2.y) * (1.0f / kD) - mean * mean, 0.f);
-      const float inv = rsqrtf(var + 1e-5f);
-      const float2 inv2 = make_float2(inv, inv), nmi2 = make_float2(-mean * inv, -mean * inv);
-      // pass 2: y = ((v - mean) * inv) * scale + offset (two packed fmas per pair) -> 16-bit image of the new edge state
-      // (each thread touches only its own row of the buffer: no barrier between the passes), then a
-      // row-coalesced copy-out.
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float2 v[16];
-        tmem_ld32v(tmem_row + q * 32, v);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 ls = *reinterpret_cast<const float4*>(sVec + 256 + q * 32 + c * 4);
-          const float4 lo = *reinterpret_cast<const float4*>(sVec + 384 + q * 32 + c * 4);
-          v[c * 2] = fma2(fma2(v[c * 2], inv2, nmi2), make_float2(ls.x, ls.y), make_float2(lo.x, lo.y));
-          v[c * 2 + 1] = fma2(fma2(v[c * 2 + 1], inv2, nmi2), make_float2(ls.z, ls.w), make_float2(lo.z, lo.w));
-        }
-        store_a_chunk2<T16>(sA, gt, q * 32, v);
-      }
-      fence_proxy_async();
-      group_sync(g);
-      PHASE(11);
-      {  // next tile's sender row (row 0 when there is none: a valid address, never used)
-        const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)my_sender * kD);
+        for (int i = 0; i < 8; ++i) ldg256(prr + i * 8, &b[i * 8]);
+#elif defined(PST_ABL_NOGATHER_PR)  // timing experiment: one 32-byte load of the receiver row instead of eight
 #pragma unroll
         for (int i = 0; i < 8; ++i) ldg256(psr + i * 8, &a[i * 8]);
-      }
-      if (gt == 0) {  // TMA store of the new edge state (rows beyond E are clipped); the buffer is reused afterwards
-        tma_store_2d(&tmap_e, 0, row0, sA_addr);
-        tma_store_2d(&tmap_e, 64, row0, sA_addr + kKBlockBytes);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-      PHASE(12);
-    } else {
-      // ---- 5b. epilogue 2 (message mode): + b2, GELU, partial sums over the rows of each receiver ------
-      // The activated tile is staged as fp16 in the operand image layout (the precision the third GEMM's operand
-      // has in update mode).  The per-receiver row sums are one more tensor-core product: the staged tile, read
-      // as an MN-major A operand (M = the 128 channels, K = the 128 edge rows: the same bytes, transposed by the
-      // descriptor), times a 0/1 selection matrix Sel^T [N = 16 (4 used) x K = 128 rows] built per tile, gives
-      // D[channel, receiver] in fp32 in 16 TMEM columns; thread = channel reads its 4 sums.
-      gelu_epilogue<__half, true>(tmem_row, sA, gt, sVec);
-      {
-        // Sel^T[s][r] for r = gt: K block r >> 6, row s (128 B each), 16-byte chunk ((r & 63) >> 3) ^ s
-        uint8_t* sel = sSel + (gt >> 6) * 2048 + ((gt & 7) << 1);
-        const int kc = (gt & 63) >> 3;
+        ldg256(prr, &b[0]);
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-          const int lo_u = (first_recv + s4) * p.K - row0;
-          const bool in = gt >= lo_u && gt < lo_u + p.K && gt < last_row;
-          *reinterpret_cast<uint16_t*>(sel + s4 * 128 + ((kc ^ s4) << 4)) = in ? (kActScale == 0.5f ? (uint16_t)0x3800 : (uint16_t)0x3C00) : (uint16_t)0;  // 0.5 or 1.0
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      group_sync(g);
-      if (gt == 0) {
-        tc_fence_after();
-        const uint32_t sel_addr = smem_u32(sSel);
+        for (int i = 8; i < 64; ++i) b[i] = b[i & 7];
+#elif defined(PST_ABL_NOGATHER)  // timing experiment: one 32-byte load per table instead of eight
+        ldg256(psr, &a[0]);
+        ldg256(prr, &b[0]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // 16 edge rows per step: two 8-row atoms of the image (SBO = 1024)
-          umma_f16(tmem_acc, make_smem_desc_mn(sA_addr + j * 2048), make_smem_desc(sel_addr + (j >> 2) * 2048 + (j & 3) * 32),
-                   p.idesc_sum, j > 0 ? 1u : 0u);
-        }
-        umma_commit(mbar_addr);
-      }
-      {  // next tile's sender row (row 0 when there is none: a valid address, never used)
-        const uint32_t* psr = reinterpret_cast<const uint32_t*>(p.ps + (size_t)my_sender * kD);
+        for (int i = 8; i < 64; ++i) { a[i] = a[i & 7]; b[i] = b[i & 7]; }
+#else
 #pragma unroll
         for (int i = 0; i < 8; ++i) ldg256(psr + i * 8, &a[i * 8]);
-      }
-      mbar_wait(mbar_addr, parity);
-      parity ^= 1;
-      tc_fence_after();
-      {
-        float r0, r1, r2, r3;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3) : "r"(tmem_row) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float* dst = p.partial + (size_t)tile * 4 * kD + gt;
-        dst[0] = r0; dst[kD] = r1; dst[2 * kD] = r2; dst[3 * kD] = r3;
-      }
-      group_sync(g);
-      PHASE(13);
-    }
-  }
-#ifdef PST_EDGE_PROFILE
-  if (tid == 0)
-    for (int i = 0; i < 16; ++i) atomicAdd(&g_edge_prof[MODE][i], prof_acc[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ldg256(prr + i * 8, &b[i * 8]);
 #endif
-  if (MODE == 1 && gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the TMA stores have landed
+      }
+      const int ntile = tile_of(j + 1);
+      if (ntile < p.num_tiles) sender = __ldg(p.senders + min(ntile * kTileM + q * 32 + lane, p.E - 1));
+      mbar_wait(smem_u32(&fbar[s * 4 + q]), par ^ 1u);  // the slot's previous tile has left the accumulator rows
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t)(s * 128) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float2 v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = add2(Unpack<__half>::two(a[c4 * 16 + c]), Unpack<__half>::two(b[c4 * 16 + c]));
+#ifdef PST_ABL_NOTMEMST  // timing experiment: one of the four accumulator stores only
+        if (c4 == 0)
+#endif
+        tmem_st32v(trow + c4 * 32, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&abar[s])) : "memory");
+      if (q == 0) {
+        mbar_wait(smem_u32(&abar[s]), par);
+        mbar_wait(smem_u32(&tbar[s]), MODE == 0 ? par : 0u);
+        if (lane == 0)
+          issue_gemm(tmem_base + (uint32_t)(s * 128), smem_u32(sAall + s * kMatBytes), sW_addr, p.idesc, smem_u32(&gbar[s]), 1u);
+        __syncwarp();
+      }
+      tile = ntile;
+    }
+  } else {
+    // ================================ work groups (epilogue warps) ========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
+    const int g = warp >> 2;          // work group
+    const int gt = tid & 127;         // thread within the group == accumulator row
+    const int wq = warp & 3;          // TMEM lane quarter this warp may access
+    for (int j = g; tile_of(j) < p.num_tiles; j += kWorkGroups) {
+      const int s = j & 3;
+      const uint32_t par = (uint32_t)(j >> 2) & 1u;
+      const int tile = tile_of(j);
+      const int row0 = tile * kTileM;
+      const int first_recv = row0 / p.K;
+      const int last_row = min(p.E - row0, kTileM);  // valid rows in this tile
+      uint8_t* sA = sAall + s * kMatBytes;
+      const uint32_t sA_addr = smem_u32(sA);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(s * 128);
+      const uint32_t tmem_row = tmem_acc + ((uint32_t)(wq * 32) << 16);
+      const uint32_t mbar_addr = smem_u32(&mbar[s]);
+      const uint32_t tbar_addr = smem_u32(&tbar[s]);
+      const uint32_t fbar_addr = smem_u32(&fbar[s * 4 + wq]);
+      // ---- 1. GEMM 1 (issued by the producer warpgroup, normally long done) -> epilogue 1: GELU -> A image -------
+      mbar_wait(smem_u32(&gbar[s]), par);
+      tc_fence_after();
+      gelu_epilogue<T16, false>(tmem_row, sA, gt, sVec);
+      fence_proxy_async();
+      tc_fence_before();
+      group_sync(g);
+      // ---- 2. GEMM 2 ----------------------------------------------------------------------------------
+      if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + kMatBytes, p.idesc, mbar_addr, 0u);
+      mbar_wait(mbar_addr, 0u);
+      tc_fence_after();
+      if (MODE == 1) {
+        // ---- 3a. epilogue 2: + b2, GELU -> A image; GEMM 3; epilogue 3: residual + LayerNorm -------------
+        gelu_epilogue<T16, true>(tmem_row, sA, gt, sVec);
+        fence_proxy_async();
+        tc_fence_before();
+        group_sync(g);
+        if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + 2 * kMatBytes, p.idesc, mbar_addr, 0u);
+        mbar_wait(mbar_addr, 1u);
+        tc_fence_after();
+        // pass 1: x = acc + b3 + e.  The tile is re-read (an L2 hit) by TMA into the free A buffer, in the operand
+        // image layout, so each thread finds its own row conflict-free; statistics; x -> TMEM.
+        if (gt == 0) tma_tile_load(sA_addr, &tmap_e, row0, tbar_addr);
+        mbar_wait(tbar_addr, 1u);
+        float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          float2 v[16];
+          tmem_ld32v(tmem_row + q * 32, v);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + jj * 8));
+            const float4 ba = *reinterpret_cast<const float4*>(sVec + 128 + q * 32 + jj * 8);
+            const float4 bb = *reinterpret_cast<const float4*>(sVec + 128 + q * 32 + jj * 8 + 4);
+            v[jj * 4 + 0] = add2(v[jj * 4 + 0], add2(Unpack<T16>::two(pk.x), make_float2(ba.x, ba.y)));
+            v[jj * 4 + 1] = add2(v[jj * 4 + 1], add2(Unpack<T16>::two(pk.y), make_float2(ba.z, ba.w)));
+            v[jj * 4 + 2] = add2(v[jj * 4 + 2], add2(Unpack<T16>::two(pk.z), make_float2(bb.x, bb.y)));
+            v[jj * 4 + 3] = add2(v[jj * 4 + 3], add2(Unpack<T16>::two(pk.w), make_float2(bb.z, bb.w)));
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            sum2 = add2(sum2, v[c]);
+            sq2 = fma2(v[c], v[c], sq2);
+          }
+          tmem_st32v(tmem_row + q * 32, v);
+        }
+        const float mean = (sum2.x + sum2.y) * (1.0f / kD);
+        const float var = fmaxf((sq2.x + sq2.y) * (1.0f / kD) - mean * mean, 0.f);
+        const float inv = rsqrtf(var + 1e-5f);
+        const float2 inv2 = make_float2(inv, inv), nmi2 = make_float2(-mean * inv, -mean * inv);
+        // pass 2: y = ((v - mean) * inv) * scale + offset (two packed fmas per pair) -> 16-bit image of the new edge state
+        // (each thread touches only its own row of the buffer: no barrier between the passes)
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          float2 v[16];
+          tmem_ld32v(tmem_row + q * 32, v);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 ls = *reinterpret_cast<const float4*>(sVec + 256 + q * 32 + c * 4);
+            const float4 lo = *reinterpret_cast<const float4*>(sVec + 384 + q * 32 + c * 4);
+            v[c * 2] = fma2(fma2(v[c * 2], inv2, nmi2), make_float2(ls.x, ls.y), make_float2(lo.x, lo.y));
+            v[c * 2 + 1] = fma2(fma2(v[c * 2 + 1], inv2, nmi2), make_float2(ls.z, ls.w), make_float2(lo.z, lo.w));
+          }
+          store_a_chunk2<T16>(sA, gt, q * 32, v);
+        }
+        // this warp has read its accumulator rows for the last time: the producer may preload the slot's next tile
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fbar_addr) : "memory");
+        fence_proxy_async();
+        group_sync(g);
+        if (gt == 0) {  // TMA store of the new edge state (rows beyond E are clipped), then the slot's next tile comes in
+          tma_store_2d(&tmap_e, 0, row0, sA_addr);
+          tma_store_2d(&tmap_e, 64, row0, sA_addr + kKBlockBytes);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          const int nt = tile_of(j + kSlots);
+          if (nt < p.num_tiles) tma_tile_load(sA_addr, &tmap_e, nt * kTileM, tbar_addr);
+        }
+      } else {
+        // ---- 3b. epilogue 2 (message mode): + b2, GELU, partial sums over the rows of each receiver ------
+        // The activated tile is staged as fp16 in the operand image layout (the precision the third GEMM's operand
+        // has in update mode).  The per-receiver row sums are one more tensor-core product: the staged tile, read
+        // as an MN-major A operand (M = the 128 channels, K = the 128 edge rows: the same bytes, transposed by the
+        // descriptor), times a 0/1 selection matrix Sel^T [N = 16 (4 used) x K = 128 rows] built per tile, gives
+        // D[channel, receiver] in fp32 in 16 TMEM columns; thread = channel reads its 4 sums.
+        uint8_t* sSel = sW + 2 * kMatBytes + s * 4096;  // the W3 slot is not loaded in this mode
+        gelu_epilogue<__half, true>(tmem_row, sA, gt, sVec);
+        {
+          // Sel^T[s][r] for r = gt: K block r >> 6, row s (128 B each), 16-byte chunk ((r & 63) >> 3) ^ s
+          uint8_t* sel = sSel + (gt >> 6) * 2048 + ((gt & 7) << 1);
+          const int kc = (gt & 63) >> 3;
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int lo_u = (first_recv + s4) * p.K - row0;
+            const bool in = gt >= lo_u && gt < lo_u + p.K && gt < last_row;
+            *reinterpret_cast<uint16_t*>(sel + s4 * 128 + ((kc ^ s4) << 4)) = in ? (kActScale == 0.5f ? (uint16_t)0x3800 : (uint16_t)0x3C00) : (uint16_t)0;  // 0.5 or 1.0
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        group_sync(g);
+        if (gt == 0) {
+          tc_fence_after();
+          const uint32_t sel_addr = smem_u32(sSel);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {  // 16 edge rows per step: two 8-row atoms of the image (SBO = 1024)
+            umma_f16(tmem_acc, make_smem_desc_mn(sA_addr + jj * 2048), make_smem_desc(sel_addr + (jj >> 2) * 2048 + (jj & 3) * 32),
+                     p.idesc_sum, jj > 0 ? 1u : 0u);
+          }
+          umma_commit(mbar_addr);
+        }
+        mbar_wait(mbar_addr, 1u);
+        tc_fence_after();
+        if (gt == 0) {  // the row-sum product has read the A buffer: the slot's next tile comes in
+          const int nt = tile_of(j + kSlots);
+          if (nt < p.num_tiles) tma_tile_load(sA_addr, &tmap_e, nt * kTileM, tbar_addr);
+        }
+        {
+          float r0, r1, r2, r3;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3) : "r"(tmem_row) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // last TMEM read of the tile: the producer may preload the slot's next tile
+          tc_fence_before();
+          __syncwarp();
+          if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fbar_addr) : "memory");
+          float* dst = p.partial + (size_t)tile * 4 * kD + gt;
+          dst[0] = r0; dst[kD] = r1; dst[2 * kD] = r2; dst[3 * kD] = r3;
+        }
+      }
+    }
+    if (MODE == 1 && gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the TMA stores have landed
+  }
 
   tc_fence_before();
   __syncthreads();
@@ -1006,12 +1060,12 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   const int need = (p.num_tiles + kGroups - 1) / kGroups;
   if (grid > need) grid = need;
   if (mode == 0) {
-    if (half) edge_mlp_tc_kernel<__half, 0><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
-    else edge_mlp_tc_kernel<__nv_bfloat16, 0><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
+    if (half) edge_mlp_tc_kernel<__half, 0><<<grid, kMlpThreads, kSmemTotal, st>>>(p, tmap);
+    else edge_mlp_tc_kernel<__nv_bfloat16, 0><<<grid, kMlpThreads, kSmemTotal, st>>>(p, tmap);
     return 1;  // the fused node kernel (node_chain_tc.cu) sums the partial rows of each receiver
   }
-  if (half) edge_mlp_tc_kernel<__half, 1><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
-  else edge_mlp_tc_kernel<__nv_bfloat16, 1><<<grid, kThreads, kSmemTotal, st>>>(p, tmap);
+  if (half) edge_mlp_tc_kernel<__half, 1><<<grid, kMlpThreads, kSmemTotal, st>>>(p, tmap);
+  else edge_mlp_tc_kernel<__nv_bfloat16, 1><<<grid, kMlpThreads, kSmemTotal, st>>>(p, tmap);
   return 1;
 }
 
