@@ -152,10 +152,17 @@ __device__ __forceinline__ void st256u(void* ptr, const uint32_t* r) {
                : "memory");
 }
 
+// Round 2, measured as a same-box A/B (profiles/r02_edge/README.md is the edge kernel's log; this one: gpurun_out/r2b, r2d):
+// the GELU of the 512-wide FFN hidden layer written with ex2 + rcp was 41 % of node_update_kernel's instructions.  One
+// MUFU.TANH (relative error ~2^-11, what the edge MLP's GELU uses; the result is split into fp16 hi / lo operand images
+// right after) and reciprocal multiplies for the two per-row divisions: node updates 0.95 -> 0.81 ms, resampler + head
+// 0.87 -> 0.78 ms per step, token agreement with the fp32 mode unchanged (99.9611 % of 131 072).  -DPST_NODE_EXACT_MATH
+// restores the round-1 arithmetic.
+#ifndef PST_NODE_EXACT_MATH
+#define PST_NODE_GELU_APPROX 1
+#define PST_NODE_RECIP_MUL 1
+#endif
 #ifdef PST_NODE_GELU_APPROX
-// EXPERIMENT, off by default and not yet measured or tolerance-tested on a GPU: one MUFU.TANH
-// (relative error ~2^-11, what the edge MLP's GELU uses) instead of ex2 + rcp; build with
-// tools/build_variant.sh nodegelu node_chain_tc.cu -DPST_NODE_GELU_APPROX and compare with tools/variant_run.sh
 __device__ __forceinline__ float tanh_fast(float u) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
 #pragma unroll
       for (int q = 0; q < 2; ++q)
 #pragma unroll
-#ifdef PST_NODE_RECIP_MUL  // EXPERIMENT (off, not yet run on a GPU): reciprocal multiply instead of IEEE division
+#ifdef PST_NODE_RECIP_MUL  // reciprocal multiply instead of IEEE division (see the note at tanh_fast)
         for (int j = 0; j < 32; ++j) x[q][j] = x[q][j] * (1.0f / kf);
 #else
         for (int j = 0; j < 32; ++j) x[q][j] = x[q][j] / kf;

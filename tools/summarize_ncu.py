@@ -10,7 +10,10 @@ import subprocess
 import sys
 
 KEYS = [
-    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__time_duration.sum", "sm__cycles_elapsed.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
@@ -80,8 +83,36 @@ def full(src, dst):
             fh.write("\nwarp stall samples: " + ", ".join(f"{n} {v / tot * 100:.0f}%" for v, n in sorted(st, reverse=True)[:8]) + "\n\n")
 
 
+def traffic(src, dst, residues):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the two edge-MLP kernels -> the JSON bench.py reads
+    (`roofline.traffic`); `residues` = the batch the capture ran on."""
+    import json
+
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        if "edge_mlp_tc_kernel" not in name:
+            continue
+        key = "msg" if ", 0>" in name or "(int)0>" in name else "upd"
+        tot = sum(float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        out.setdefault(key, []).append(tot)
+    doc = {k: sum(v) / len(v) for k, v in out.items()}
+    doc["residues"] = int(residues)
+    doc["source"] = f"ncu --set full --clock-control none, {src} (dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled to this batch)"
+    with open(dst, "w") as fh:
+        json.dump(doc, fh, indent=1)
+    print(doc)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else None)
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 131072)
     else:
         full(sys.argv[2], sys.argv[3])

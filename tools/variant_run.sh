@@ -4,7 +4,7 @@ tag=$1; shift
 for v in "$@"; do
   lib=$PWD/protein-structure-tokenizer_b200/pst/libpst_b200_$v.so
   [ "$v" = "main" ] && lib=$PWD/protein-structure-tokenizer_b200/pst/libpst_b200.so
-  PST_LIB_PATH=$lib python bench.py --no-cpu-baseline --steps 10 > gpurun_out/${tag}_$v.json 2> gpurun_out/${tag}_$v.err || tail -5 gpurun_out/${tag}_$v.err
+  PST_LIB_PATH=$lib python bench.py --no-cpu-baseline --sustained-steps 0 --steps 10 > gpurun_out/${tag}_$v.json 2> gpurun_out/${tag}_$v.err || tail -5 gpurun_out/${tag}_$v.err
   python - <<PY
 import json
 try:
