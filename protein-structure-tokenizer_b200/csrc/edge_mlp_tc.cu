@@ -24,6 +24,7 @@
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cstdio>
 
 #include "pst_internal.h"
 
@@ -35,6 +36,7 @@ constexpr int kGroups = 4;
 constexpr int kThreads = kGroups * 128;      // threads of the tile groups (edge MLP: epilogue warps; embedding kernel: all)
 // edge MLP kernel: four tile SLOTS (A buffer + 128-column accumulator each), three work groups of epilogue warps and one
 // producer warpgroup (warps 12..15, one per TMEM lane quarter)
+constexpr int kImagesPerMlp = 4;  // operand images per MLP in pst_model::tc: W1[256:384], W2, W3, W1[0:128]
 constexpr int kSlots = 4;
 constexpr int kWorkGroups = 3;
 constexpr int kMlpThreads = (kWorkGroups + 1) * 128;
@@ -286,6 +288,31 @@ __device__ __forceinline__ void ldg256(const uint32_t* ptr, uint32_t* r) {
                : "l"(ptr));
 }
 __device__ __forceinline__ void tmem_ld32v(uint32_t taddr, float2 (&v)[16]) { tmem_ld32(taddr, *reinterpret_cast<float (*)[32]>(&v)); }
+// The same load in two halves, so that the next chunk's load is in flight while the current chunk is computed: the wait
+// names the registers as in/out operands, which keeps every use of them behind it.
+__device__ __forceinline__ void tmem_ld32v_issue(uint32_t taddr, float2 (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(&v[0]);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(float2 (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(&v[0]);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st32v(uint32_t taddr, const float2 (&v)[16]) { tmem_st32(taddr, *reinterpret_cast<const float (*)[32]>(&v)); }
 
 // 32 consecutive K-elements [k0, k0+32) of `row` -> the group's 16-bit A image (4 x 16 B, swizzled)
@@ -673,6 +700,345 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Message MLP, TRANSPOSED formulation (round 2; fp16 operands, even K >= 43).
+//
+// The kernel above computes  D[edge, channel] = X . W  with the edges on the accumulator rows.  Its limit is the L1 /
+// shared-memory data pipe (profiles/r02_edge/README.md): addend rows gathered through registers, bias / receiver vectors,
+// a selection matrix and one more product for the row sums.  Here every product is transposed,
+//     D^T[channel, edge] = W^T . X^T        (A = the weight image [n][k], exactly the B image of the kernel above;
+//                                            B = the edge-level operand),
+// so that a thread owns one CHANNEL (accumulator row = TMEM lane) and walks along the edges (columns):
+//   * sender term     (h.W1a)[s]   = one more product: the fp16 `h` rows of the senders are gathered by 16-byte
+//                                    cp.async copies into a K-major B operand image and multiplied by W1a^T on the
+//                                    tensor core: no register gather, no tcgen05.st;
+//   * receiver term   (h.W1b+b1)[r] = a per-thread scalar per receiver (at most 4 receivers per 128-edge tile), added in
+//                                    epilogue 1; b2 is a per-thread scalar as well: no bias vectors in shared memory;
+//   * the activations of epilogue 1 are stored thread-per-row (row = channel) and read as an MN-major B operand;
+//   * the per-receiver sums over the K edges are sums over column ranges of a thread's own row: no selection matrix, no
+//     row-sum product, no activation store in epilogue 2.
+// Operand traffic per tile: 16 x 16 KB of tensor-core operand reads and ONE 32 KB activation store (before: 2 940 LSU +
+// 1 310 operand wavefronts).  Structure: a ring of four 16 KB stages (H k-blocks 0 / 1, E k-blocks 0 / 1) filled by a
+// two loader warps, an MMA warp that runs the first two products (sender + edge term) of the next tiles into one of four
+// 128-column accumulator slots while four work groups (4 epilogue warps each) finish 64-edge HALF tiles: second product
+// with N = 64 on the group's own [128 x 64] activation image, partial sums per half tile.
+constexpr int kTWorkGroups = 4;  // 4 warps each; a group finishes one 64-edge HALF tile at a time
+constexpr int kTThreads = 640;   // warps 0-15: the work groups; warps 16, 18: loaders; warp 17: MMA issuer; warp 19: idle
+constexpr int kTStages = 4;
+constexpr int kTAccSlots = 4;    // 128-column accumulators (one per 128-edge tile)
+constexpr uint32_t kTSmemW = 3 * kMatBytes;                    // W1a, W1c, W2 images
+constexpr uint32_t kTSmemRing = kTStages * kKBlockBytes;       // 4 x [128 rows x 64 k] operand blocks
+constexpr uint32_t kTSmemAct = kTWorkGroups * kKBlockBytes;    // one [128 channels x 64 edges] activation image per work group
+constexpr uint32_t kTSmemMisc = 256;
+constexpr uint32_t kTSmemTotal = kTSmemW + kTSmemRing + kTSmemAct + kTSmemMisc;
+static_assert(kTSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+
+#ifdef PST_T_PROFILE  // per-role cycle accounting, printed by block 0 (debug builds only)
+#define TPROF_DECL long long tp_last = clock64(); long long tp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TPROF(i) do { long long _t = clock64(); tp_acc[i] += _t - tp_last; tp_last = _t; } while (0)
+#define TPROF_PRINT(name) do { if (blockIdx.x == 0 && lane == 0) printf("%s warp %d: %lld %lld %lld %lld %lld %lld %lld %lld\n", name, warp, \
+    tp_acc[0], tp_acc[1], tp_acc[2], tp_acc[3], tp_acc[4], tp_acc[5], tp_acc[6], tp_acc[7]); } while (0)
+#else
+#define TPROF_DECL do {} while (0)
+#define TPROF(i) do {} while (0)
+#define TPROF_PRINT(name) do {} while (0)
+#endif
+
+struct MsgTParams {
+  const uint16_t* w1a_image;  // W1[0:128]   image (32 KB)
+  const uint16_t* w_image;    // W1[256:384], W2 images (2 x 32 KB; W2 pre-scaled by 0.5, see gelu2)
+  const float* b2;
+  const __half* pr;           // [R,128] fp16  (h.W1b + b1)
+  const __half* h16;          // [R,128] fp16 node state (gathered by sender)
+  const int32_t* senders;     // [E] ABSOLUTE sender rows
+  float* partial;             // [num_tiles][4][128] per-receiver partial row sums of the 2nd hidden layer
+  int E, K, R, num_tiles;
+  uint32_t idesc;             // A, B K-major
+  uint32_t idesc_bmn;         // A K-major, B MN-major
+};
+
+__global__ void __launch_bounds__(kTThreads, 1) edge_msg_t_kernel(MsgTParams p, const __grid_constant__ CUtensorMap tmap_e) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sRing = smem + kTSmemW;
+  uint8_t* sAct = smem + kTSmemW + kTSmemRing;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kTSmemW + kTSmemRing + kTSmemAct);  // per stage: operand block landed
+  uint64_t* empty = full + kTStages;     // per stage: the products that read it have completed
+  uint64_t* gbar = empty + kTStages;     // per accumulator slot: sender + edge products done
+  uint64_t* fbar = gbar + kTAccSlots;    // per accumulator slot: both work groups have read it for the last time (8 warps)
+  uint64_t* mbar = fbar + kTAccSlots;    // per work group x quarter: second product done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * kTWorkGroups);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  {
+    const uint4* src_a = reinterpret_cast<const uint4*>(p.w1a_image);
+    const uint4* src = reinterpret_cast<const uint4*>(p.w_image);
+    uint4* dst = reinterpret_cast<uint4*>(sW);
+    for (int i = tid; i < (int)(kMatBytes / 16); i += kTThreads) dst[i] = src_a[i];
+    for (int i = tid; i < (int)(2 * kMatBytes / 16); i += kTThreads) dst[kMatBytes / 16 + i] = src[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kTStages; ++i) { mbar_init(smem_u32(&full[i]), i < 2 ? 64 : 1); mbar_init(smem_u32(&empty[i]), 1); }
+    for (int i = 0; i < kTAccSlots; ++i) { mbar_init(smem_u32(&gbar[i]), 1); mbar_init(smem_u32(&fbar[i]), 8); }
+    for (int i = 0; i < 2 * kTWorkGroups; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sW_addr = smem_u32(sW);
+  const uint32_t ring_addr = smem_u32(sRing);
+  auto tile_of = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
+
+  if (warp == 16 || warp == 18) {
+    // ================================ loader warps ===================================================
+    // per tile: the sender rows of fp16 `h` -> stages 0 / 1 (the two k-blocks of a [128 x 128] K-major SWIZZLE_128B
+    // image) by 16-byte cp.async copies, sixteen lanes per 256-byte row (two rows per warp instruction: whole lines on
+    // the L2 side, no registers in flight, each lane computes its swizzled destination; TMA tile::gather4 moves one
+    // 128-byte row segment per ~16 cycles per SM, 4 000 cycles per tile: measured, profiles/r02_edge), warp 16 the tile's
+    // rows 0..63, warp 18 rows 64..127; warp 16 also loads the edge-state tile -> stages 2 / 3 by TMA.
+    const int lw = (warp - 16) >> 1;     // 0 / 1: which 64 rows
+    const int max_row = p.R - 1;
+    auto load_idx = [&](int tile_) {  // sender rows of this warp's rows 2 lane, 2 lane + 1
+      int2 v = make_int2(0, 0);
+      if (tile_ < p.num_tiles) {
+        v = __ldg(reinterpret_cast<const int2*>(p.senders + (size_t)tile_ * kTileM + lw * 64 + lane * 2));  // the workspace pads the array
+        v.x = min(max(v.x, 0), max_row); v.y = min(max(v.y, 0), max_row);  // rows beyond E hold anything: any valid row will do
+      }
+      return v;
+    };
+    const int half = lane >> 4;          // which of the instruction's two rows
+    const int chunk = lane & 15;         // 16-byte chunk of the row
+    const uint32_t dst_lane = ring_addr + (uint32_t)(chunk >> 3) * kKBlockBytes;  // k-block = stage
+    int tile = tile_of(0);
+    int2 idx = load_idx(tile);
+    TPROF_DECL;
+    for (int j = 0; tile < p.num_tiles; ++j) {
+      const uint32_t ph = (uint32_t)j & 1u;
+      TPROF(0);
+      mbar_wait(smem_u32(&empty[0]), ph ^ 1u);
+      mbar_wait(smem_u32(&empty[1]), ph ^ 1u);
+      TPROF(1);  // waiting for the H stages
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {  // rows 2 i, 2 i + 1 of this warp's 64: their indices sit in lane i
+        const int ia = __shfl_sync(0xffffffffu, idx.x, i);
+        const int ib = __shfl_sync(0xffffffffu, idx.y, i);
+        const int r = lw * 64 + 2 * i + half;
+        const __half* src = p.h16 + (size_t)(half ? ib : ia) * kD + chunk * 8;
+        const uint32_t dst = dst_lane + (uint32_t)r * 128u + ((uint32_t)((chunk & 7) ^ (r & 7)) << 4);
+#ifdef PST_ABL_T_NOGATHER  // timing experiment: one copy in eight
+        if ((i & 7) == 0)
+#endif
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+      // both stages complete when every lane's copies have landed (the barriers expect 2 x 32 arrivals)
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[0])) : "memory");
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[1])) : "memory");
+      TPROF(2);  // issuing the gather
+      if (lw == 0) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(smem_u32(&empty[2 + kb]), ph ^ 1u);
+          if (lane == 0) {
+            mbar_expect_tx(smem_u32(&full[2 + kb]), kKBlockBytes);
+            tma_load_2d(ring_addr + (2 + kb) * kKBlockBytes, &tmap_e, kb * 64, tile * kTileM, smem_u32(&full[2 + kb]));
+          }
+        }
+      }
+      TPROF(3);  // waiting for the E stages + issuing their loads
+      tile = tile_of(j + 1);
+      idx = load_idx(tile);
+    }
+    TPROF_PRINT("loader [-, wait H stages, issue gather, wait + issue E, ...]");
+  } else if (warp == 17) {
+    // ================================ MMA warp ========================================================
+    // D^T = W1a^T . H_s^T + W1c^T . E^T  into the tile's accumulator slot, one operand block (4 k-steps) at a time
+    TPROF_DECL;
+    for (int j = 0; tile_of(j) < p.num_tiles; ++j) {
+      const int slot = j % kTAccSlots;
+      const uint32_t acc = tmem_base + (uint32_t)(slot * 128);
+      TPROF(0);
+      mbar_wait(smem_u32(&fbar[slot]), ((uint32_t)(j / kTAccSlots) & 1u) ^ 1u);  // the slot's previous tile has been read
+      TPROF(1);  // waiting for a free accumulator slot
+      tc_fence_after();
+#pragma unroll
+      for (int st = 0; st < kTStages; ++st) {
+        mbar_wait(smem_u32(&full[st]), (uint32_t)j & 1u);
+        TPROF(2 + st);  // waiting for stage st (+ issuing the previous stage's products)
+        if (st < 2) fence_proxy_async();  // the cp.async copies are generic-proxy writes; the tensor core reads through the async proxy
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t wblk = sW_addr + (st < 2 ? 0u : kMatBytes) + (uint32_t)(st & 1) * kKBlockBytes;
+          const uint32_t xblk = ring_addr + (uint32_t)st * kKBlockBytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(acc, make_smem_desc(wblk + ks * 32), make_smem_desc(xblk + ks * 32), p.idesc, (st | ks) ? 1u : 0u);
+          umma_commit(smem_u32(&empty[st]));
+          if (st == kTStages - 1) umma_commit(smem_u32(&gbar[slot]));
+        }
+        __syncwarp();
+#ifndef PST_T_NO_PACING
+        // Pacing: the tensor pipe runs the products of all issuers in order, and the work groups' second products are on
+        // their critical path while these are a tile or two ahead.  Never more than one operand block (4 k-steps,
+        // 256 cycles) of look-ahead work is queued in front of them.
+        mbar_wait(smem_u32(&empty[st]), (uint32_t)j & 1u);
+#endif
+      }
+    }
+    TPROF_PRINT("mma [-, wait slot, wait stage 0, 1, 2, 3]");
+  } else if (warp < 16) {
+    // ================================ work groups (epilogue warps) ========================================
+    // Group g (4 warps, warp w owns TMEM lane quarter w & 3 = 32 output channels) finishes the 64-edge half
+    // (g & 1) of the tiles j = g >> 1, (g >> 1) + 2, ...: four independent half tiles in flight per SM, one warp of each on
+    // every SM sub-partition, so that the MUFU-bound epilogues of some overlap the tensor-core waits of the others.
+    // A thread = one channel x 64 edges.
+    const int g = warp >> 2;
+    const int wq = warp & 3;
+    const int hf = g & 1;
+    const int gt = wq * 32 + lane;    // output channel == accumulator row
+    uint8_t* act = sAct + g * kKBlockBytes;
+    const uint32_t act_addr = smem_u32(act);
+    const uint32_t mbar_addr = smem_u32(&mbar[2 * g]);
+    const float b2m = __ldg(p.b2 + gt);
+    const int last_recv = (p.E - 1) / p.K;
+    uint32_t mparity = 0;
+    // receiver-term scalars of the half tile (fp16 table; at most 3 receivers in 64 edges), fetched one ahead
+    __half prn[3];
+    auto load_pr = [&](int tile_, __half (&out)[3]) {
+      if (tile_ < p.num_tiles) {
+        const int fr = (tile_ * kTileM + hf * 64) / p.K;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[i] = __ldg(p.pr + (size_t)min(fr + i, last_recv) * kD + gt);
+      }
+    };
+    load_pr(tile_of(g >> 1), prn);
+    TPROF_DECL;
+    for (int j = g >> 1; tile_of(j) < p.num_tiles; j += 2) {
+      TPROF(0);
+      const int slot = j % kTAccSlots;
+      const int tile = tile_of(j);
+      const int u0 = tile * kTileM + hf * 64;          // first edge of the half tile
+      const int first_recv = u0 / p.K;
+      const int last_row = min(p.E - u0, 64);          // valid columns (<= 0: none)
+      const uint32_t trow = tmem_base + (uint32_t)(slot * 128 + hf * 64) + ((uint32_t)(wq * 32) << 16);
+      // column (relative to the half tile) where receiver slot i starts: b1 < b2; slot 0 starts at or before column 0;
+      // both even (K and 64 are)
+      const int b1 = (first_recv + 1) * p.K - u0, b2c = b1 + p.K;
+      const float pr0 = __half2float(prn[0]), pr1 = __half2float(prn[1]), pr2 = __half2float(prn[2]);
+      load_pr(tile_of(j + 2), prn);
+      // ---- epilogue 1: x = acc + receiver term -> G(x) -> activation image (row = channel, columns = edges) ----------
+      mbar_wait(smem_u32(&gbar[slot]), (uint32_t)(j / kTAccSlots) & 1u);
+      TPROF(1);  // waiting for the first two products
+      tc_fence_after();
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const int c0 = qq * 32;
+        float2 v[16];
+        tmem_ld32v(trow + c0, v);
+        const int i0 = (c0 >= b1) + (c0 >= b2c);
+        const float pa = i0 == 0 ? pr0 : i0 == 1 ? pr1 : pr2;
+        const float pb = i0 == 0 ? pr1 : pr2;
+        const int t = (i0 == 0 ? b1 : i0 == 1 ? b2c : 1 << 20) - c0;  // columns of this chunk before the next receiver
+        if (t >= 32) {
+          const float2 pp = make_float2(pa, pa);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = gelu2(add2(v[c], pp));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float pc = 2 * c < t ? pa : pb;
+            v[c] = gelu2(add2(v[c], make_float2(pc, pc)));
+          }
+        }
+        store_a_chunk2<__half>(act, gt, c0, v);
+      }
+      TPROF(2);  // epilogue 1
+      fence_proxy_async();
+      tc_fence_before();
+      group_sync(g);
+      TPROF(3);  // group barrier
+      // ---- second product: D^T[:, half] = W2^T . act1 (B = the activation image read MN-major, N = 64) ----------------
+      if ((warp & 3) == 0 && lane == 0) {
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(slot * 128 + hf * 64);
+        const uint32_t w2 = sW_addr + 2 * kMatBytes;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_f16(acc, make_smem_desc(w2 + (ks >> 2) * kKBlockBytes + (ks & 3) * 32), make_smem_desc_mn(act_addr + ks * 2048),
+                   p.idesc_bmn, ks > 0 ? 1u : 0u);
+        umma_commit(mbar_addr);
+      }
+      mbar_wait(mbar_addr, mparity);
+      mparity ^= 1;
+      TPROF(4);  // second product
+      tc_fence_after();
+      // ---- epilogue 2: + b2, G, sums over the columns of each receiver (thread-local) ------------------------------
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const int c0 = qq * 32;
+        float2 v[16];
+        tmem_ld32v(trow + c0, v);
+        const float2 bb = make_float2(b2m, b2m);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = gelu2(add2(v[c], bb));
+        if (c0 + 32 > last_row) {  // last tile only: columns beyond E do not exist
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            if (c0 + 2 * c >= last_row) v[c].x = 0.f;
+            if (c0 + 2 * c + 1 >= last_row) v[c].y = 0.f;
+          }
+        }
+        const int i0 = (c0 >= b1) + (c0 >= b2c);
+        const int t = (i0 == 0 ? b1 : i0 == 1 ? b2c : 1 << 20) - c0;
+        float2 sa2 = make_float2(0.f, 0.f), sb2 = make_float2(0.f, 0.f);
+        if (t >= 32) {
+          float2 sc2 = make_float2(0.f, 0.f), sd2 = make_float2(0.f, 0.f), se2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {  // four independent chains
+            sa2 = add2(sa2, v[c]); sc2 = add2(sc2, v[c + 1]); sd2 = add2(sd2, v[c + 2]); se2 = add2(se2, v[c + 3]);
+          }
+          sa2 = add2(add2(sa2, sc2), add2(sd2, se2));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            if (2 * c < t) sa2 = add2(sa2, v[c]);
+            else sb2 = add2(sb2, v[c]);
+          }
+        }
+        const float sa = sa2.x + sa2.y, sb = sb2.x + sb2.y;
+        if (i0 == 0) { s0 += sa; s1 += sb; }
+        else if (i0 == 1) { s1 += sa; s2 += sb; }
+        else s2 += sa;
+      }
+      TPROF(5);  // epilogue 2
+      // last TMEM read of the half tile: when both halves are through, the MMA warp may reuse the slot
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fbar[slot])) : "memory");
+      float* dst = p.partial + ((size_t)tile * 2 + hf) * 4 * kD + gt;  // [64-edge half tile][receiver slot][channel]
+      dst[0] = kActScale * s0; dst[kD] = kActScale * s1; dst[2 * kD] = kActScale * s2;
+      TPROF(6);
+    }
+    TPROF_PRINT("work [-, wait products 1+2, epilogue 1, barrier, product 3, epilogue 2, store]");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Input edge embedding on the tensor cores (reference: structure_tokenizer/model/structure_encoder.py:94-105):
 //   e0 = PE_edge(s - r) . W[0:128] + b  (a constant table row, folded at weight-pack time)  +  f27 . W[128:155]
 // Per 128-edge tile: the 27 features are read as one contiguous coalesced block, split into fp16 hi/lo
@@ -959,20 +1325,22 @@ extern "C" int pst_debug_edge_profile(unsigned long long* out32, int reset) {
 
 int pst_prepare_tc_weights(pst_model* m) {
   const int layers = m->cfg.gnn_layers;
-  const size_t per_mlp = 3 * (size_t)kMatBytes;
+  const size_t per_mlp = kImagesPerMlp * (size_t)kMatBytes;  // W1[256:384], W2, W3, W1[0:128]
   const size_t total = (size_t)layers * 2 * per_mlp;
   if (cudaMalloc(&m->tc_dev, total) != cudaSuccess) return PST_ERR_CUDA;
   m->tc.w = m->tc_dev;
   for (int l = 0; l < layers; ++l) {
     const PstLayerW& L = m->w.layer[l];
-    const float* src[2][3] = {{L.msg_w1 + 2 * kD * kD, L.msg_w2, L.msg_w3}, {L.edge_w1 + 2 * kD * kD, L.edge_w2, L.edge_w3}};
+    const float* src[2][kImagesPerMlp] = {{L.msg_w1 + 2 * kD * kD, L.msg_w2, L.msg_w3, L.msg_w1},
+                                          {L.edge_w1 + 2 * kD * kD, L.edge_w2, L.edge_w3, L.edge_w1}};
     for (int t = 0; t < 2; ++t)
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < kImagesPerMlp; ++j) {
         uint16_t* dst = m->tc_dev + ((size_t)(l * 2 + t) * per_mlp + (size_t)j * kMatBytes) / 2;
+        const float scale = (j == 1 || j == 2) ? kActScale : 1.0f;  // the consumers of G(x) = 2 gelu(x)
         if (m->cfg.precision == PST_PREC_FP16)
-          build_weight_image_kernel<__half><<<64, 256>>>(src[t][j], dst, j > 0 ? kActScale : 1.0f);
+          build_weight_image_kernel<__half><<<64, 256>>>(src[t][j], dst, scale);
         else
-          build_weight_image_kernel<__nv_bfloat16><<<64, 256>>>(src[t][j], dst, j > 0 ? kActScale : 1.0f);
+          build_weight_image_kernel<__nv_bfloat16><<<64, 256>>>(src[t][j], dst, scale);
       }
   }
   {
@@ -988,6 +1356,7 @@ int pst_prepare_tc_weights(pst_model* m) {
       return PST_ERR_CUDA;
   }
   if (cudaGetLastError() != cudaSuccess) return PST_ERR_CUDA;
+  if (cudaFuncSetAttribute(edge_msg_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmemTotal) != cudaSuccess) return PST_ERR_CUDA;
   cudaError_t e1 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   cudaError_t e2 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   cudaError_t e3 = cudaFuncSetAttribute(edge_mlp_tc_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
@@ -997,8 +1366,9 @@ int pst_prepare_tc_weights(pst_model* m) {
 }
 
 size_t pst_tc_partial_floats(int R, int K) {
+  // the transposed message kernel takes its partial sums over 64-edge half tiles, both halves of the last tile included
   size_t tiles = ((size_t)R * K + kTileM - 1) / kTileM;
-  return tiles * 4 * kD;
+  return tiles * 2 * 4 * kD;
 }
 
 // Tensor map of the 16-bit edge state [E, 128]: boxes of [128 rows x 64 columns], SWIZZLE_128B (= one K block of
@@ -1007,7 +1377,7 @@ size_t pst_tc_partial_floats(int R, int K) {
 typedef CUresult (*PstEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_edge_state_map(const uint16_t* e, int E, CUtensorMap* out) {
+static int make_edge_state_map(const uint16_t* e, int E, CUtensorMap* out, int box_rows = kTileM) {
   static PstEncodeTiledFn fn = nullptr;
   if (!fn) {
     void* sym = nullptr;
@@ -1017,7 +1387,7 @@ static int make_edge_state_map(const uint16_t* e, int E, CUtensorMap* out) {
   }
   const cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)E};
   const cuuint64_t strides[1] = {(cuuint64_t)kD * sizeof(uint16_t)};
-  const cuuint32_t box[2] = {64u, (cuuint32_t)kTileM};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};  // box_rows = 1: TMA row gather (tile::gather4, tools/probes/gather4_probe.cu)
   const cuuint32_t estr[2] = {1u, 1u};
   CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t*>(e), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1033,7 +1403,7 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   const int K = m->cfg.num_neighbor;
   const PstLayerW& L = m->w.layer[layer];
   EdgeMlpParams p{};
-  p.w_image = m->tc.w + ((size_t)(layer * 2 + mode) * 3 * kMatBytes) / 2;
+  p.w_image = m->tc.w + ((size_t)(layer * 2 + mode) * kImagesPerMlp * kMatBytes) / 2;
   p.b2 = mode == 0 ? L.msg_b2 : L.edge_b2;
   p.b3 = mode == 0 ? L.msg_b3 : L.edge_b3;
   p.ln_s = L.ln2_s;
@@ -1066,6 +1436,44 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   }
   if (half) edge_mlp_tc_kernel<__half, 1><<<grid, kMlpThreads, kSmemTotal, st>>>(p, tmap);
   else edge_mlp_tc_kernel<__nv_bfloat16, 1><<<grid, kMlpThreads, kSmemTotal, st>>>(p, tmap);
+  return 1;
+}
+
+// Transposed message MLP (edge_msg_t_kernel): fp16 operands, even K >= 43.  `h16` = fp16 copy of the node state [R,128]
+// (the sender term is a product with its gathered rows), `pr` = fp16 (h.W1b + b1) [R,128].
+bool pst_edge_msg_t_ok(const pst_model* m) {
+  const int K = m->cfg.num_neighbor;
+  return m->cfg.precision == PST_PREC_FP16 && K >= 43 && (K & 1) == 0;
+}
+int pst_launch_to_half(cudaStream_t st, const float* src, uint16_t* dst, size_t n) {
+  if (n == 0) return 0;
+  to_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<__half*>(dst), (int)n);
+  return 1;
+}
+int pst_launch_edge_msg_t(const pst_model* m, cudaStream_t st, int layer, const uint16_t* e, const uint16_t* h16, const uint16_t* pr,
+                          const int32_t* senders_abs, float* partial, int R) {
+  const int K = m->cfg.num_neighbor;
+  MsgTParams p{};
+  const uint16_t* base = m->tc.w + ((size_t)(layer * 2 + 0) * kImagesPerMlp * kMatBytes) / 2;
+  p.w_image = base;                                 // W1[256:384], W2
+  p.w1a_image = base + (3 * (size_t)kMatBytes) / 2;  // W1[0:128]
+  p.b2 = m->w.layer[layer].msg_b2;
+  p.pr = reinterpret_cast<const __half*>(pr);
+  p.senders = senders_abs;
+  p.partial = partial;
+  p.E = R * K;
+  p.K = K;
+  p.R = R;
+  p.num_tiles = (p.E + kTileM - 1) / kTileM;
+  p.idesc = (1u << 4) | ((uint32_t)(kD >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);  // fp16 x fp16 -> fp32, M = N = 128
+  // second product per 64-edge half tile: B operand MN-major, N = 64
+  p.idesc_bmn = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  if (p.num_tiles == 0) return 0;
+  p.h16 = reinterpret_cast<const __half*>(h16);
+  CUtensorMap tmap_e;
+  if (int rc = make_edge_state_map(e, p.E, &tmap_e)) return rc;
+  const int grid = m->num_sms < p.num_tiles ? m->num_sms : p.num_tiles;
+  edge_msg_t_kernel<<<grid, kTThreads, kTSmemTotal, st>>>(p, tmap_e);
   return 1;
 }
 

@@ -441,6 +441,7 @@ __device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_
 // ------------------------------------------------------------------------------------------------------------
 struct NodeUpdateParams {
   const float* partial;  // [num_edge_tiles][4][128]: per-receiver partial row sums written by the message-mode edge kernel
+  int tile_shift;        // log2 of the edge tile the partial sums are taken over (7: edge_mlp_tc_kernel, 6: edge_msg_t_kernel)
   int K;
   float* h;           // [R,128] in / out
   const uint8_t* const* sched;
@@ -478,11 +479,11 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
     // ---- 1. agg = tbar . W3 -------------------------------------------------------------------------------
     // tbar[row] = (sum of the partial row sums of the one or two 128-edge tiles that hold the row's K edges) / K
     {
-      const int e0 = row * p.K, t0 = e0 >> 7, t1 = (e0 + p.K - 1) >> 7;
-      load_row_half(e, p.partial + ((size_t)t0 * 4 + (row - (t0 * 128) / p.K)) * D, valid, x);
+      const int e0 = row * p.K, t0 = e0 >> p.tile_shift, t1 = (e0 + p.K - 1) >> p.tile_shift;
+      load_row_half(e, p.partial + ((size_t)t0 * 4 + (row - (t0 << p.tile_shift) / p.K)) * D, valid, x);
       if (valid && t1 != t0) {
         float y[2][32];
-        load_row_half(e, p.partial + ((size_t)t1 * 4 + (row - (t1 * 128) / p.K)) * D, true, y);
+        load_row_half(e, p.partial + ((size_t)t1 * 4 + (row - (t1 << p.tile_shift) / p.K)) * D, true, y);
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -843,13 +844,13 @@ void pst_destroy_node_chain(pst_model* m) {
 
 // h <- node update of MPNN layer `layer` (see the header); for layer < last also the four fp16 addend tables:
 // out_edge_s/r for this layer's edge MLP, out_msg_s/r for the next layer's message MLP.
-int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, float* h, int R,
+int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, int partial_tile_shift, float* h, int R,
                            uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r) {
   if (!m->node_chain || R <= 0) return 0;
   const PstNodeChain& C = *m->node_chain;
   const PstLayerW& w = m->w.layer[layer];
   NodeUpdateParams p{};
-  p.partial = partial; p.K = m->cfg.num_neighbor; p.h = h;
+  p.partial = partial; p.tile_shift = partial_tile_shift; p.K = m->cfg.num_neighbor; p.h = h;
   auto put = [&](int off, const float* dev, int n) {  // device pointer into the weight blob -> its host copy
     if (dev) memcpy(p.cv + off, m->blob_host + (dev - m->blob_dev), (size_t)n * sizeof(float));
   };

@@ -73,6 +73,7 @@ struct pst_model {
   // FSQ constants (model/quantize.py:175-181), fp32
   float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
   int32_t basis[PST_C8], half_width[PST_C8];
+  bool use_msg_t;            // message MLPs through the transposed kernel (edge_msg_t_kernel; PST_MSG_T=0 switches it off)
   mutable int launch_count;
   // CUDA-graph cache of the fused hot call (api.cu): a pst_tokenize call whose arguments (pointers and sizes) repeat
   // is captured once and replayed, which removes the launch gaps between its ~110 dependent kernels
@@ -159,6 +160,11 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
                            const uint16_t* ps, const uint16_t* pr, const int32_t* senders,
                            const int32_t* row_base, float* partial, int R);
 size_t pst_tc_partial_floats(int R, int K);
+// transposed message MLP (round 2): the sender term is a product with the TMA-gathered rows of h16 = fp16(h)
+bool pst_edge_msg_t_ok(const pst_model* m);
+int pst_launch_to_half(cudaStream_t st, const float* src, uint16_t* dst, size_t n);
+int pst_launch_edge_msg_t(const pst_model* m, cudaStream_t st, int layer, const uint16_t* e, const uint16_t* h16, const uint16_t* pr,
+                          const int32_t* senders_abs, float* partial, int R);
 int pst_launch_abs_senders(const pst_model* m, cudaStream_t st, const int32_t* senders, const int32_t* row_base, int R,
                            int32_t* senders_abs);
 int pst_launch_edge_embed_tc(const pst_model* m, cudaStream_t st, const float* feat, const int32_t* senders,
@@ -175,7 +181,7 @@ const uint8_t* pst_linear_tc_image(const pst_model* m, const float* W, int K, in
 int pst_prepare_node_chain(pst_model* m);
 void pst_destroy_node_chain(pst_model* m);
 int pst_prepare_layer0_tables(pst_model* m);  // encoder_fp32.cu
-int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, float* h, int R,
+int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, int partial_tile_shift, float* h, int R,
                            uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r);
 int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z);
 
