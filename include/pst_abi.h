@@ -56,7 +56,8 @@ typedef enum pst_status {
   PST_ERR_PDB_MODEL_COUNT = -8,     /* the file does not hold exactly one model */
   PST_ERR_PDB_INSERTION_CODE = -9,  /* a residue carries an insertion code */
   PST_ERR_PDB_MALFORMED = -10,      /* an ATOM / HETATM record is too short or has non-numeric fields */
-  PST_ERR_FILE_NOT_FOUND = -11      /* pst_parse_pdb_files: the path could not be opened */
+  PST_ERR_FILE_NOT_FOUND = -11,     /* pst_parse_pdb_files: the path could not be opened */
+  PST_ERR_NON_FINITE = -12          /* device status: a latent reached the quantiser as Inf / NaN (16-bit operand range exceeded) */
 } pst_status;
 
 /* GEMM operand precision of the edge-level MLPs (accumulation is always fp32;

@@ -28,7 +28,8 @@ struct PstGraphEntry {
   unsigned long long last_use = 0;
 };
 struct PstGraphCache {
-  static constexpr size_t kMaxEntries = 8;
+  // a streamed ragged workload sends a different (B, R, T) per chunk: every chunk of a repeated pass keeps its own graph
+  static constexpr size_t kMaxEntries = 128;
   std::mutex mu;
   std::vector<PstGraphEntry> entries;
   unsigned long long clock = 0;
@@ -196,6 +197,7 @@ const char* pst_status_string(int status) {
     case PST_ERR_PDB_INSERTION_CODE: return "PDB contains an insertion code; these are not supported";
     case PST_ERR_PDB_MALFORMED: return "malformed ATOM / HETATM record";
     case PST_ERR_FILE_NOT_FOUND: return "file could not be opened";
+    case PST_ERR_NON_FINITE: return "a latent is Inf / NaN (activations exceeded the 16-bit operand range; use PST_PREC_FP32)";
     default: return "unknown status";
   }
 }
@@ -419,7 +421,7 @@ static int tokenize_enqueue(const pst_model* m, cudaStream_t st, const float* at
   count += n;
   {
     PstSpan span(m, st, 6);
-    count += pst_launch_quantize(m, st, ws.z, total_tokens, tokens_out, nullptr);
+    count += pst_launch_quantize(m, st, ws.z, total_tokens, tokens_out, nullptr, ws.status);
   }
   m->launch_count = count;
   return cudaGetLastError() == cudaSuccess ? PST_OK : PST_ERR_CUDA;

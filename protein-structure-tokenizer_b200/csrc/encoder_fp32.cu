@@ -456,6 +456,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       L.gemm(ws.h, w0.msg_w1 + D * D, ws.pr, R, D, D, Launcher::epi(w0.msg_b1), 1);
     }
     bool msg_t = false;
+    uint16_t* h16 = reinterpret_cast<uint16_t*>(ws.dn);
     for (int l = 0; l < cfg.gnn_layers; ++l) {
       {
         // message MLP: returns the per-receiver mean of the 2nd hidden layer; the 3rd linear commutes with
@@ -464,9 +465,9 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
         int n;
         msg_t = m->use_msg_t && pst_edge_msg_t_ok(m);
         if (msg_t) {
-          // transposed kernel: the sender term is a product with the gathered rows of fp16(h) (ws.dn is free until the resampler)
-          uint16_t* h16 = reinterpret_cast<uint16_t*>(ws.dn);
-          L.count += pst_launch_to_half(st, ws.h, h16, (size_t)R * D);
+          // transposed kernel: the sender term is a product with the gathered rows of fp16(h) (ws.dn is free until the
+          // resampler); the node kernel of the previous layer has written it, layer 0 converts the embedding
+          if (l == 0) L.count += pst_launch_to_half(st, ws.h, h16, (size_t)R * D);
           n = pst_launch_edge_msg_t(m, st, l, reinterpret_cast<const uint16_t*>(ws.e), h16, pr, ws.senders_abs, ws.partial, R);
         } else {
           n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, ws.senders_abs, row_base, ws.partial, R);  // the node kernel sums the partials itself
@@ -476,7 +477,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
       }
       {
         PstSpan span(m, st, 3);
-        int n = pst_launch_node_update(m, st, l, ws.partial, msg_t ? 6 : 7, ws.h, R, ps2, pr2, ps, pr);
+        int n = pst_launch_node_update(m, st, l, ws.partial, msg_t ? 6 : 7, ws.h, R, ps2, pr2, ps, pr, msg_t ? h16 : nullptr);
         if (n < 0) return n;
         L.count += n;
       }

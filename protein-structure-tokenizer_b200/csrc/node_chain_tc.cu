@@ -444,6 +444,7 @@ struct NodeUpdateParams {
   int tile_shift;        // log2 of the edge tile the partial sums are taken over (7: edge_mlp_tc_kernel, 6: edge_msg_t_kernel)
   int K;
   float* h;           // [R,128] in / out
+  __half* h16;        // [R,128] out (optional): fp16 copy of the new node state, gathered by the transposed message kernel
   const uint8_t* const* sched;
   int n_sched, n_out;
   __half* out[4];
@@ -530,6 +531,21 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
       for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int j = 0; j < 4; ++j) st256f(hdst + q * 32 + j * 8, &x[q][j * 8]);
+      if (p.h16) {
+        __half* h16dst = p.h16 + (size_t)row * D + e.half * 64;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const __half2 v2 = __floats2half2_rn(x[q][j * 16 + 2 * k], x[q][j * 16 + 2 * k + 1]);
+              pk[k] = *reinterpret_cast<const uint32_t*>(&v2);
+            }
+            st256u(h16dst + q * 32 + j * 16, pk);
+          }
+      }
     }
     if (p.n_out > 0) {
       split_store_half(e, X, x);
@@ -845,12 +861,13 @@ void pst_destroy_node_chain(pst_model* m) {
 // h <- node update of MPNN layer `layer` (see the header); for layer < last also the four fp16 addend tables:
 // out_edge_s/r for this layer's edge MLP, out_msg_s/r for the next layer's message MLP.
 int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, int partial_tile_shift, float* h, int R,
-                           uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r) {
+                           uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r, uint16_t* h16) {
   if (!m->node_chain || R <= 0) return 0;
   const PstNodeChain& C = *m->node_chain;
   const PstLayerW& w = m->w.layer[layer];
   NodeUpdateParams p{};
   p.partial = partial; p.tile_shift = partial_tile_shift; p.K = m->cfg.num_neighbor; p.h = h;
+  p.h16 = reinterpret_cast<__half*>(h16);
   auto put = [&](int off, const float* dev, int n) {  // device pointer into the weight blob -> its host copy
     if (dev) memcpy(p.cv + off, m->blob_host + (dev - m->blob_dev), (size_t)n * sizeof(float));
   };

@@ -147,7 +147,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
                            PstWorkspace& ws, int compact_features = 0);
 
 int pst_launch_quantize(const pst_model* m, cudaStream_t st, const float* z, int n,
-                        int32_t* tokens, float* bounded);
+                        int32_t* tokens, float* bounded, int32_t* status = nullptr);
 int pst_launch_fsq_pack(const pst_model* m, cudaStream_t st, const float* bounded, int n,
                         int32_t* tokens);
 int pst_launch_indexes_to_codes(const pst_model* m, cudaStream_t st, const int32_t* tokens, int n,
@@ -182,7 +182,8 @@ int pst_prepare_node_chain(pst_model* m);
 void pst_destroy_node_chain(pst_model* m);
 int pst_prepare_layer0_tables(pst_model* m);  // encoder_fp32.cu
 int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, int partial_tile_shift, float* h, int R,
-                           uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r);
+                           uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r,
+                           uint16_t* h16 = nullptr);
 int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z);
 
 #define PST_CUDA_OK(expr)                                  \

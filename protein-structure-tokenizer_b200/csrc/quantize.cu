@@ -15,23 +15,28 @@ struct FsqParams {
 };
 
 __global__ void fsq_quantize_kernel(const float* __restrict__ z, int n, FsqParams p, int32_t* __restrict__ tokens,
-                                    float* __restrict__ bounded) {
+                                    float* __restrict__ bounded, int32_t* __restrict__ status) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const float4* zp = reinterpret_cast<const float4*>(z + (size_t)t * PST_C8);
   float4 a = zp[0], b = zp[1];
   float v[PST_C8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   int tok = 0;
+  bool finite = true;
 #pragma unroll
   for (int c = 0; c < PST_C8; ++c) {
     float bd = 0.f;
     if (c < p.C) {
+      finite = finite && isfinite(v[c]);
       bd = tanhf(v[c] + p.shift[c]) * p.half_l[c] - p.offset[c];
       tok += ((int)rintf(bd) + p.half_width[c]) * p.basis[c];
     }
     v[c] = bd;
   }
   tokens[t] = tok;
+  // No silent Inf / NaN: the 16-bit operand modes have a finite range (fp16: 65 504); a latent that arrives here
+  // non-finite raises the call's device status word instead of becoming an arbitrary token id.
+  if (!finite && status) atomicMin(status, (int)PST_ERR_NON_FINITE);
   if (bounded) {
     float4* bp = reinterpret_cast<float4*>(bounded + (size_t)t * PST_C8);
     bp[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -71,9 +76,10 @@ FsqParams make_params(const pst_model* m) {
 
 }  // namespace
 
-int pst_launch_quantize(const pst_model* m, cudaStream_t st, const float* z, int n, int32_t* tokens, float* bounded) {
+int pst_launch_quantize(const pst_model* m, cudaStream_t st, const float* z, int n, int32_t* tokens, float* bounded,
+                        int32_t* status) {
   if (n <= 0) return 0;
-  fsq_quantize_kernel<<<(n + 255) / 256, 256, 0, st>>>(z, n, make_params(m), tokens, bounded);
+  fsq_quantize_kernel<<<(n + 255) / 256, 256, 0, st>>>(z, n, make_params(m), tokens, bounded, status);
   return 1;
 }
 int pst_launch_fsq_pack(const pst_model* m, cudaStream_t st, const float* bounded, int n, int32_t* tokens) {

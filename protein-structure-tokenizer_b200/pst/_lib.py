@@ -13,6 +13,7 @@ PST_ABI_VERSION = 1
 PST_ERR_WORKSPACE_TOO_SMALL = -4
 PST_ERR_PDB_MODEL_COUNT, PST_ERR_PDB_INSERTION_CODE, PST_ERR_PDB_MALFORMED = -8, -9, -10
 PST_ERR_FILE_NOT_FOUND = -11
+PST_ERR_NON_FINITE = -12  # device status: a latent reached the quantiser as Inf / NaN
 PST_MAX_LEVELS = 8
 
 

@@ -203,6 +203,8 @@ class StructureTokenizer:
             z = self.encode_graph_device(f, s, t.from_numpy(offs).to(self.device), t.from_numpy(toff).to(self.device), B, R, T)
             tokens = self.quantize_device(z).cpu().numpy()
             st = self.read_status()
+            if st == 0 and not bool(t.isfinite(z).all()):
+                st = _lib.PST_ERR_NON_FINITE  # the standalone quantiser has no status word: same rule as the fused call
             if st != 0:
                 raise _lib.PstError(st, "pst_encode_graph (device status)")
             out.extend(tokens[toff[i] : toff[i + 1]].astype(np.uint32) for i in range(B))

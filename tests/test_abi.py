@@ -63,6 +63,7 @@ def test_python_binding_covers_the_header(built_lib):
     lib = _lib.load()
     assert lib.pst_abi_version() == 1
     assert lib.pst_status_string(-3).decode().startswith("structure length")
+    assert "Inf / NaN" in lib.pst_status_string(-12).decode()
 
 
 def test_blob_size_matches_packer(built_lib):

@@ -290,3 +290,34 @@ def test_graph_cache_eviction_keeps_results(built_lib):
             assert torch.equal(out, w), rep
     assert tok.read_status() == 0
     tok.close()
+
+
+@pytest.mark.parametrize("scale", [8.0, 32.0, 512.0])
+def test_scaled_weights_give_agreeing_tokens_or_a_device_status_never_silent_garbage(built_lib, scale):
+    """The 16-bit operand modes have a finite range (fp16: 65 504) and the gathered addend tables hold PRE-activation
+    values.  With the edge-level weights scaled up, the default mode must either still agree with the all-fp32 mode or
+    raise PST_ERR_NON_FINITE through the device status word: never return token ids computed from Inf / NaN."""
+    from pst import _lib
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg16 = TokenizerConfig.named(4096, 1, precision="fp16")
+    cfg32 = TokenizerConfig.named(4096, 1, precision="fp32")
+    params = dict(init_params(cfg16, 5, "spread"))
+    for k in list(params):
+        if ("node_mlp_0" in k or "edge_mlp" in k) and k.endswith("/w"):
+            params[k] = (params[k] * np.float32(scale)).astype(np.float32)
+    bbs = syn.make_backbones(17, [96, 160, 64, 128])
+    ref = StructureTokenizer(cfg32, params).tokenize(bbs)
+    assert all(np.isfinite(r.astype(np.float64)).all() for r in ref)
+    tok = StructureTokenizer(cfg16, params)
+    try:
+        out = tok.tokenize(bbs)
+    except _lib.PstError as e:
+        assert e.status == _lib.PST_ERR_NON_FINITE, e
+        return
+    agree = sum(int((a == b).sum()) for a, b in zip(out, ref)) / sum(len(r) for r in ref)
+    # with saturated activations the latents sit on few distinct codes; what must not happen is disagreement from overflow
+    assert agree >= 0.97, (scale, agree)
