@@ -178,6 +178,12 @@ int pst_graph_cache_enable(const pst_model* model, int enable);
 int pst_parse_pdb(const char* text, size_t text_bytes, int max_residues, float* atom37_positions,
                   uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out);
 
+/* The same with the reference's `chain_id` argument (protein_structure_sample.py:166-168,201-203; the second caller,
+ * data_pipeline.py:69-128, passes it): only the chain with this one-character id is emitted; 0 = every chain
+ * (= pst_parse_pdb).  An insertion code in a chain that is skipped is not an error, as in the reference. */
+int pst_parse_pdb_chain(const char* text, size_t text_bytes, char chain_id, int max_residues, float* atom37_positions,
+                        uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out);
+
 /* HOST function: n_files PDB texts parsed side by side on up to n_threads host threads (<= 0: all hardware threads),
  * the feeder in front of pst_tokenize (the reference parses one file at a time in Python,
  * scripts/inference_runner.py:40-74 called from :288-296).  The output arrays are shared: file i's residues are rows

@@ -213,7 +213,9 @@ struct Residue {
 
 // Phase 1: the records of one file -> `residues` (order of first appearance) and `order`, the positions of the residues
 // that are emitted, in output order (chains by first appearance, residues without a kept atom skipped).
-int parse_text(const char* text, size_t len, std::vector<Residue>& residues, std::vector<int>& order) {
+// only_chain != 0: only that chain is emitted (protein_structure_sample.py:201-203: the chain filter comes BEFORE the
+// insertion-code check, so an insertion code in a skipped chain is not an error; the model count is checked on the file).
+int parse_text(const char* text, size_t len, std::vector<Residue>& residues, std::vector<int>& order, char only_chain = 0) {
   residues.clear();
   order.clear();
   residues.reserve(len / 640 + 16);  // ~8 records of 81 bytes per residue in an all-atom file: no regrowth copies of the 750-byte entries
@@ -308,6 +310,7 @@ int parse_text(const char* text, size_t len, std::vector<Residue>& residues, std
     for (size_t r = 0; r < residues.size(); ++r) {
       const Residue& res = residues[r];
       if (res.chain_rank != c) continue;
+      if (only_chain && res.chain != only_chain) continue;
       if (res.icode != ' ') return PST_ERR_PDB_INSERTION_CODE;
       bool any = false;
       for (int s = 0; s < 37; ++s) any = any || res.atoms[s].set;
@@ -340,11 +343,16 @@ void emit_residue(const Residue& res, size_t row, float* atom37_positions, uint8
 
 extern "C" int pst_parse_pdb(const char* text, size_t len, int max_residues, float* atom37_positions, uint8_t* gt_exists,
                              uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out) {
+  return pst_parse_pdb_chain(text, len, 0, max_residues, atom37_positions, gt_exists, atom_exists, aatype, n_residues_out);
+}
+
+extern "C" int pst_parse_pdb_chain(const char* text, size_t len, char chain_id, int max_residues, float* atom37_positions,
+                                   uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out) {
   if (!text || !n_residues_out) return PST_ERR_BAD_ARGUMENT;
   *n_residues_out = 0;
   std::vector<Residue> residues;
   std::vector<int> order;
-  const int rc = parse_text(text, len, residues, order);
+  const int rc = parse_text(text, len, residues, order, chain_id);
   if (rc != PST_OK) return rc;
   const int n_out = static_cast<int>(order.size());
   *n_residues_out = n_out;

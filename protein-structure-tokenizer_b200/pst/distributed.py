@@ -41,7 +41,9 @@ def lpt_partition(lengths: Sequence[int], world: int, alpha: float = 1.0, beta: 
 
 
 class GatheredTokens(NamedTuple):
-    """Rank 0's view of a gather: `flat[r]` holds rank r's tokens back to back in the order of `index[r]`."""
+    """Rank 0's view of a gather: `flat[r]` holds rank r's tokens back to back in the order of `index[r]`.  On a CUDA
+    group the `flat` arrays are views of a pinned staging buffer that the next gather of this process overwrites:
+    consume (or copy) them first."""
 
     flat: List[np.ndarray]     # per rank, int32 [sum of that rank's token counts]
     index: List[np.ndarray]    # per rank, int64 [n_r] global structure indices
@@ -78,35 +80,68 @@ def gather_tokens_flat(local_indices: Sequence[int], local_counts: Sequence[int]
         flat = local_flat.cpu().numpy() if isinstance(local_flat, torch.Tensor) else np.asarray(local_flat)
         return GatheredTokens([flat.astype(np.int32, copy=False)], [idx], [cnt], n_total)
     dev = device if device is not None else torch.device("cpu")
+    on_gpu = dev.type == "cuda"
     if isinstance(local_flat, torch.Tensor):
         payload_local = local_flat.to(device=dev, dtype=torch.int32)
     else:
-        payload_local = torch.from_numpy(np.ascontiguousarray(local_flat, np.int32)).to(dev)
+        host = torch.from_numpy(np.ascontiguousarray(local_flat, np.int32))
+        payload_local = host.to(dev, non_blocking=False)
     sizes_t = torch.tensor([idx.size, int(payload_local.numel())], dtype=torch.int64, device=dev)
     all_sizes = [torch.zeros_like(sizes_t) for _ in range(world)]
     dist.all_gather(all_sizes, sizes_t, group=group)
-    sizes = np.stack([s.cpu().numpy() for s in all_sizes])  # [world, 2]
+    sizes = torch.stack(all_sizes).cpu().numpy()  # [world, 2]
     cap_n, cap_t = int(sizes[:, 0].max()), int(sizes[:, 1].max())
-    table = torch.zeros((2, max(cap_n, 1)), dtype=torch.int64, device=dev)
+    # padded to the largest rank's size; the padding is never read back, so nothing is zero-filled
+    table = torch.empty((2, max(cap_n, 1)), dtype=torch.int64, device=dev)
     if idx.size:
-        table[0, : idx.size] = torch.from_numpy(idx).to(dev)
-        table[1, : idx.size] = torch.from_numpy(cnt).to(dev)
-    payload = torch.zeros(max(cap_t, 1), dtype=torch.int32, device=dev)
-    payload[: payload_local.numel()] = payload_local
-    tables = [torch.zeros_like(table) for _ in range(world)] if rank == 0 else None
-    bufs = [torch.zeros_like(payload) for _ in range(world)] if rank == 0 else None
+        table[:, : idx.size] = torch.from_numpy(np.stack([idx, cnt])).to(dev)
+    if payload_local.numel() == max(cap_t, 1):
+        payload = payload_local
+    else:
+        payload = torch.empty(max(cap_t, 1), dtype=torch.int32, device=dev)
+        payload[: payload_local.numel()] = payload_local
+    if rank == 0:
+        # one flat receive buffer per kind: the per-rank views are what `gather` fills
+        tables_all = torch.empty((world,) + tuple(table.shape), dtype=torch.int64, device=dev)
+        bufs_all = torch.empty((world, payload.numel()), dtype=torch.int32, device=dev)
+        tables, bufs = list(tables_all.unbind(0)), list(bufs_all.unbind(0))
+    else:
+        tables = bufs = None
     dist.gather(table, tables, dst=0, group=group)
     dist.gather(payload, bufs, dst=0, group=group)
     if rank != 0:
         return None
+    if on_gpu:
+        # device -> pinned host memory (pageable destinations run at a fraction of the PCIe rate), one copy per kind
+        host_bufs = _pinned("tokens", (world, payload.numel()), torch.int32)
+        host_tabs = _pinned("tables", (world,) + tuple(table.shape), torch.int64)
+        host_bufs.copy_(bufs_all, non_blocking=True)
+        host_tabs.copy_(tables_all, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        bufs_np, tabs_np = host_bufs.numpy(), host_tabs.numpy()
+    else:
+        bufs_np, tabs_np = bufs_all.numpy(), tables_all.numpy()
     flats, idxs, cnts = [], [], []
     for r in range(world):
         n_r, t_r = int(sizes[r, 0]), int(sizes[r, 1])
-        tb = tables[r].cpu().numpy()
-        idxs.append(tb[0, :n_r].copy())
-        cnts.append(tb[1, :n_r].copy())
-        flats.append(bufs[r][:t_r].cpu().numpy())
+        idxs.append(tabs_np[r, 0, :n_r].copy())
+        cnts.append(tabs_np[r, 1, :n_r].copy())
+        flats.append(bufs_np[r, :t_r])  # a VIEW of the staging buffer: valid until this process gathers again
     return GatheredTokens(flats, idxs, cnts, n_total)
+
+
+_PINNED = {}
+
+
+def _pinned(kind: str, shape, dtype):
+    """Grow-only pinned host staging buffers of rank 0's gather (kept between calls)."""
+    import torch
+
+    need = int(np.prod(shape))
+    buf = _PINNED.get(kind)
+    if buf is None or buf.numel() < need or buf.dtype != dtype:
+        buf = _PINNED[kind] = torch.empty(need, dtype=dtype).pin_memory()
+    return buf[:need].view(*shape)
 
 
 def gather_tokens(local_indices: Sequence[int], local_tokens: Sequence[np.ndarray], n_total: int, rank: int, world: int,

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import pickle
 import threading
-from typing import Dict, List, NamedTuple, Tuple
+from typing import Dict, List, NamedTuple, Optional, Tuple
 
 import numpy as np
 
@@ -71,7 +71,8 @@ class StructureSample(NamedTuple):
         return np.ascontiguousarray(self.atom37_positions[keep], np.float32), np.ascontiguousarray(mask, np.uint8)
 
 
-def structure_from_pdb_string(pdb_str: str) -> StructureSample:
+def structure_from_pdb_string(pdb_str: str, chain_id: Optional[str] = None) -> StructureSample:
+    """`chain_id`: only that chain is parsed (protein_structure_sample.py:166-168,201-203); None = all chains."""
     residues: Dict[Tuple[str, str, int, str], dict] = {}
     chain_order: List[str] = []
     models = 0
@@ -118,6 +119,8 @@ def structure_from_pdb_string(pdb_str: str) -> StructureSample:
         for (c, het, resseq, icode), res in residues.items():
             if c != chain:
                 continue
+            if chain_id is not None and c != chain_id:
+                continue
             if icode != " ":
                 raise ValueError(f"PDB contains an insertion code at chain {chain} and residue index {resseq}. These are not supported.")
             rn = res["resname"] if res["resname"] in RESIDUE_ATOMS else "UNK"
@@ -144,24 +147,27 @@ def structure_from_pdb_string(pdb_str: str) -> StructureSample:
     )
 
 
-def structure_from_pdb_file(path: str) -> StructureSample:
+def structure_from_pdb_file(path: str, chain_id: Optional[str] = None) -> StructureSample:
     with open(path, "r") as fh:
-        return structure_from_pdb_string(fh.read())
+        return structure_from_pdb_string(fh.read(), chain_id)
 
 
 _scratch = threading.local()
 
 
-def structure_from_pdb_bytes_native(data: bytes) -> StructureSample:
+def structure_from_pdb_bytes_native(data: bytes, chain_id: Optional[str] = None) -> StructureSample:
     """The same result through the C++ parser of the C ABI (`pst_parse_pdb`, csrc/pdb_parse.cc): ~100x faster than
     the pure-Python loop above, which is kept as an independent restatement for the tests.  Raises ValueError where
-    the reference does (protein_structure_sample.py:187-190, :205-209)."""
+    the reference does (protein_structure_sample.py:187-190, :205-209).  `chain_id`: only that chain (`pst_parse_pdb_chain`)."""
     import ctypes as C
 
     from . import _lib
 
     lib = _lib.load()
     n = C.c_int32(0)
+    if chain_id is not None and len(chain_id) != 1:
+        raise ValueError(f"chain_id must be one character, got {chain_id!r}")
+    chain = C.c_char(chain_id.encode()) if chain_id is not None else C.c_char(b"\0")
     # Per-thread scratch arrays, grown on demand and reused from file to file (the runner parses files side by side:
     # fresh multi-hundred-KB arrays per file are mmap'ed and page-faulted every time, which serialises the threads in the
     # kernel), no scan of the text in Python (the GIL is only released inside the C call): capacity guess = one
@@ -174,8 +180,8 @@ def structure_from_pdb_bytes_native(data: bytes) -> StructureSample:
             sc = _scratch.arrays = (np.empty((grow, 37, 3), np.float32), np.empty((grow, 37), np.uint8),
                                     np.empty((grow, 37), np.uint8), np.empty((grow,), np.int32))
         pos, gt, ex, aa = sc
-        rc = lib.pst_parse_pdb(data, len(data), pos.shape[0], pos.ctypes.data, gt.ctypes.data, ex.ctypes.data, aa.ctypes.data,
-                               C.byref(n))
+        rc = lib.pst_parse_pdb_chain(data, len(data), chain, pos.shape[0], pos.ctypes.data, gt.ctypes.data, ex.ctypes.data,
+                                     aa.ctypes.data, C.byref(n))
         if rc == _lib.PST_ERR_WORKSPACE_TOO_SMALL:
             cap = int(n.value)
             continue
@@ -188,9 +194,9 @@ def structure_from_pdb_bytes_native(data: bytes) -> StructureSample:
                            atom37_gt_exists=gt[:k].astype(np.bool_), atom37_atom_exists=ex[:k].astype(np.bool_))
 
 
-def structure_from_pdb_file_native(path: str) -> StructureSample:
+def structure_from_pdb_file_native(path: str, chain_id: Optional[str] = None) -> StructureSample:
     with open(path, "rb") as fh:
-        return structure_from_pdb_bytes_native(fh.read())
+        return structure_from_pdb_bytes_native(fh.read(), chain_id)
 
 
 def _parse_batch_native(n_files: int, guess_rows: int, call, names):

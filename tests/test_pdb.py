@@ -232,3 +232,28 @@ def test_batch_parser_equals_the_single_file_parser(built_lib, tmp_path):
     assert isinstance(out[1], FileNotFoundError)
     _same_samples(out[0], ppdb.structure_from_pdb_bytes_native(datas[0]))
     _same_samples(out[2], ppdb.structure_from_pdb_bytes_native(datas[3]))
+
+
+def test_chain_filter_matches_the_reference_argument(built_lib):
+    """`chain_id` of protein_structure_from_pdb_string (protein_structure_sample.py:166-168,201-203): only that chain
+    is emitted, an insertion code in a skipped chain is not an error, the model count is still checked on the file."""
+    from pst import pdb as ppdb
+    from pst import synthetic as syn
+
+    bbs = syn.make_backbones(3, [64, 70])
+    a = _pdb_from_backbone(bbs[0], chain="A")
+    b = _pdb_from_backbone(bbs[1], chain="B")
+    text = "".join(l + "\n" for l in (a + "\n" + b).splitlines() if l.startswith("ATOM"))
+    for parse in (ppdb.structure_from_pdb_string, lambda t, c=None: ppdb.structure_from_pdb_bytes_native(t.encode(), c)):
+        both = parse(text)
+        only_a, only_b = parse(text, "A"), parse(text, "B")
+        assert both.nb_residues == 134 and only_a.nb_residues == 64 and only_b.nb_residues == 70
+        assert np.array_equal(only_b.atom37_positions, both.atom37_positions[64:])
+        assert parse(text, "Z").nb_residues == 0
+        lines = text.splitlines()
+        bad = "\n".join(l[:26] + "X" + l[27:] if l[21] == "B" and int(l[22:26]) == 5 else l for l in lines) + "\n"
+        assert parse(bad, "A").nb_residues == 64          # the insertion code sits in the skipped chain
+        with pytest.raises(ValueError):
+            parse(bad, "B")
+        with pytest.raises(ValueError):
+            parse(bad)
