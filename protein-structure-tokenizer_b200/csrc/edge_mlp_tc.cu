@@ -1048,7 +1048,9 @@ __global__ void __launch_bounds__(kTThreads, 1) edge_msg_t_kernel(MsgTParams p, 
 // 16-bit edge state in place and the tile is copied out row-coalesced.  Same 4-group persistent structure
 // as the edge MLP kernel.
 constexpr uint32_t kEmbSmemW = 2 * 16384;  // W hi / lo images, [128 n x 64 k] (k < 32 used)
-constexpr uint32_t kEmbSmemTotal = kEmbSmemW + kSmemA + kGroups * 256 + 64;
+// + per group: the tile's 128 table row indices and a 16 KB landing buffer for the first k-block of the gathered rows
+constexpr uint32_t kEmbSmemTotal = kEmbSmemW + kSmemA + kGroups * 512 + 64 + kGroups * kKBlockBytes;
+static_assert(kEmbSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 
 struct EmbedParams {
   const uint16_t* w_img;     // hi image (16 KB) then lo image (16 KB)
@@ -1070,11 +1072,32 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sAall = smem + kEmbSmemW;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kEmbSmemW + kSmemA + kGroups * 256);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kEmbSmemW + kSmemA + kGroups * 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kGroups);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = warp >> 2, gt = tid & 127, wq = warp & 3;
   uint8_t* sA = sAall + g * kMatBytes;
+  int* sIdx = reinterpret_cast<int*>(smem + kEmbSmemW + kSmemA) + g * 128;  // PE-table row of each edge of the group's tile
+  uint8_t* sT = smem + kEmbSmemW + kSmemA + kGroups * 512 + 64 + g * kKBlockBytes;  // landing buffer (k-block 0 of the table rows)
+  const uint32_t sT_addr = smem_u32(sT);
+  // The fp16 PE-table rows of the tile, one 64-column k-block at a time, by 16-byte cp.async copies into the operand
+  // image layout: eight lanes per 128-byte half row, four rows per warp instruction (whole lines; each thread loading
+  // its own row with eight 32-byte loads cost one L1 data-pipe wavefront per load, 1 024 per tile, and 0.24 ms of this
+  // kernel's 0.59: profiles/r02_edge/README.md).  One commit group per call.
+  auto gather_table_block = [&](int kb, uint32_t dst_base) {
+    const int chunk = gt & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 16 + (gt >> 3);
+#ifdef PST_ABL_EMB_NOTABLE  // timing experiment: one copy in eight
+      if (i != 0) continue;
+#endif
+      const __half* src = p.table + (size_t)sIdx[r] * kD + kb * 64 + chunk * 8;
+      const uint32_t dst = dst_base + (uint32_t)r * 128u + ((uint32_t)(chunk ^ (r & 7)) << 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img);
@@ -1158,7 +1181,9 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
       }
       // the buffer is free once the previous tile's TMA store has read it: waited for here, behind the loads above
       if (gt == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      sIdx[gt] = trow;
       group_sync(g);
+      gather_table_block(0, sT_addr);  // columns 0..63 of the tile's PE-table rows: lands behind the staging and the product
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t hi[4], lo[4];
@@ -1201,7 +1226,9 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
       trow_next = table_row(tile + gridDim.x * kGroups);
       // the buffer is free once the previous tile's TMA store has read it: waited for here, behind the loads above
       if (gt == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      sIdx[gt] = trow;
       group_sync(g);
+      gather_table_block(0, sT_addr);  // columns 0..63 of the tile's PE-table rows: lands behind the staging and the product
 #pragma unroll
       for (int i = 0; i < PST_EDGE_FEATURES; ++i) {
         const int idx = gt + i * 128;
@@ -1221,14 +1248,6 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
         *reinterpret_cast<uint16_t*>(sA + kKBlockBytes + off) = 0;
       }
     }
-    // this thread's row of the fp16 PE table (256 B, eight 32-byte loads): issued now, consumed in the epilogue, so
-    // the L2 latency hides behind the barrier and the MMA
-    // (in two halves: the second one is issued at the start of the epilogue and lands while the first is consumed,
-    // which keeps the kernel clear of register spills: with 226 KB of shared memory there is no L1 behind local memory)
-    uint32_t tabA[32], tabB[32];
-    const uint32_t* tb = reinterpret_cast<const uint32_t*>(p.table + (size_t)trow * kD);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) ldg256(tb + i * 8, &tabA[i * 8]);
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
@@ -1246,16 +1265,30 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
     mbar_wait(mbar_addr, parity);
     parity ^= 1;
     tc_fence_after();
-    // ---- epilogue: acc + table row -> 16-bit edge state in the operand image layout of the (now free) buffer,
-    // which is also the layout of the TMA store boxes (each thread only touches its own row) ----
-#pragma unroll
-    for (int i = 0; i < 4; ++i) ldg256(tb + 32 + i * 8, &tabB[i * 8]);
+    // the product has read the buffer: columns 64..127 of the table rows land in its second k-block, in place, while
+    // the first half of the epilogue runs from the landing buffer
+    gather_table_block(1, sA_addr + kKBlockBytes);
+    // ---- epilogue: acc + table row -> 16-bit edge state in the operand image layout (each thread only touches its
+    // own row), which is also the layout of the TMA store boxes ----
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    group_sync(g);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+      if (q == 2) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        group_sync(g);
+      }
       float2 v[16];
       tmem_ld32v(tmem_row + q * 32, v);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = add2(v[c], Unpack<__half>::two(q < 2 ? tabA[q * 16 + c] : tabB[(q - 2) * 16 + c]));
+      for (int j = 0; j < 4; ++j) {
+        const uint4 pk = q < 2 ? *reinterpret_cast<const uint4*>(sT + swz_k64(gt, q * 32 + j * 8))
+                               : *reinterpret_cast<const uint4*>(sA + swz_offset(gt, q * 32 + j * 8));
+        v[j * 4 + 0] = add2(v[j * 4 + 0], Unpack<__half>::two(pk.x));
+        v[j * 4 + 1] = add2(v[j * 4 + 1], Unpack<__half>::two(pk.y));
+        v[j * 4 + 2] = add2(v[j * 4 + 2], Unpack<__half>::two(pk.z));
+        v[j * 4 + 3] = add2(v[j * 4 + 3], Unpack<__half>::two(pk.w));
+      }
       store_a_chunk2<T16>(sA, gt, q * 32, v);
     }
     fence_proxy_async();

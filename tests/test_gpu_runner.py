@@ -206,3 +206,52 @@ def test_runner_under_torchrun_shards_files_and_gathers_on_rank0(built_lib, tmp_
     assert names == sorted(os.listdir(tmp_path / "two")) == [f"S{i}_tokens.npy" for i in range(5)]
     for n in names:
         assert np.array_equal(np.load(tmp_path / "one" / n), np.load(tmp_path / "two" / n))
+
+
+def test_data_pipeline_mirror_feeds_the_callable(built_lib, casp14, tmp_path):
+    """The reference's second caller of the featurisation path (data_pipeline.py:36-332): sample -> padded BatchDataVQ3D
+    (GPU featuriser + the reference's padding) -> saved .npy / .npz -> the runner's callable (boundary B1).  The graph
+    equals the oracle's padded graph (senders exactly, features to 1 fp32 ulp) and the tokens equal the B2 path's."""
+    from conftest import valid_atoms
+    from oracle import featurize as fz
+    from pst import pdb as ppdb
+    from pst.config import TokenizerConfig
+    from pst.data_pipeline import DataPipeline
+    from pst.inference_runner import InferenceRunner
+    from pst.weights import init_params
+    from test_host import _pad_like_the_reference
+
+    name = "T1046s1"
+    e = casp14[name]
+    n_all = e["pos"].shape[0]
+    sample = ppdb.StructureSample(nb_residues=n_all, aatype=np.zeros(n_all, np.int32), atom37_positions=e["pos"].astype(np.float32),
+                                  atom37_gt_exists=e["gt"], atom37_atom_exists=e["exists"])
+    pipe = DataPipeline({"num_neighbor": 50, "downsampling_ratio": 2, "padding_num_residue": 512, "crop_index": 512})
+    assert pipe.validate_sample(sample)
+    data = pipe.preprocess(sample)
+    g = fz.featurize(e["pos"].astype(np.float64), e["gt"], e["exists"], 50)
+    ref = _pad_like_the_reference(g, 50, 512, 2)
+    assert np.array_equal(data.graph.senders, ref["senders"]) and np.array_equal(data.graph.receivers, ref["receivers"])
+    assert np.array_equal(data.graph.n_node, ref["n_node"]) and np.array_equal(data.graph.tokens_mask, ref["tokens_mask"])
+    assert np.array_equal(data.graph.nodes_mask, ref["nodes_mask"])
+    ulp = np.spacing(np.abs(ref["edge_features"]).astype(np.float32))
+    assert (np.abs(data.graph.edge_features - ref["edge_features"]) <= ulp).all()
+    # both output formats round-trip
+    for fmt in ("npy", "npz"):
+        pipe.config["output_format"] = fmt
+        out = str(tmp_path / f"g.{fmt}")
+        pipe.save_output(data, out)
+        back = DataPipeline.load_output(out)
+        assert np.array_equal(back.graph.edge_features, data.graph.edge_features) and np.array_equal(back.graph.senders, data.graph.senders)
+    # the saved batch through the callable == the atoms through the fused call
+    cfg = TokenizerConfig.named(4096, 2, precision="fp32")
+    params = init_params(cfg, 0, "spread")
+    fn = InferenceRunner.prepare_tokenize_fn(cfg, [0])
+    t_graph = fn(params, None, back)["tokens"]
+    atoms, mask = valid_atoms(e)
+    t_atoms = fn(params, None, [(atoms, mask)])["tokens"][0]
+    nt = int(back.graph.tokens_mask.sum())
+    assert t_graph.shape == (256,) and nt == t_atoms.shape[0]
+    assert (t_graph[:nt] == t_atoms).mean() >= 0.99  # fp32 features (two-call path) vs compact features (fused call)
+    with pytest.raises(NotImplementedError):
+        DataPipeline({"num_neighbor": 50, "noise_level": 0.1}).preprocess(sample)

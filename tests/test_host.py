@@ -286,3 +286,27 @@ def test_alpha_carbon_flag_is_checked():
     cfg.data.data["graph_residue_loc_is_alphac"] = False
     with pytest.raises(NotImplementedError):
         TokenizerConfig.from_reference_cfg(cfg)
+
+
+def test_data_pipeline_mirror_host_side(tmp_path):
+    """filter rule (data/preprocessing.py:29-39), config defaults (data_pipeline.py:47-61) and the saved formats."""
+    from pst import pdb as ppdb
+    from pst import synthetic as syn
+    from pst.data_pipeline import BatchDataVQ3D, DataPipeline, ProteinGraph, filter_out_sample
+
+    bb = syn.make_backbones(4, [64])[0]
+    pos, gt, ex = syn.backbone_to_atom37(bb)
+    s = ppdb.StructureSample(nb_residues=64, aatype=np.full(64, 7, np.int32), atom37_positions=pos, atom37_gt_exists=gt, atom37_atom_exists=ex)
+    assert not filter_out_sample(s, 10, 1000) and filter_out_sample(s, 65, 1000) and filter_out_sample(s, 10, 63)
+    pipe = DataPipeline()
+    assert pipe.config["num_neighbor"] == 30 and pipe.config["downsampling_ratio"] == 4 and pipe.config["output_format"] == "npy"
+    assert pipe.validate_sample(s) and pipe.get_sample_info(s)["valid_residues"] == 64
+    g = ProteinGraph(n_node=np.array([3]), n_edge=np.array([6]), nodes_mask=np.ones((4, 1), bool), nodes_original_coordinates=np.zeros((4, 3), np.float32),
+                     node_features=np.zeros((4, 3), np.float32), edge_features=np.arange(8 * 27, dtype=np.float32).reshape(8, 27),
+                     tokens_mask=np.ones((4, 1), bool), senders=np.arange(8), receivers=np.repeat(np.arange(4), 2))
+    for fmt in ("npy", "npz"):
+        pipe.config["output_format"] = fmt
+        out = str(tmp_path / f"b.{fmt}")
+        pipe.save_output(BatchDataVQ3D(g, {}), out)
+        back = DataPipeline.load_output(out)
+        assert all(np.array_equal(getattr(back.graph, k), getattr(g, k)) for k in g._fields)
