@@ -162,7 +162,7 @@ int pst_tokenize(const pst_model* model, void* stream, const float* atoms,
  * the cached graphs).  The launch sequence of pst_tokenize depends only on its arguments (the host never reads device
  * data), so when a call repeats the pointers and sizes of an earlier one on a named stream, the library captures the
  * sequence into a CUDA graph once (on the second occurrence) and replays it afterwards: ~110 dependent kernels per
- * call otherwise pay a launch gap each (0.4 ms of a 9 ms call on B200).  Up to 8 argument sets are kept per model (LRU);
+ * call otherwise pay a launch gap each (0.4 ms of a 9 ms call on B200).  Up to 128 argument sets are kept per model (LRU: a streamed ragged pass keeps one graph per chunk);
  * the cache is the only mutable state of a pst_model and is guarded by a mutex.  Calls on the legacy / per-thread
  * default stream, calls made while the caller is itself capturing `stream`, and calls with profiling enabled are
  * enqueued kernel by kernel as before. */
