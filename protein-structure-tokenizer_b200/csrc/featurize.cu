@@ -286,6 +286,33 @@ __device__ __forceinline__ void bitonic_sort64(unsigned long long& a0, unsigned 
   for (int k = 2; k <= 64; k <<= 1) bitonic_stages(a0, a1, lane, k);
 }
 
+// The same network on 32-bit keys (the coarse pre-selection below): one shuffle and one min / max per exchange instead of
+// two shuffles, a two-word compare and two selects.
+__device__ __forceinline__ void ce_remote32(unsigned& a, int lane_mask, bool keep_min) {
+  const unsigned o = __shfl_xor_sync(0xffffffffu, a, lane_mask);
+  const unsigned lo = min(a, o), hi = max(a, o);
+  a = keep_min ? lo : hi;
+}
+__device__ __forceinline__ void bitonic_stages32(unsigned& a0, unsigned& a1, int lane, int k) {
+  const int e0 = 2 * lane;
+  const bool asc = (e0 & k) == 0;
+#pragma unroll
+  for (int j = 32; j >= 2; j >>= 1) {
+    if (j < k) {
+      const bool keep_min = (((e0 & j) == 0) == asc);
+      ce_remote32(a0, j >> 1, keep_min);
+      ce_remote32(a1, j >> 1, keep_min);
+    }
+  }
+  const unsigned lo = min(a0, a1), hi = max(a0, a1);
+  a0 = asc ? lo : hi;
+  a1 = asc ? hi : lo;
+}
+__device__ __forceinline__ void bitonic_sort64_32(unsigned& a0, unsigned& a1, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 64; k <<= 1) bitonic_stages32(a0, a1, lane, k);
+}
+
 // 1 / 1.5**k, k = 0..14: the RBF argument -d*d / 1.5**k (utils/protein_utils.py:266-270) is formed as a product; the one-ulp
 // (fp64) difference from the reference's division is 1e-14 relative on the result, far below the fp32 rounding.
 __constant__ double c_rbf_inv_scale[15] = {1.0 / 1.0, 1.0 / 1.5, 1.0 / 2.25, 1.0 / 3.375, 1.0 / 5.0625, 1.0 / 7.59375,
@@ -328,6 +355,16 @@ __device__ __forceinline__ unsigned long long packed_key(const double3& ci, cons
   return (bits & ~kIdxMask) | (unsigned long long)j;
 }
 
+// Coarse 32-bit key of the pre-selection: the squared distance rounded to fp32 (monotone in the fp64 value), its 11
+// lowest mantissa bits replaced by the candidate index.  Monotone: d2_a < d2_b  =>  key_a >> 11 <= key_b >> 11.
+__device__ __forceinline__ unsigned coarse_key(const double3& ci, const double* __restrict__ cx, const double* __restrict__ cy,
+                                               const double* __restrict__ cz, int base, int j, int L) {
+  if (j >= L) return 0xFFFFFFFFu;
+  const double dx = ci.x - cx[base + j], dy = ci.y - cy[base + j], dz = ci.z - cz[base + j];
+  const float d2 = (float)((dx * dx + dy * dy) + dz * dz);
+  return (__float_as_uint(d2) & ~(unsigned)kIdxMask) | (unsigned)j;
+}
+
 template <bool COMPACT>
 __global__ void __launch_bounds__(kKnnWarps * 32)
 knn_warp_kernel(const double* __restrict__ prep, const double* __restrict__ cen, const int32_t* __restrict__ offsets,
@@ -363,33 +400,39 @@ knn_warp_kernel(const double* __restrict__ prep, const double* __restrict__ cen,
   const double* cx = cen;
   const double* cy = cen + (size_t)R;
   const double* cz = cen + 2 * (size_t)R;
-  unsigned long long b0 = 0, b1 = 0;  // running 64 smallest keys, ascending, element e = 2*lane + r
+  // ---- phase 1 (round 2): COARSE pre-selection of 64 candidates on 32-bit keys (fp32 squared distance | index): the
+  // compare-exchange network was half of the kernel's instructions with 64-bit keys.  Phase 2 recomputes the exact
+  // fp64 keys of the 64 survivors and sorts those once.  The coarse key is monotone in the exact squared distance, so
+  // every candidate outside the coarse top 64 is at least as far as the 64-th one; the survivors therefore contain the
+  // exact top K + 4 whenever the truncated key of coarse rank K + 3 is strictly below that of rank 63 (checked; a
+  // row that fails goes to the exact kernel like a row with a clash in its head).
+  unsigned c0 = 0, c1 = 0;  // running 64 smallest coarse keys, ascending, element e = 2*lane + r
   const int n_chunks = (L + 63) >> 6;
   // Chunks are visited outwards from the one that holds the row itself; a chunk none of whose keys is below
   // the current 64-th smallest cannot change the result and is skipped after the distance evaluation.
   const int c_home = (row - base) >> 6;
-  unsigned long long bound = 0xFFFFFFFFFFFFFFFFull;
+  unsigned bound = 0xFFFFFFFFu;
   // Only keys below the current bound can enter the result.  They are few per chunk once the home chunk has set the
   // bound (about 100 per row over all other chunks at L = 512), so they are COMPACTED into a 64-entry buffer (ballot +
   // popc, order irrelevant: the keys are unique) and one sort-and-merge round is spent per full buffer instead of
   // per chunk (3.4 instead of 5.1 rounds per row at L = 512, 3.9 instead of 6.2 at L = 2 048).
-  unsigned long long* buf = reinterpret_cast<unsigned long long*>(s_d2[warp]);  // free until the feature phase
+  unsigned* buf = reinterpret_cast<unsigned*>(s_d2[warp]);  // free until the feature phase
   int cnt = 0;
-  auto merge_sorted = [&](unsigned long long a0, unsigned long long a1) {
-    // a ascending; reversed: element e <- element 63 - e (lane 31 - lane, registers swapped); min against b gives a
+  auto merge_sorted = [&](unsigned a0, unsigned a1) {
+    // a ascending; reversed: element e <- element 63 - e (lane 31 - lane, registers swapped); min against c gives a
     // bitonic sequence holding the 64 smallest of the union
-    const unsigned long long r0 = __shfl_xor_sync(0xffffffffu, a1, 31), r1 = __shfl_xor_sync(0xffffffffu, a0, 31);
-    b0 = r0 < b0 ? r0 : b0;
-    b1 = r1 < b1 ? r1 : b1;
-    bitonic_stages(b0, b1, lane, 64);  // bitonic -> ascending
-    bound = __shfl_sync(0xffffffffu, b1, 31);  // largest of the current 64 smallest
+    const unsigned r0 = __shfl_xor_sync(0xffffffffu, a1, 31), r1 = __shfl_xor_sync(0xffffffffu, a0, 31);
+    c0 = min(r0, c0);
+    c1 = min(r1, c1);
+    bitonic_stages32(c0, c1, lane, 64);  // bitonic -> ascending
+    bound = __shfl_sync(0xffffffffu, c1, 31);  // largest of the current 64 smallest
   };
   auto flush = [&]() {
     __syncwarp();
-    unsigned long long x0 = 2 * lane < cnt ? buf[2 * lane] : 0xFFFFFFFFFFFFFFFFull;
-    unsigned long long x1 = 2 * lane + 1 < cnt ? buf[2 * lane + 1] : 0xFFFFFFFFFFFFFFFFull;
+    unsigned x0 = 2 * lane < cnt ? buf[2 * lane] : 0xFFFFFFFFu;
+    unsigned x1 = 2 * lane + 1 < cnt ? buf[2 * lane + 1] : 0xFFFFFFFFu;
     __syncwarp();
-    bitonic_sort64(x0, x1, lane);
+    bitonic_sort64_32(x0, x1, lane);
     merge_sorted(x0, x1);
     cnt = 0;
   };
@@ -399,13 +442,13 @@ knn_warp_kernel(const double* __restrict__ prep, const double* __restrict__ cen,
     const int c = (step & 1) ? c_home + delta : c_home - delta;
     if (step > 0 && (c < 0 || c >= n_chunks)) continue;
     const int j0 = c * 64 + lane;  // lanes on consecutive candidates (which lane holds which key does not matter below)
-    const unsigned long long a0 = packed_key(ci, cx, cy, cz, base, j0, L);
-    const unsigned long long a1 = packed_key(ci, cx, cy, cz, base, j0 + 32, L);
+    const unsigned a0 = coarse_key(ci, cx, cy, cz, base, j0, L);
+    const unsigned a1 = coarse_key(ci, cx, cy, cz, base, j0 + 32, L);
     if (step == 0) {  // the home chunk sets the first bound
-      b0 = a0;
-      b1 = a1;
-      bitonic_sort64(b0, b1, lane);
-      bound = __shfl_sync(0xffffffffu, b1, 31);
+      c0 = a0;
+      c1 = a1;
+      bitonic_sort64_32(c0, c1, lane);
+      bound = __shfl_sync(0xffffffffu, c1, 31);
       continue;
     }
     unsigned m0 = __ballot_sync(0xffffffffu, a0 < bound), m1 = __ballot_sync(0xffffffffu, a1 < bound);
@@ -423,6 +466,20 @@ knn_warp_kernel(const double* __restrict__ prep, const double* __restrict__ cen,
     cnt += n;
   }
   if (cnt > 0) flush();
+  // the survivors contain the exact head only if the coarse keys separate rank K + 3 from rank 63
+  {
+    const int rk = min(K + 3, 62);
+    const unsigned krk = __shfl_sync(0xffffffffu, (rk & 1) ? c1 : c0, rk >> 1);
+    const unsigned k63 = __shfl_sync(0xffffffffu, c1, 31);
+    if (L > 64 && (krk >> 11) >= (k63 >> 11)) {  // L <= 64: every candidate is a survivor
+      if (lane == 0) redo[1 + atomicAdd(redo, 1)] = row;
+      return;
+    }
+  }
+  // ---- phase 2: exact fp64 keys of the 64 survivors, one 64-bit sort
+  unsigned long long b0 = c0 == 0xFFFFFFFFu ? 0xFFFFFFFFFFFFFFFFull : packed_key(ci, cx, cy, cz, base, (int)(c0 & (unsigned)kIdxMask), L);
+  unsigned long long b1 = c1 == 0xFFFFFFFFu ? 0xFFFFFFFFFFFFFFFFull : packed_key(ci, cx, cy, cz, base, (int)(c1 & (unsigned)kIdxMask), L);
+  bitonic_sort64(b0, b1, lane);
   // exactness check on the sorted head (ranks 0 .. K+2): equal (squared keys: equal or adjacent) truncated values ->
   // exact recompute
   {

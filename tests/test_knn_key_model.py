@@ -110,3 +110,59 @@ def test_constructed_same_sqrt_pair_needs_the_adjacent_key_rule(straddle):
     # ... while 'equal truncated values only' would let the straddling pair through with the wrong order
     _, flagged0 = packed_select(cen, K, "d2", 0)
     assert bool(flagged0[0]) == (not straddle)
+
+
+def coarse_preselect(cen: np.ndarray, k: int):
+    """Round-2 phase 1 of `knn_warp_kernel` as a NumPy model: 32-bit keys = fp32(d2) with the 11 lowest mantissa bits
+    replaced by the index; survivors = the 64 smallest; a row is handed to the exact kernel unless the truncated key of
+    coarse rank min(k + 3, 62) is strictly below that of rank 63.  Returns (survivor index sets, flagged)."""
+    L = cen.shape[0]
+    d = cen[:, None, :] - cen[None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    keys = (d2.astype(np.float32).view(np.uint32) & ~np.uint32(0x7FF)) | np.arange(L, dtype=np.uint32)[None, :]
+    order = np.argsort(keys, axis=1, kind="stable")
+    if L <= 64:
+        return order, np.zeros(L, bool)
+    srt = np.take_along_axis(keys, order[:, :64], axis=1) >> np.uint32(11)
+    rk = min(k + 3, 62)
+    return order[:, :64], srt[:, rk] >= srt[:, 63]
+
+
+def _exact_head(cen: np.ndarray, n: int) -> np.ndarray:
+    d = cen[:, None, :] - cen[None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    return np.argsort(d2, axis=1, kind="stable")[:, :n]
+
+
+def test_coarse_survivors_hold_the_exact_head_on_casp14_and_synthetic(casp14):
+    """the claim phase 2 relies on: an unflagged row's 64 survivors contain every candidate of exact rank 0 .. K+3
+    (what the exact sort and the clash check of the head look at)"""
+    from pst import synthetic as syn
+
+    sets = [_casp14_centroids(e) for e in casp14.values()]
+    for bb in syn.make_backbones(77, [512, 1024, 2048, 130]):
+        c = bb.astype(np.float64)
+        sets.append((((c[:, 0] + c[:, 1]) + c[:, 2]) + c[:, 3]) / 4.0)
+    rows = flagged_rows = 0
+    for cen in sets:
+        surv, flagged = coarse_preselect(cen, K)
+        head = _exact_head(cen, min(K + 4, cen.shape[0]))
+        ok = np.array([set(h.tolist()) <= set(s.tolist()) for h, s in zip(head, surv)])
+        assert ok[~flagged].all()
+        rows += len(cen)
+        flagged_rows += int(flagged.sum())
+    assert flagged_rows <= rows // 1000  # the exact kernel stays a rare path
+
+
+def test_coarse_preselection_flags_what_it_cannot_separate():
+    """more than 64 candidates whose squared distances agree to fp32's 13 kept mantissa bits: the coarse keys cannot tell
+    which of them belong to the head, the row must be flagged (points on a sphere around the first residue)"""
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((200, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    cen = np.concatenate([np.zeros((1, 3)), 10.0 * v * (1.0 + 1e-7 * rng.random((200, 1)))])
+    surv, flagged = coarse_preselect(cen, K)
+    assert flagged[0]
+    head = _exact_head(cen, K + 4)
+    ok = np.array([set(h.tolist()) <= set(s.tolist()) for h, s in zip(head, surv)])
+    assert ok[~flagged].all()
