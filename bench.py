@@ -59,7 +59,8 @@ def load_ncu_traffic():
     if not os.path.exists(p):
         return None
     with open(p) as fh:
-        return json.load(fh)
+        d = json.load(fh)
+    return d if all(k in d for k in ("msg", "upd", "residues", "source")) else None
 PORT_DETAIL = ("vectorised NumPy / torch-CPU restatement of the reference path (oracle/): it has none of the reference's per-edge "
                "Python loops, so it is FASTER than the reference's own code and the GPU/CPU ratio is conservative")
 

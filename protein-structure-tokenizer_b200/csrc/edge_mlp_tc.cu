@@ -37,14 +37,17 @@ constexpr int kThreads = kGroups * 128;      // threads of the tile groups (edge
 // edge MLP kernel: four tile SLOTS (A buffer + 128-column accumulator each), three work groups of epilogue warps and one
 // producer warpgroup (warps 12..15, one per TMEM lane quarter)
 constexpr int kImagesPerMlp = 4;  // operand images per MLP in pst_model::tc: W1[256:384], W2, W3, W1[0:128]
-constexpr int kSlots = 4;
-constexpr int kWorkGroups = 3;
+#ifndef PST_UPD_SLOTS
+#define PST_UPD_SLOTS 4
+#endif
+constexpr int kSlots = PST_UPD_SLOTS;
+constexpr int kWorkGroups = kSlots - 1;
 constexpr int kMlpThreads = (kWorkGroups + 1) * 128;
 // register split (setmaxnreg): 512 threads launch with 128 registers each; the work groups shrink to 120, the producer
 // warpgroup grows to 152 (3 * 128 * 120 + 128 * 152 = 65 536)
 constexpr int kRegsEpilogue = 120;
 constexpr int kRegsGather = 152;
-static_assert(kSlots == kGroups, "the A buffers and the selection-matrix slots are sized by kGroups");
+static_assert(kSlots <= kGroups, "the A buffers and the selection-matrix slots are sized by kGroups");
 constexpr uint32_t kMatBytes = 128 * 128 * 2;  // one 16-bit 128x128 operand image
 constexpr uint32_t kKBlockBytes = 128 * 128;    // 128 rows x 64 elements x 2 B
 constexpr uint32_t kSmemW = 3 * kMatBytes;
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
   // The CTA's tile sequence j = 0, 1, 2, ...: four consecutive tiles per round.  Tile j lives in slot j & 3 (A buffer +
   // accumulator) and is finished by work group j % 3; validity is monotone in j.
   const int round_stride = (int)gridDim.x * kSlots;
-  auto tile_of = [&](int j) { return (int)blockIdx.x * kSlots + (j & 3) + (j >> 2) * round_stride; };
+  auto tile_of = [&](int j) { return (int)blockIdx.x * kSlots + (j % kSlots) + (j / kSlots) * round_stride; };
 
   if (warp >= 4 * kWorkGroups) {
     // ================================ producer warpgroup =============================================
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
     // tcgen05.st.  Warp 12 then issues GEMM 1 (acc += e . W1[256:384]) as soon as the slot's TMA load has landed, so a
     // work group that picks the tile up finds the first product done: the load, the gather and GEMM 1 of tile j + 3
     // overlap the epilogues of tiles j .. j + 2.
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsGather));
+    if (kSlots == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsGather));
     const int q = warp - 4 * kWorkGroups;
     const int lane = tid & 31;
     const int last_recv = (p.E - 1) / p.K;
@@ -479,8 +482,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
     int tile = tile_of(0);
     int sender = tile < p.num_tiles ? __ldg(p.senders + min(tile * kTileM + q * 32 + lane, p.E - 1)) : 0;
     for (int j = 0; tile < p.num_tiles; ++j) {
-      const int s = j & 3;
-      const uint32_t par = (uint32_t)(j >> 2) & 1u;
+      const int s = j % kSlots;
+      const uint32_t par = (uint32_t)(j / kSlots) & 1u;
       const int er = min(tile * kTileM + q * 32 + lane, p.E - 1);
       uint32_t a[64], b[64];
       {
@@ -539,13 +542,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
     }
   } else {
     // ================================ work groups (epilogue warps) ========================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
+    if (kSlots == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
     const int g = warp >> 2;          // work group
     const int gt = tid & 127;         // thread within the group == accumulator row
     const int wq = warp & 3;          // TMEM lane quarter this warp may access
     for (int j = g; tile_of(j) < p.num_tiles; j += kWorkGroups) {
-      const int s = j & 3;
-      const uint32_t par = (uint32_t)(j >> 2) & 1u;
+      const int s = j % kSlots;
+      const uint32_t par = (uint32_t)(j / kSlots) & 1u;
       const int tile = tile_of(j);
       const int row0 = tile * kTileM;
       const int first_recv = row0 / p.K;
@@ -1460,7 +1463,7 @@ int pst_launch_edge_mlp_tc(const pst_model* m, cudaStream_t st, int layer, int m
   if (int rc = make_edge_state_map(e, p.E, &tmap)) return rc;
   const bool half = m->cfg.precision == PST_PREC_FP16;
   int grid = m->num_sms;
-  const int need = (p.num_tiles + kGroups - 1) / kGroups;
+  const int need = (p.num_tiles + kSlots - 1) / kSlots;
   if (grid > need) grid = need;
   if (mode == 0) {
     if (half) edge_mlp_tc_kernel<__half, 0><<<grid, kMlpThreads, kSmemTotal, st>>>(p, tmap);

@@ -96,9 +96,12 @@ def traffic(src, dst, residues):
     out = {}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]]
-        if "edge_mlp_tc_kernel" not in name:
+        if "edge_msg_t_kernel" in name:
+            key = "msg"
+        elif "edge_mlp_tc_kernel" in name:
+            key = "msg" if ", 0>" in name or "(int)0>" in name else "upd"
+        else:
             continue
-        key = "msg" if ", 0>" in name or "(int)0>" in name else "upd"
         tot = sum(float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         out.setdefault(key, []).append(tot)
     doc = {k: sum(v) / len(v) for k, v in out.items()}
