@@ -16,7 +16,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 SOURCES = {
     "featurize.cu": ["-fmad=false"],
     "encoder_fp32.cu": [],
-    "edge_mlp_tc.cu": (["-DPST_EDGE_PROFILE"] if os.environ.get("PST_EDGE_PROFILE") else []),
+    # -DPST_T_PROFILE: per-role cycle counters of edge_msg_t_kernel, printed by block 0 (tools/build_variant.sh)
+    "edge_mlp_tc.cu": (["-DPST_T_PROFILE"] if os.environ.get("PST_T_PROFILE") else []),
     "linear_tc.cu": [],
     "node_chain_tc.cu": [],
     "quantize.cu": [],
@@ -33,7 +34,7 @@ def nvcc() -> str:
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
-    objdir = os.path.join(HERE, "build_prof" if os.environ.get("PST_EDGE_PROFILE") else "build")
+    objdir = os.path.join(HERE, "build_prof" if os.environ.get("PST_T_PROFILE") else "build")
     os.makedirs(objdir, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "pst_abi.h"), __file__]
     newest = max(os.path.getmtime(d) for d in deps)

@@ -384,21 +384,6 @@ __device__ __forceinline__ void gelu_epilogue(uint32_t tmem_row, uint8_t* sA, in
 // boxes are the K-major operand image.  The gathered addend rows never touch shared memory: each thread reads its
 // own sender / receiver rows with 32-byte loads and writes its accumulator row with tcgen05.st.  Activations are
 // written thread-per-row into the operand image (16-byte chunks at chunk ^ (row & 7): conflict-free).
-// Optional per-phase cycle accounting (debug builds only: -DPST_EDGE_PROFILE): group 0 / thread 0 of every
-// CTA accumulates clock64() deltas per phase into g_edge_prof[mode][phase].
-#ifdef PST_EDGE_PROFILE
-__device__ unsigned long long g_edge_prof[2][16];
-#define PHASE(i)                                              \
-  do {                                                        \
-    if (tid == 0) {                                           \
-      long long _t = clock64();                               \
-      prof_acc[i] += (unsigned long long)(_t - prof_last);    \
-      prof_last = _t;                                         \
-    }                                                         \
-  } while (0)
-#else
-#define PHASE(i) do {} while (0)
-#endif
 
 template <typename T16, int MODE>
 __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpParams p, const __grid_constant__ CUtensorMap tmap_e) {
@@ -1348,16 +1333,6 @@ __global__ void build_weight_image_kernel(const float* __restrict__ w, uint16_t*
 
 }  // namespace
 
-#ifdef PST_EDGE_PROFILE
-extern "C" int pst_debug_edge_profile(unsigned long long* out32, int reset) {
-  if (cudaMemcpyFromSymbol(out32, g_edge_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
-  if (reset) {
-    unsigned long long z[32] = {0};
-    cudaMemcpyToSymbol(g_edge_prof, z, sizeof(z));
-  }
-  return 0;
-}
-#endif
 
 int pst_prepare_tc_weights(pst_model* m) {
   const int layers = m->cfg.gnn_layers;
