@@ -162,11 +162,15 @@ int pst_tokenize(const pst_model* model, void* stream, const float* atoms,
  * the cached graphs).  The launch sequence of pst_tokenize depends only on its arguments (the host never reads device
  * data), so when a call repeats the pointers and sizes of an earlier one on a named stream, the library captures the
  * sequence into a CUDA graph once (on the second occurrence) and replays it afterwards: ~110 dependent kernels per
- * call otherwise pay a launch gap each (0.4 ms of a 9 ms call on B200).  Up to 128 argument sets are kept per model (LRU: a streamed ragged pass keeps one graph per chunk);
+ * call otherwise pay a launch gap each (0.4 ms of a 9 ms call on B200).  The cache is keyed by the BUFFERS of a call, up to 64 sets per model (LRU); when the same buffers come back with other sizes (the next ragged chunk of a stream) the instantiated graph is updated in place (cudaGraphExecUpdate);
  * the cache is the only mutable state of a pst_model and is guarded by a mutex.  Calls on the legacy / per-thread
  * default stream, calls made while the caller is itself capturing `stream`, and calls with profiling enabled are
  * enqueued kernel by kernel as before. */
 int pst_graph_cache_enable(const pst_model* model, int enable);
+
+/* How the pst_tokenize calls of this model were enqueued so far: counts4 = {graph replays with unchanged sizes, graph
+ * launches after an in-place update to new sizes, launches after a fresh instantiation, kernel-by-kernel calls}. */
+int pst_graph_cache_stats(const pst_model* model, int* counts4);
 
 /* HOST function (no CUDA): PDB text -> atom37 arrays.  Replaces protein_structure_from_pdb_string
  * (structure_tokenizer/data/protein_structure_sample.py:166-248) together with the BioPython PDBParser semantics it

@@ -10,30 +10,34 @@
 #include <mutex>
 #include <vector>
 
+// The cache is keyed by the BUFFERS of a call (a staging slot of a chunk pipeline, a resident batch), not by its sizes:
+// when the same buffers come back with another (B, R, T) -- the next ragged chunk of a stream -- the launch sequence is
+// captured again and the instantiated graph is UPDATED in place (cudaGraphExecUpdate: same kernels in the same order,
+// new parameters and grids), so a stream of distinct chunk shapes also runs as one graph launch per call.
 struct PstGraphKey {
   const void *atoms, *mask, *offsets, *token_offsets, *tokens, *workspace;
   size_t ws_bytes;
-  int apr, B, R, T;
+  int apr;
   bool operator==(const PstGraphKey& o) const {
     return atoms == o.atoms && mask == o.mask && offsets == o.offsets && token_offsets == o.token_offsets &&
-           tokens == o.tokens && workspace == o.workspace && ws_bytes == o.ws_bytes && apr == o.apr && B == o.B &&
-           R == o.R && T == o.T;
+           tokens == o.tokens && workspace == o.workspace && ws_bytes == o.ws_bytes && apr == o.apr;
   }
 };
 struct PstGraphEntry {
   PstGraphKey key;
   cudaGraphExec_t exec = nullptr;
+  int B = -1, R = -1, T = -1;  // sizes the instantiated graph currently holds
   int launches = 0;
   bool failed = false;
   unsigned long long last_use = 0;
 };
 struct PstGraphCache {
-  // a streamed ragged workload sends a different (B, R, T) per chunk: every chunk of a repeated pass keeps its own graph
-  static constexpr size_t kMaxEntries = 128;
+  static constexpr size_t kMaxEntries = 64;  // buffer sets (a resident pass over many chunks has one per chunk)
   std::mutex mu;
   std::vector<PstGraphEntry> entries;
   unsigned long long clock = 0;
   bool enabled = true;
+  int n_replay = 0, n_update = 0, n_instantiate = 0, n_eager = 0;  // pst_graph_cache_stats
   PstGraphEntry* find(const PstGraphKey& k) {
     for (auto& e : entries)
       if (e.key == k) return &e;
@@ -445,15 +449,15 @@ int pst_tokenize(const pst_model* m, void* stream, const float* atoms, const uin
   if (gc && gc->enabled && named_stream && !m->prof_on) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
-      PstGraphKey key{atoms, atom_mask, offsets, token_offsets, tokens_out, workspace, workspace_bytes,
-                      atoms_per_residue, num_structures, total_residues, total_tokens};
+      PstGraphKey key{atoms, atom_mask, offsets, token_offsets, tokens_out, workspace, workspace_bytes, atoms_per_residue};
       std::lock_guard<std::mutex> lock(gc->mu);
       PstGraphEntry* e = gc->find(key);
       if (!e) {
-        gc->insert(key);  // first sighting: run eagerly below, capture if it comes back
-      } else if (e->exec) {
+        gc->insert(key);  // first sighting: run eagerly below, capture if the buffers come back
+      } else if (e->exec && e->B == num_structures && e->R == total_residues && e->T == total_tokens) {
         e->last_use = ++gc->clock;
         m->launch_count = e->launches;
+        ++gc->n_replay;
         return cudaGraphLaunch(e->exec, st) == cudaSuccess ? PST_OK : PST_ERR_CUDA;
       } else if (!e->failed) {
         e->last_use = ++gc->clock;
@@ -462,22 +466,49 @@ int pst_tokenize(const pst_model* m, void* stream, const float* atoms, const uin
           const int crc = tokenize_enqueue(m, st, atoms, atom_mask, atoms_per_residue, offsets, token_offsets,
                                            num_structures, total_residues, total_tokens, tokens_out, workspace);
           const cudaError_t end = cudaStreamEndCapture(st, &graph);
-          if (crc == PST_OK && end == cudaSuccess && graph &&
-              cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess) {
-            e->launches = m->launch_count;
-            cudaGraphDestroy(graph);
-            return cudaGraphLaunch(e->exec, st) == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+          if (crc == PST_OK && end == cudaSuccess && graph) {
+            bool ready = false;
+            if (e->exec) {  // same buffers, new sizes: retarget the instantiated graph
+              cudaGraphExecUpdateResultInfo info;
+              ready = cudaGraphExecUpdate(e->exec, graph, &info) == cudaSuccess;
+              if (ready) ++gc->n_update;
+              if (!ready) {
+                cudaGetLastError();
+                cudaGraphExecDestroy(e->exec);
+                e->exec = nullptr;
+              }
+            }
+            if (!ready) {
+              ready = cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess;
+              if (ready) ++gc->n_instantiate;
+            }
+            if (ready) {
+              e->B = num_structures; e->R = total_residues; e->T = total_tokens;
+              e->launches = m->launch_count;
+              cudaGraphDestroy(graph);
+              return cudaGraphLaunch(e->exec, st) == cudaSuccess ? PST_OK : PST_ERR_CUDA;
+            }
           }
           if (graph) cudaGraphDestroy(graph);
         }
         cudaGetLastError();  // a failed capture is not an error of the call: enqueue eagerly from now on
+        if (e->exec) cudaGraphExecDestroy(e->exec);
         e->exec = nullptr;
         e->failed = true;
       }
     }
   }
+  if (gc) ++gc->n_eager;
   return tokenize_enqueue(m, st, atoms, atom_mask, atoms_per_residue, offsets, token_offsets, num_structures,
                           total_residues, total_tokens, tokens_out, workspace);
+}
+
+int pst_graph_cache_stats(const pst_model* m, int* counts4) {
+  if (!m || !m->graphs || !counts4) return PST_ERR_BAD_ARGUMENT;
+  std::lock_guard<std::mutex> lock(m->graphs->mu);
+  counts4[0] = m->graphs->n_replay; counts4[1] = m->graphs->n_update;
+  counts4[2] = m->graphs->n_instantiate; counts4[3] = m->graphs->n_eager;
+  return PST_OK;
 }
 
 int pst_graph_cache_enable(const pst_model* m, int enable) {

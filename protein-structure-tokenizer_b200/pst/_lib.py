@@ -60,6 +60,7 @@ SIGNATURES = {
     "pst_read_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pst_last_launch_count": (C.c_int, [C.c_void_p]),
     "pst_graph_cache_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "pst_graph_cache_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "pst_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pst_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }

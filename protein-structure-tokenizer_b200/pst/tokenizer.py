@@ -214,6 +214,12 @@ class StructureTokenizer:
         """CUDA-graph replay of repeated pst_tokenize calls (on by default; see include/pst_abi.h)."""
         _lib.check(self.lib.pst_graph_cache_enable(self._h, int(on)), "pst_graph_cache_enable")
 
+    def graph_cache_stats(self) -> dict:
+        """{'replay', 'update', 'instantiate', 'eager'}: how the fused calls of this model were enqueued so far."""
+        c = (C.c_int * 4)()
+        _lib.check(self.lib.pst_graph_cache_stats(self._h, c), "pst_graph_cache_stats")
+        return {"replay": c[0], "update": c[1], "instantiate": c[2], "eager": c[3]}
+
     def profile_enable(self, on: bool = True) -> None:
         _lib.check(self.lib.pst_profile_enable(self._h, int(on)), "pst_profile_enable")
 

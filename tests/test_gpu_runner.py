@@ -255,3 +255,34 @@ def test_data_pipeline_mirror_feeds_the_callable(built_lib, casp14, tmp_path):
     assert (t_graph[:nt] == t_atoms).mean() >= 0.99  # fp32 features (two-call path) vs compact features (fused call)
     with pytest.raises(NotImplementedError):
         DataPipeline({"num_neighbor": 50, "noise_level": 0.1}).preprocess(sample)
+
+
+def test_ragged_chunk_stream_runs_on_graph_updates(built_lib):
+    """A stream of chunks with distinct (B, R, T) through the two staging slots of tokenize(): after the first two
+    sightings of a slot's buffers every call is ONE graph launch, retargeted in place to the chunk's sizes
+    (cudaGraphExecUpdate), and the tokens equal the kernel-by-kernel path's."""
+    from pst import synthetic as syn
+    from pst.config import TokenizerConfig
+    from pst.tokenizer import StructureTokenizer
+    from pst.weights import init_params
+
+    cfg = TokenizerConfig.named(4096, 1, precision="fp16")
+    params = init_params(cfg, 0, "spread")
+    lengths = [64, 200, 90, 150, 77, 300, 64, 128, 51, 260, 99, 180, 70, 310, 55, 140]
+    bbs = syn.make_backbones(19, lengths)
+    eager = StructureTokenizer(cfg, params, max_rows_per_call=420)
+    eager.graph_cache_enable(False)
+    want = eager.tokenize(bbs)
+    tok = StructureTokenizer(cfg, params, max_rows_per_call=420)
+    n_chunks = len(tok._chunks(lengths))
+    assert n_chunks >= 6
+    got = tok.tokenize(bbs)
+    st = tok.graph_cache_stats()
+    assert all(np.array_equal(a, b) for a, b in zip(want, got))
+    # two slots: each slot's first call is eager, its second instantiates, every later call updates (sizes differ) or replays
+    assert st["eager"] == 2 and st["instantiate"] == 2 and st["update"] + st["replay"] == n_chunks - 4, st
+    assert st["update"] >= 1
+    got2 = tok.tokenize(bbs)  # second pass over the same stream
+    st2 = tok.graph_cache_stats()
+    assert all(np.array_equal(a, b) for a, b in zip(want, got2))
+    assert st2["eager"] == 2 and st2["instantiate"] == 2, st2
