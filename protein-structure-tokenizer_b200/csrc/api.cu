@@ -233,6 +233,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   m->graphs = new (std::nothrow) PstGraphCache();
   if (m->graphs) { const char* g = getenv("PST_CUDA_GRAPH"); m->graphs->enabled = !(g && g[0] == '0'); }
   { const char* t = getenv("PST_MSG_T"); m->use_msg_t = !(t && t[0] == '0'); }
+  { const char* t = getenv("PST_FUSED_RESAMPLER"); m->use_fused_resampler = !(t && t[0] == '0'); }
   m->linear_tc = nullptr;
   m->node_chain = nullptr;
   m->embed_img_dev = nullptr;

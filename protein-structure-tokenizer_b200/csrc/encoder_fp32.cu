@@ -531,6 +531,15 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     if (n < 0) return n;
     return L.count + n;
   }
+  if (tc && cfg.downsampling_ratio > 1 && cfg.num_blocks <= 3 && m->use_fused_resampler && T > 0) {
+    // df > 1: residue track and token track as two chain kernels (node_chain_tc.cu); k / v of the three blocks live in
+    // buffers the GNN no longer needs (ws.u holds four [R,128] arrays)
+    PstSpan span(m, st, 5);
+    float* kv[6] = {ws.kx, ws.vx, ws.u, ws.u + (size_t)R * D, ws.u + 2 * (size_t)R * D, ws.u + 3 * (size_t)R * D};
+    int n = pst_launch_resampler_dfn(m, st, ws.h, offsets, token_offsets, B, R, T, kv, ws.q, z_out);
+    if (n < 0) return n;
+    return L.count + n;
+  }
   token_embed_kernel<<<(T + 7) / 8, 256, 0, st>>>(m->w.token_table, token_offsets, B, ws.res, T);
   ++L.count;
   const float* orig = ws.h;

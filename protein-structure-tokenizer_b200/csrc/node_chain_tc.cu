@@ -750,6 +750,303 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
   chain_teardown(S, warp);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Resampler for downsampling_ratio > 1 (round 2; reference: model/modules.py:438-636, masks model/model.py:264-318):
+// token t of a structure attends its residues t*df .. t*df+df-1.  The residue ("original") track does not depend on
+// the token track, so the three blocks split into TWO chain kernels instead of ~50 launches with [R,128] / [T,128]
+// intermediates bouncing through HBM:
+//   resampler_orig_kernel   per 128-residue tile, for every block b:  k_b = LN_d(orig).Wk, v_b = LN_d(orig).Wv -> HBM,
+//                           orig += Transition(orig)  (not after the last block: modules.py:624-629 result unused)
+//   resampler_token_kernel  per 128-token tile, for every block b:  q = LN_q(res).Wq * 32^-1/2, gate = LN_q(res).Wg + bg,
+//                           a = softmax_j(q . k_b[row0 + j]) . v_b[row0 + j]  per head (thread = token row x 2 heads:
+//                           thread-local), res += (a * sigmoid(gate)).Wo + bo, res += Transition(res);  then the head
+//                           (spherical norm + down_proj) as in the df = 1 kernel.
+struct OB {  // per-block parameter vectors of the residue track
+  enum { kDnS = 0, kDnO = 128, kOtLnS = 256, kOtLnO = 384, kOtB1 = 512, kOtB2 = 768, kBlk = 896 };
+};
+struct ResamplerOrigParams {
+  const float* h;            // [R,128] node features after the GNN
+  float* k[3];               // per block [R,128]
+  float* v[3];
+  int num_blocks;
+  const uint8_t* const* sched;
+  int n_sched;
+  int R, num_tiles;
+  uint32_t idesc;
+  float cv[3 * OB::kBlk];
+};
+
+__global__ void __launch_bounds__(kThreads, 1) resampler_orig_kernel(const __grid_constant__ ResamplerOrigParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  Setup S = chain_setup(smem, tid, warp);
+  const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
+  if (warp == kEpiThreads / 32) {
+    if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
+    __syncwarp();
+    chain_teardown(S, warp);
+    return;
+  }
+  uint8_t* X = smem + kOffX;
+  uint8_t* U = smem + kOffU;
+  const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
+  Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
+  const uint32_t t_orig = S.tmem_base + 0, t_accA = S.tmem_base + 128, t_accB = S.tmem_base + 256, t_accC = S.tmem_base + 384;
+  Groups G{S.ring, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, p.idesc, 0, 0, tid};
+
+  for (int ti = 0, tile = blockIdx.x; ti < my_tiles; ++ti, tile += gridDim.x) {  // tiles past the end: all rows invalid
+    const int row = tile * 128 + e.row;
+    const bool valid = row < p.R;
+    float x[2][32];
+    load_row_half(e, p.h + (size_t)row * D, valid, x);
+    tmem_st_half(e, t_orig, x);
+#pragma unroll 1
+    for (int b = 0; b < p.num_blocks; ++b) {
+      const int w = b * OB::kBlk;
+      if (b > 0) tmem_ld_half(e, t_orig, x);
+      layer_norm_row(e, x, p.cv, w + OB::kDnS, w + OB::kDnO);
+      split_store_half(e, X, x);
+      publish();
+      G.issue(X_addr, t_accA, 0u);  // k = LNd(orig) . Wk
+      G.issue(X_addr, t_accB, 0u);  // v = LNd(orig) . Wv
+#pragma unroll 1
+      for (int kv = 0; kv < 2; ++kv) {
+        G.wait_next();
+        tmem_ld_half(e, kv ? t_accB : t_accA, x);
+        if (valid) {
+          float* dst = (kv ? p.v[b] : p.k[b]) + (size_t)row * D + e.half * 64;
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st256f(dst + q * 32 + j * 8, &x[q][j * 8]);
+        }
+      }
+      if (b < p.num_blocks - 1) {  // original transition (modules.py:227-252)
+        tmem_ld_half(e, t_orig, x);
+        layer_norm_row(e, x, p.cv, w + OB::kOtLnS, w + OB::kOtLnO);
+        split_store_half(e, X, x);
+        publish();
+        chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accC, 2, p.cv, w + OB::kOtB1);
+        float r[2][32];
+        tmem_ld_half(e, t_accC, x);
+        tmem_ld_half(e, t_orig, r);
+        add_residual_bias_half(e, x, r, p.cv, w + OB::kOtB2);
+        tmem_st_half(e, t_orig, x);
+      }
+    }
+    tc_before();
+    epi_sync();  // the TMEM state is rewritten by the next tile
+  }
+  chain_teardown(S, warp);
+}
+
+struct TB {  // per-block parameter vectors of the token track
+  enum { kQnS = 0, kQnO = 128, kBg = 256, kBo = 384, kRtLnS = 512, kRtLnO = 640, kRtB1 = 768, kRtB2 = 1024, kBlk = 1152 };
+};
+struct ResamplerTokenParams {
+  const float* token_table;  // [max_out_len,128] PE of the token index (modules.py:486-500)
+  const int2* info;          // per token: (index inside its structure, first residue row it attends)
+  const float* k[3];         // per block [R,128]
+  const float* v[3];
+  float* z;                  // [T,8]
+  int num_blocks, df;
+  const float* down_w;
+  const float* down_b;
+  int C;
+  const uint8_t* const* sched;
+  int n_sched;
+  int T, num_tiles;
+  uint32_t idesc;
+  float cv[3 * TB::kBlk];
+};
+static_assert(sizeof(ResamplerTokenParams) <= 32764, "kernel parameter space");
+
+__global__ void __launch_bounds__(kThreads, 1) resampler_token_kernel(const __grid_constant__ ResamplerTokenParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  Setup S = chain_setup(smem, tid, warp);
+  const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (warp == kEpiThreads / 32) {
+    if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
+    __syncwarp();
+    chain_teardown(S, warp);
+    return;
+  }
+  uint8_t* X = smem + kOffX;
+  uint8_t* U = smem + kOffU;
+  const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
+  Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
+  const uint32_t t_res = S.tmem_base + 0, t_accA = S.tmem_base + 128, t_accB = S.tmem_base + 256, t_accC = S.tmem_base + 384;
+  Groups G{S.ring, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, p.idesc, 0, 0, tid};
+  const float qscale = 0.17677669529663687f;  // 32 ** -0.5 (modules.py:334)
+
+  for (int ti = 0, tile = blockIdx.x; ti < my_tiles; ++ti, tile += gridDim.x) {
+    const int t = tile * 128 + e.row;
+    const bool valid = t < p.T;
+    const int2 inf = valid ? __ldg(p.info + t) : make_int2(0, 0);
+    float x[2][32];
+    load_row_half(e, p.token_table + (size_t)inf.x * D, valid, x);
+    tmem_st_half(e, t_res, x);
+#pragma unroll 1
+    for (int b = 0; b < p.num_blocks; ++b) {
+      const int w = b * TB::kBlk;
+      if (b > 0) tmem_ld_half(e, t_res, x);
+      layer_norm_row(e, x, p.cv, w + TB::kQnS, w + TB::kQnO);
+      split_store_half(e, X, x);
+      publish();
+      G.issue(X_addr, t_accA, 0u);  // q    = LNq(res) . Wq
+      G.issue(X_addr, t_accB, 0u);  // gate = LNq(res) . Wg
+      G.wait_next();
+      G.wait_next();
+      // ---- local attention (modules.py:303-380; model/model.py:264-318: token t sees its own df residues): this thread
+      // holds heads 2 half, 2 half + 1 of its token (32 dims each); softmax over df logits per head, all in registers
+      {
+        tmem_ld_half(e, t_accA, x);
+        const float* kb = p.k[b] + (size_t)inf.y * D + e.half * 64;
+        const float* vb = p.v[b] + (size_t)inf.y * D + e.half * 64;
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          // df <= 8: the loops are unrolled over 8 with a predicate so that the logits stay in registers
+          float logit[8];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            logit[j] = -INFINITY;
+            if (j < p.df) {
+              float acc = 0.f;
+              if (valid) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  float kr[8];
+                  ld256f(kb + (size_t)j * D + hq * 32 + c * 8, kr);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) acc = fmaf(x[hq][c * 8 + i] * qscale, kr[i], acc);
+                }
+              }
+              logit[j] = acc;
+              mx = fmaxf(mx, acc);
+            }
+          }
+          float den = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            logit[j] = j < p.df ? expf(logit[j] - mx) : 0.f;
+            den += logit[j];
+          }
+          float a[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < p.df && valid) {
+              const float pj = logit[j] / den;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float vr[8];
+                ld256f(vb + (size_t)j * D + hq * 32 + c * 8, vr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[c * 8 + i] = fmaf(pj, vr[i], a[c * 8 + i]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[hq][i] = a[i];
+        }
+        float g[2][32];
+        tmem_ld_half(e, t_accB, g);
+        const int bg = w + TB::kBg + e.half * 64;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[q][j] *= sigmoid_f(g[q][j] + p.cv[bg + q * 32 + j]);
+      }
+      split_store_half(e, X, x);
+      publish();
+      G.issue(X_addr, t_accA, 0u);  // . Wo
+      G.wait_next();
+      {
+        float r[2][32];
+        tmem_ld_half(e, t_accA, x);
+        tmem_ld_half(e, t_res, r);
+        add_residual_bias_half(e, x, r, p.cv, w + TB::kBo);
+      }
+      tmem_st_half(e, t_res, x);
+      // ---- resampled transition (modules.py:227-252) ------------------------------------------------------------
+      layer_norm_row(e, x, p.cv, w + TB::kRtLnS, w + TB::kRtLnO);
+      split_store_half(e, X, x);
+      publish();
+      chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accC, 2, p.cv, w + TB::kRtB1);
+      {
+        float r[2][32];
+        tmem_ld_half(e, t_accC, x);
+        tmem_ld_half(e, t_res, r);
+        add_residual_bias_half(e, x, r, p.cv, w + TB::kRtB2);
+      }
+      tmem_st_half(e, t_res, x);
+    }
+    // ---- head (model.py:169-174,148-164): z = (res / (||res|| + 1e-6)) . Wd + bd -------------------------------------
+    {
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ss = fmaf(x[q][j], x[q][j], ss);
+      e.red[e.half * 128 + e.row] = ss;
+      epi_sync();
+      const float d = sqrtf(e.red[e.row] + e.red[128 + e.row]) + 1e-6f;
+      float zc[PST_C8];
+#pragma unroll
+      for (int c = 0; c < PST_C8; ++c) zc[c] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+#ifdef PST_NODE_RECIP_MUL
+          const float r = x[q][j] * (1.0f / d);
+#else
+          const float r = x[q][j] / d;
+#endif
+          const float4* wr = reinterpret_cast<const float4*>(p.down_w + (size_t)(e.half * 64 + q * 32 + j) * PST_C8);
+          const float4 w0 = __ldg(wr), w1 = __ldg(wr + 1);
+          zc[0] = fmaf(r, w0.x, zc[0]); zc[1] = fmaf(r, w0.y, zc[1]); zc[2] = fmaf(r, w0.z, zc[2]); zc[3] = fmaf(r, w0.w, zc[3]);
+          zc[4] = fmaf(r, w1.x, zc[4]); zc[5] = fmaf(r, w1.y, zc[5]); zc[6] = fmaf(r, w1.z, zc[6]); zc[7] = fmaf(r, w1.w, zc[7]);
+        }
+      float* zs = reinterpret_cast<float*>(U);  // U is free: [128 rows][8]
+      if (e.half == 1) {
+        *reinterpret_cast<float4*>(zs + e.row * 8) = make_float4(zc[0], zc[1], zc[2], zc[3]);
+        *reinterpret_cast<float4*>(zs + e.row * 8 + 4) = make_float4(zc[4], zc[5], zc[6], zc[7]);
+      }
+      epi_sync();
+      if (e.half == 0 && valid) {
+        const float4 a = *reinterpret_cast<const float4*>(zs + e.row * 8), bq = *reinterpret_cast<const float4*>(zs + e.row * 8 + 4);
+        float o[PST_C8] = {zc[0] + a.x, zc[1] + a.y, zc[2] + a.z, zc[3] + a.w, zc[4] + bq.x, zc[5] + bq.y, zc[6] + bq.z, zc[7] + bq.w};
+#pragma unroll
+        for (int c = 0; c < PST_C8; ++c) o[c] = c < p.C ? o[c] + __ldg(p.down_b + c) : 0.f;
+        float4* zd = reinterpret_cast<float4*>(p.z + (size_t)t * PST_C8);
+        zd[0] = make_float4(o[0], o[1], o[2], o[3]);
+        zd[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      tc_before();
+      epi_sync();  // zs (in U) and the TMEM state are rewritten by the next tile
+    }
+  }
+  chain_teardown(S, warp);
+}
+
+// per token: its index inside its structure and the first residue row it attends (offsets[b] + local * df)
+__global__ void token_info_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ token_offsets, int B, int df, int T,
+                                  int2* __restrict__ info) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int lo = 0, hi = B;  // largest b with token_offsets[b] <= t
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (token_offsets[mid] <= t) lo = mid; else hi = mid;
+  }
+  const int local = t - token_offsets[lo];
+  info[t] = make_int2(local, offsets[lo] + local * df);
+}
+
 struct Entry {
   const float* w;
   int K, N;
@@ -765,6 +1062,7 @@ struct PstNodeChain {
   const uint8_t** sched_dev = nullptr;  // all schedules, concatenated
   int layer_off[PST_MAX_LAYERS], layer_n[PST_MAX_LAYERS], layer_nout[PST_MAX_LAYERS];
   int resampler_off = 0, resampler_n = 0;
+  int orig_off = 0, orig_n = 0, token_off = 0, token_n = 0;  // df > 1: residue-track / token-track schedules
 };
 
 // persistent grid of whole clusters: one CTA per SM, at most one per tile
@@ -842,11 +1140,32 @@ int pst_prepare_node_chain(pst_model* m) {
     if (b < m->cfg.num_blocks - 1) push_chunked(w.ot_w1, w.ot_w2, PST_TRANS, 2);
   }
   C.resampler_n = (int)all.size() - C.resampler_off;
+  // resampler (df > 1): residue track (per block key, value, original transition) and token track (per block query,
+  // gate, output, resampled transition), in the issue order of resampler_orig_kernel / resampler_token_kernel
+  C.orig_off = (int)all.size();
+  for (int b = 0; b < m->cfg.num_blocks; ++b) {
+    const PstBlockW& w = m->w.block[b];
+    push_unit(w.wk, D, D, 0, 0);
+    push_unit(w.wv, D, D, 0, 0);
+    if (b < m->cfg.num_blocks - 1) push_chunked(w.ot_w1, w.ot_w2, PST_TRANS, 2);
+  }
+  C.orig_n = (int)all.size() - C.orig_off;
+  C.token_off = (int)all.size();
+  for (int b = 0; b < m->cfg.num_blocks; ++b) {
+    const PstBlockW& w = m->w.block[b];
+    push_unit(w.wq, D, D, 0, 0);
+    push_unit(w.wg, D, D, 0, 0);
+    push_unit(w.wo, D, D, 0, 0);
+    push_chunked(w.rt_w1, w.rt_w2, PST_TRANS, 2);
+  }
+  C.token_n = (int)all.size() - C.token_off;
   if (!ok) return PST_ERR_BAD_ARGUMENT;
   if (cudaMalloc(&C.sched_dev, all.size() * sizeof(void*)) != cudaSuccess) return PST_ERR_CUDA;
   if (cudaMemcpy(C.sched_dev, all.data(), all.size() * sizeof(void*), cudaMemcpyHostToDevice) != cudaSuccess) return PST_ERR_CUDA;
   if (cudaFuncSetAttribute(node_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(resampler_df1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      cudaFuncSetAttribute(resampler_df1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(resampler_orig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(resampler_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
     return PST_ERR_CUDA;
   return PST_OK;
 }
@@ -915,4 +1234,51 @@ int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h
   p.num_tiles = (R + 127) / 128;
   p.idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   return launch_clustered(resampler_df1_kernel, m, st, p.num_tiles, p);
+}
+
+// z <- the whole resampler + head for downsampling_ratio > 1: token-info lookup, residue track, token track.
+// kv: six [R,128] fp32 buffers (k and v of the three blocks); info: int2 [T].
+int pst_launch_resampler_dfn(const pst_model* m, cudaStream_t st, const float* h, const int32_t* offsets, const int32_t* token_offsets,
+                             int B, int R, int T, float* const* kv, void* info, float* z) {
+  if (!m->node_chain || R <= 0 || T <= 0 || m->cfg.downsampling_ratio <= 1) return 0;
+  if (m->cfg.num_blocks > 3 || m->cfg.downsampling_ratio > 8) return PST_ERR_UNSUPPORTED_CONFIG;
+  const PstNodeChain& C = *m->node_chain;
+  const int nb = m->cfg.num_blocks;
+  token_info_kernel<<<(T + 255) / 256, 256, 0, st>>>(offsets, token_offsets, B, m->cfg.downsampling_ratio, T, static_cast<int2*>(info));
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  auto host = [&](const float* dev) { return m->blob_host + (dev - m->blob_dev); };
+  {
+    ResamplerOrigParams p{};
+    p.h = h; p.num_blocks = nb;
+    for (int b = 0; b < nb; ++b) {
+      const PstBlockW& w = m->w.block[b];
+      p.k[b] = kv[2 * b]; p.v[b] = kv[2 * b + 1];
+      float* c = p.cv + b * OB::kBlk;
+      memcpy(c + OB::kDnS, host(w.dn_s), 512); memcpy(c + OB::kDnO, host(w.dn_o), 512);
+      memcpy(c + OB::kOtLnS, host(w.ot_ln_s), 512); memcpy(c + OB::kOtLnO, host(w.ot_ln_o), 512);
+      memcpy(c + OB::kOtB1, host(w.ot_b1), 1024); memcpy(c + OB::kOtB2, host(w.ot_b2), 512);
+    }
+    p.sched = C.sched_dev + C.orig_off; p.n_sched = C.orig_n;
+    p.R = R; p.num_tiles = (R + 127) / 128; p.idesc = idesc;
+    if (int rc = launch_clustered(resampler_orig_kernel, m, st, p.num_tiles, p); rc < 0) return rc;
+  }
+  {
+    ResamplerTokenParams p{};
+    p.token_table = m->w.token_table; p.info = static_cast<const int2*>(info); p.z = z;
+    p.num_blocks = nb; p.df = m->cfg.downsampling_ratio;
+    for (int b = 0; b < nb; ++b) {
+      const PstBlockW& w = m->w.block[b];
+      p.k[b] = kv[2 * b]; p.v[b] = kv[2 * b + 1];
+      float* c = p.cv + b * TB::kBlk;
+      memcpy(c + TB::kQnS, host(w.qn_s), 512); memcpy(c + TB::kQnO, host(w.qn_o), 512);
+      memcpy(c + TB::kBg, host(w.bg), 512); memcpy(c + TB::kBo, host(w.bo), 512);
+      memcpy(c + TB::kRtLnS, host(w.rt_ln_s), 512); memcpy(c + TB::kRtLnO, host(w.rt_ln_o), 512);
+      memcpy(c + TB::kRtB1, host(w.rt_b1), 1024); memcpy(c + TB::kRtB2, host(w.rt_b2), 512);
+    }
+    p.down_w = m->w.down_w; p.down_b = m->w.down_b; p.C = m->cfg.num_levels;
+    p.sched = C.sched_dev + C.token_off; p.n_sched = C.token_n;
+    p.T = T; p.num_tiles = (T + 127) / 128; p.idesc = idesc;
+    if (int rc = launch_clustered(resampler_token_kernel, m, st, p.num_tiles, p); rc < 0) return rc;
+  }
+  return 3;
 }

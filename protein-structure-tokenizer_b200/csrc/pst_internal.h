@@ -73,6 +73,7 @@ struct pst_model {
   // FSQ constants (model/quantize.py:175-181), fp32
   float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
   int32_t basis[PST_C8], half_width[PST_C8];
+  bool use_fused_resampler;  // df > 1: the two fused chain kernels instead of the per-op path (PST_FUSED_RESAMPLER=0 switches them off)
   bool use_msg_t;            // message MLPs through the transposed kernel (edge_msg_t_kernel; PST_MSG_T=0 switches it off)
   mutable int launch_count;
   // CUDA-graph cache of the fused hot call (api.cu): a pst_tokenize call whose arguments (pointers and sizes) repeat
@@ -185,6 +186,9 @@ int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const
                            uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r,
                            uint16_t* h16 = nullptr);
 int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z);
+// downsampling_ratio > 1: two chain kernels (residue track, token track); kv = six [R,128] fp32 buffers, info = int2 [T]
+int pst_launch_resampler_dfn(const pst_model* m, cudaStream_t st, const float* h, const int32_t* offsets, const int32_t* token_offsets,
+                             int B, int R, int T, float* const* kv, void* info, float* z);
 
 #define PST_CUDA_OK(expr)                                  \
   do {                                                     \
