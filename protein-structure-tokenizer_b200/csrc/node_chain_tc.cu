@@ -196,7 +196,9 @@ __device__ __forceinline__ void split_store(uint8_t* set, int row, int k0, const
     }
     const uint32_t off = swz64(row, kk0 + c * 8);
     *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+#ifndef PST_NODE_NOSPLIT
     *reinterpret_cast<uint4*>(base + kImgBlk + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#endif
   }
 }
 
@@ -220,8 +222,10 @@ __device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tme
     for (int j = 0; j < 4; ++j) {
       const uint32_t o = j * 32;
       umma(tmem_acc, make_desc(a_hi + o), make_desc(w_hi + o), idesc, (kb | j) ? 1u : accumulate);
+#ifndef PST_NODE_NOSPLIT
       umma(tmem_acc, make_desc(a_hi + o), make_desc(w_lo + o), idesc, 1u);
       umma(tmem_acc, make_desc(a_lo + o), make_desc(w_hi + o), idesc, 1u);
+#endif
     }
     umma_commit_mc(r.empty + slot * 8, (uint16_t)((1u << kCluster) - 1));  // the slot is refilled for the whole cluster
     ++r.n;
@@ -236,12 +240,17 @@ __device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tme
 // pull the same 64 KB per 128 x 128 product from a few L2 slices, which bounds the kernel.
 __device__ __forceinline__ void producer_loop(Ring r, const uint8_t* const* sched, int n_sched, int my_tiles) {
   const uint32_t rank = cluster_ctarank();
-  constexpr uint32_t kSlice = kSlotBytes / kCluster;
+#ifdef PST_NODE_NOSPLIT  // experiment: hi images only (plain fp16 products)
+  constexpr uint32_t kFetch = kImgBlk;
+#else
+  constexpr uint32_t kFetch = kSlotBytes;
+#endif
+  constexpr uint32_t kSlice = kFetch / kCluster;
   for (int t = 0; t < my_tiles; ++t)
     for (int i = 0; i < n_sched; ++i) {
       const uint32_t slot = r.n % kSlots;
       if (r.n >= kSlots) mbar_wait(r.empty + slot * 8, ((r.n / kSlots) - 1) & 1);
-      mbar_expect_tx(r.full + slot * 8, kSlotBytes);
+      mbar_expect_tx(r.full + slot * 8, kFetch);
       bulk_g2s_mc(r.wbase + slot * kSlotBytes + rank * kSlice, sched[i] + rank * kSlice, kSlice, r.full + slot * 8,
                   (uint16_t)((1u << kCluster) - 1));
       ++r.n;
