@@ -31,6 +31,7 @@
 
 #include <vector>
 
+#include <cstdio>
 #include <cstring>
 
 #include "pst_internal.h"
@@ -45,8 +46,10 @@ constexpr int kSlots = 3;
 constexpr int kCluster = 2;  // CTAs per cluster: each weight half-unit is fetched from L2 once per cluster and multicast
 constexpr uint32_t kOffX = 0, kOffU = kSetBytes, kOffW = 2 * kSetBytes;
 constexpr uint32_t kOffBar = kOffW + kSlots * kSlotBytes;
-constexpr uint32_t kSmemBytes = kOffBar + 128 + 2 * 2 * 128 * 4;  // barriers + TMEM slot, row-statistics exchange
-constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 32;
+constexpr uint32_t kBarBytes = 512;  // barriers + TMEM slot (128), command barriers (128), command queue (256)
+constexpr uint32_t kSmemBytes = kOffBar + kBarBytes + 2 * 2 * 128 * 4;  // + row-statistics exchange
+constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 64;  // + weight producer warp + MMA warp
+constexpr int kCmdSlots = 8;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 
 __host__ __device__ __forceinline__ uint32_t swz64(uint32_t row, uint32_t k) {
@@ -206,7 +209,22 @@ __device__ __forceinline__ void split_store(uint8_t* set, int row, int k0, const
 struct Ring {
   uint32_t full, empty, wbase;  // smem addresses: full[kSlots], empty[kSlots] mbarriers, slot 0
   uint32_t n;                   // half-units consumed / produced so far
+#ifdef PST_NODE_PROFILE
+  long long waited = 0;         // cycles the thread spent waiting on the ring's barriers
+#endif
 };
+// -DPST_NODE_PROFILE: per-phase cycle counters of block 0 (issuing thread, one other epilogue thread, the producer),
+// printed at the end of the kernel; the ring's `waited` = cycles the issuing thread waited for weights.
+#ifdef PST_NODE_PROFILE
+#define NPROF_DECL long long np_last = clock64(); long long np_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define NPROF(i) do { long long _t = clock64(); np_acc[i] += _t - np_last; np_last = _t; } while (0)
+#define NPROF_PRINT(name, extra) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 160)) printf("%s thread %d: %lld %lld %lld %lld %lld %lld %lld %lld | ring wait %lld\n", name, \
+  (int)threadIdx.x, np_acc[0], np_acc[1], np_acc[2], np_acc[3], np_acc[4], np_acc[5], np_acc[6], np_acc[7], (long long)(extra)); } while (0)
+#else
+#define NPROF_DECL do {} while (0)
+#define NPROF(i) do {} while (0)
+#define NPROF_PRINT(name, extra) do {} while (0)
+#endif
 
 // one 128 x 128 x 128 product (split precision): A image set x the next two half-units of the ring -> acc
 __device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tmem_acc, uint32_t accumulate, uint32_t idesc,
@@ -214,7 +232,13 @@ __device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tme
 #pragma unroll
   for (int kb = 0; kb < 2; ++kb) {
     const uint32_t slot = r.n % kSlots, par = (r.n / kSlots) & 1;
+#ifdef PST_NODE_PROFILE
+    const long long t0 = clock64();
+#endif
     mbar_wait(r.full + slot * 8, par);
+#ifdef PST_NODE_PROFILE
+    r.waited += clock64() - t0;
+#endif
     tc_after();
     const uint32_t a_hi = a_set + kb * kSlotBytes, a_lo = a_hi + kImgBlk;
     const uint32_t w_hi = r.wbase + slot * kSlotBytes, w_lo = w_hi + kImgBlk;
@@ -249,12 +273,21 @@ __device__ __forceinline__ void producer_loop(Ring r, const uint8_t* const* sche
   for (int t = 0; t < my_tiles; ++t)
     for (int i = 0; i < n_sched; ++i) {
       const uint32_t slot = r.n % kSlots;
+#ifdef PST_NODE_PROFILE
+      const long long t0 = clock64();
+#endif
       if (r.n >= kSlots) mbar_wait(r.empty + slot * 8, ((r.n / kSlots) - 1) & 1);
+#ifdef PST_NODE_PROFILE
+      r.waited += clock64() - t0;
+#endif
       mbar_expect_tx(r.full + slot * 8, kFetch);
       bulk_g2s_mc(r.wbase + slot * kSlotBytes + rank * kSlice, sched[i] + rank * kSlice, kSlice, r.full + slot * 8,
                   (uint16_t)((1u << kCluster) - 1));
       ++r.n;
     }
+#ifdef PST_NODE_PROFILE
+  if (blockIdx.x == 0) printf("producer: %u half-units, waited %lld cycles for free slots\n", r.n, r.waited);
+#endif
 }
 
 // ---- epilogue thread layout ----------------------------------------------------------------------------------
@@ -349,6 +382,7 @@ struct Setup {
   uint8_t* smem;
   uint32_t tmem_base;
   uint32_t bar_done[4];
+  uint32_t cmd_bar, cmd;  // smem addresses: kCmdSlots mbarriers, kCmdSlots 16-byte commands
   Ring ring;
   float* red;
 };
@@ -360,6 +394,7 @@ __device__ __forceinline__ Setup chain_setup(uint8_t* smem, int tid, int warp) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   if (tid == 0) {
     for (int i = 0; i < 10; ++i) mbar_init(smem_u32(&bars[i]), (i >= 3 && i < 6) ? kCluster : 1);
+    for (int i = 0; i < kCmdSlots; ++i) mbar_init(smem_u32(&bars[16 + i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -376,7 +411,9 @@ __device__ __forceinline__ Setup chain_setup(uint8_t* smem, int tid, int warp) {
   s.ring.wbase = smem_u32(smem + kOffW);
   s.ring.n = 0;
   for (int i = 0; i < 4; ++i) s.bar_done[i] = smem_u32(&bars[6 + i]);
-  s.red = reinterpret_cast<float*>(smem + kOffBar + 128);
+  s.cmd_bar = smem_u32(&bars[16]);
+  s.cmd = smem_u32(smem + kOffBar + 256);
+  s.red = reinterpret_cast<float*>(smem + kOffBar + kBarBytes);
   return s;
 }
 
@@ -387,17 +424,26 @@ __device__ __forceinline__ void chain_teardown(const Setup& s, int warp) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "r"(512u) : "memory");
 }
 
-// MMA groups: every epilogue thread counts them, thread 0 issues.  Group i commits to done[i & 3] and the threads
-// wait for the groups in issue order, so each barrier has at most one unobserved completion as long as no more than
-// four groups are in flight.
+// MMA groups: every epilogue thread counts them; thread 0 POSTS each group (operand set, accumulator, accumulate flag,
+// completion barrier) into a small command queue in shared memory and the MMA warp issues it.  Round 2: with thread 0
+// issuing the 24 products of a group itself (descriptor arithmetic + waiting for the weight slots) every other
+// epilogue thread waited for it at the next barrier, about 1 000 cycles per group on the critical path of a chain
+// that is latency-bound anyway (per-phase counters, -DPST_NODE_PROFILE).  Group i commits to done[i & 3] and the
+// threads wait for the groups in issue order, so each barrier has at most one unobserved completion as long as no
+// more than four groups are in flight; that also keeps the kCmdSlots = 8 deep queue from wrapping onto an unread entry.
 struct Groups {
-  Ring ring;
+  uint32_t cmd_bar, cmd;
   uint32_t bar_done[4];
-  uint32_t idesc;
   uint32_t n_issued = 0, n_waited = 0;
   int tid;
   __device__ __forceinline__ void issue(uint32_t a_set, uint32_t acc, uint32_t accumulate) {
-    if (tid == 0) issue_unit(ring, a_set, acc, accumulate, idesc, bar_done[n_issued & 3]);
+    if (tid == 0) {
+      const uint32_t slot = n_issued % kCmdSlots;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cmd + slot * 16), "r"(a_set), "r"(acc), "r"(accumulate),
+                   "r"(bar_done[n_issued & 3])
+                   : "memory");
+      asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(cmd_bar + slot * 8) : "memory");
+    }
     ++n_issued;
   }
   __device__ __forceinline__ void wait_next() {
@@ -406,6 +452,20 @@ struct Groups {
     tc_after();
   }
 };
+// the MMA warp's loop (one thread): `total` groups, in the order the epilogue threads post them
+__device__ __forceinline__ void mma_loop(Ring ring, uint32_t cmd_bar, uint32_t cmd, uint32_t idesc, int total) {
+  for (int i = 0; i < total; ++i) {
+    const uint32_t slot = (uint32_t)i % kCmdSlots;
+    mbar_wait(cmd_bar + slot * 8, ((uint32_t)i / kCmdSlots) & 1);
+    uint32_t a_set, acc, accumulate, done;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a_set), "=r"(acc), "=r"(accumulate), "=r"(done) : "r"(cmd + slot * 16) : "memory");
+    tc_after();
+    issue_unit(ring, a_set, acc, accumulate, idesc, done);
+  }
+#ifdef PST_NODE_PROFILE
+  if (blockIdx.x == 0) printf("mma warp: waited %lld cycles for weights\n", ring.waited);
+#endif
+}
 // images written by the epilogue threads become visible to the tensor core; accumulators read by them may be reused
 __device__ __forceinline__ void publish() {
   fence_async();
@@ -469,8 +529,9 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
   const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
-  if (warp == kEpiThreads / 32) {
+  if (warp >= kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
+    if (tid == kEpiThreads + 32) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
     __syncwarp();
     chain_teardown(S, warp);
     return;
@@ -480,12 +541,14 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
   const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
   Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
   const uint32_t t_acc0 = S.tmem_base + 0, t_h1 = S.tmem_base + 128, t_acc1 = S.tmem_base + 256, t_acc2 = S.tmem_base + 384;
-  Groups G{S.ring, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, p.idesc, 0, 0, tid};
+  Groups G{S.cmd_bar, S.cmd, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, 0, 0, tid};
 
+  NPROF_DECL;
   for (int ti = 0, tile = blockIdx.x; ti < my_tiles; ++ti, tile += gridDim.x) {  // tiles past the end: all rows invalid
     const int row = tile * 128 + e.row;
     const bool valid = row < p.R;
     float x[2][32];
+    NPROF(0);
     // ---- 1. agg = tbar . W3 -------------------------------------------------------------------------------
     // tbar[row] = (sum of the partial row sums of the one or two 128-edge tiles that hold the row's K edges) / K
     {
@@ -511,8 +574,10 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
     }
     split_store_half(e, X, x);
     publish();
+    NPROF(1);  // partial sums -> images
     G.issue(X_addr, t_acc0, 0u);
     G.wait_next();
+    NPROF(2);  // product 1 (issue + wait)
     // ---- 2. h1 = LN0(h + agg + b3) -> TMEM (fp32) + X images ---------------------------------------------------
     {
       float hh[2][32];
@@ -524,8 +589,10 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
     tmem_st_half(e, t_h1, x);
     split_store_half(e, X, x);
     publish();
+    NPROF(3);  // LN0
     // ---- 3. FFN 128 -> 512 -> 128 (gnn_layers.py:385-394), hidden chunked 4 x 128 ---------------------------------
     chunked_mlp<1>(G, e, X_addr, U, U_addr, t_acc1, t_acc0, t_acc2, 4, p.cv, NodeUpdateParams::kFfnB1);
+    NPROF(4);  // FFN (8 products)
     // ---- 4. h2 = LN1(h1 + ffn + b2) -> global h, X images ------------------------------------------------------
     {
       float h1[2][32];
@@ -556,6 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
           }
       }
     }
+    NPROF(5);  // LN1 + stores of h
     if (p.n_out > 0) {
       split_store_half(e, X, x);
       publish();
@@ -589,7 +657,9 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
       tc_before();
       epi_sync();
     }
+    NPROF(6);  // output tables
   }
+  NPROF_PRINT("node_update [-, partials, product 1, LN0, FFN, LN1, tables]", 0);
   chain_teardown(S, warp);
 }
 
@@ -622,8 +692,9 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
   const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
-  if (warp == kEpiThreads / 32) {
+  if (warp >= kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
+    if (tid == kEpiThreads + 32) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
     __syncwarp();
     chain_teardown(S, warp);
     return;
@@ -633,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
   const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
   Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
   const uint32_t t_res = S.tmem_base + 0, t_orig = S.tmem_base + 128, t_accA = S.tmem_base + 256, t_accB = S.tmem_base + 384;
-  Groups G{S.ring, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, p.idesc, 0, 0, tid};
+  Groups G{S.cmd_bar, S.cmd, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, 0, 0, tid};
 
   for (int ti = 0, tile = blockIdx.x; ti < my_tiles; ++ti, tile += gridDim.x) {  // tiles past the end: all rows invalid
     const int row = tile * 128 + e.row;
@@ -725,7 +796,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
       for (int c = 0; c < PST_C8; ++c) zc[c] = 0.f;
 #pragma unroll
       for (int q = 0; q < 2; ++q)
-#pragma unroll 8
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
 #ifdef PST_NODE_RECIP_MUL
           const float r = x[q][j] * (1.0f / d);
@@ -790,8 +861,9 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_orig_kernel(const __gri
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
   const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
-  if (warp == kEpiThreads / 32) {
+  if (warp >= kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
+    if (tid == kEpiThreads + 32) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
     __syncwarp();
     chain_teardown(S, warp);
     return;
@@ -801,7 +873,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_orig_kernel(const __gri
   const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
   Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
   const uint32_t t_orig = S.tmem_base + 0, t_accA = S.tmem_base + 128, t_accB = S.tmem_base + 256, t_accC = S.tmem_base + 384;
-  Groups G{S.ring, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, p.idesc, 0, 0, tid};
+  Groups G{S.cmd_bar, S.cmd, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, 0, 0, tid};
 
   for (int ti = 0, tile = blockIdx.x; ti < my_tiles; ++ti, tile += gridDim.x) {  // tiles past the end: all rows invalid
     const int row = tile * 128 + e.row;
@@ -875,8 +947,9 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_token_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5;
   Setup S = chain_setup(smem, tid, warp);
   const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  if (warp == kEpiThreads / 32) {
+  if (warp >= kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
+    if (tid == kEpiThreads + 32) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
     __syncwarp();
     chain_teardown(S, warp);
     return;
@@ -886,7 +959,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_token_kernel(const __gr
   const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
   Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
   const uint32_t t_res = S.tmem_base + 0, t_accA = S.tmem_base + 128, t_accB = S.tmem_base + 256, t_accC = S.tmem_base + 384;
-  Groups G{S.ring, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, p.idesc, 0, 0, tid};
+  Groups G{S.cmd_bar, S.cmd, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, 0, 0, tid};
   const float qscale = 0.17677669529663687f;  // 32 ** -0.5 (modules.py:334)
 
   for (int ti = 0, tile = blockIdx.x; ti < my_tiles; ++ti, tile += gridDim.x) {
@@ -1008,7 +1081,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_token_kernel(const __gr
       for (int c = 0; c < PST_C8; ++c) zc[c] = 0.f;
 #pragma unroll
       for (int q = 0; q < 2; ++q)
-#pragma unroll 8
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
 #ifdef PST_NODE_RECIP_MUL
           const float r = x[q][j] * (1.0f / d);
