@@ -101,6 +101,13 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, ui
       "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand from TMEM (K-major only: lane = row, each 32-bit column holds two consecutive K elements), B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // arrive on the barrier at the same shared-memory offset in every CTA of the cluster
 __device__ __forceinline__ void umma_commit_mc(uint32_t mbar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(mask)
@@ -144,6 +151,7 @@ __device__ __forceinline__ void ld256f(const float* ptr, float* r) {
                : "l"(ptr)
                : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void st256f(float* ptr, const float* r) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]),
                "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
@@ -226,9 +234,14 @@ struct Ring {
 #define NPROF_PRINT(name, extra) do {} while (0)
 #endif
 
-// one 128 x 128 x 128 product (split precision): A image set x the next two half-units of the ring -> acc
-__device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tmem_acc, uint32_t accumulate, uint32_t idesc,
+// one 128 x 128 x 128 product (split precision): A image set x the next two half-units of the ring -> acc.
+// flags bit 0: accumulate onto the accumulator's contents; bit 1: the A image set is in TMEM (a_set = TMEM address of a
+// 128-column region: K block kb at columns [64 kb, 64 kb + 64): 32 columns of hi pairs, then 32 columns of lo pairs),
+// otherwise in shared memory (a_set = address of an activation image set).
+constexpr uint32_t kFlagAcc = 1u, kFlagTmemA = 2u;
+__device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tmem_acc, uint32_t flags, uint32_t idesc,
                                            uint32_t done_bar) {
+  const uint32_t accumulate = flags & kFlagAcc;
 #pragma unroll
   for (int kb = 0; kb < 2; ++kb) {
     const uint32_t slot = r.n % kSlots, par = (r.n / kSlots) & 1;
@@ -240,16 +253,29 @@ __device__ __forceinline__ void issue_unit(Ring& r, uint32_t a_set, uint32_t tme
     r.waited += clock64() - t0;
 #endif
     tc_after();
-    const uint32_t a_hi = a_set + kb * kSlotBytes, a_lo = a_hi + kImgBlk;
     const uint32_t w_hi = r.wbase + slot * kSlotBytes, w_lo = w_hi + kImgBlk;
+    if (flags & kFlagTmemA) {
+      const uint32_t a_hi = a_set + kb * 64, a_lo = a_hi + 32;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t o = j * 32;
-      umma(tmem_acc, make_desc(a_hi + o), make_desc(w_hi + o), idesc, (kb | j) ? 1u : accumulate);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t o = j * 32;
+        umma_ts(tmem_acc, a_hi + j * 8, make_desc(w_hi + o), idesc, (kb | j) ? 1u : accumulate);
 #ifndef PST_NODE_NOSPLIT
-      umma(tmem_acc, make_desc(a_hi + o), make_desc(w_lo + o), idesc, 1u);
-      umma(tmem_acc, make_desc(a_lo + o), make_desc(w_hi + o), idesc, 1u);
+        umma_ts(tmem_acc, a_hi + j * 8, make_desc(w_lo + o), idesc, 1u);
+        umma_ts(tmem_acc, a_lo + j * 8, make_desc(w_hi + o), idesc, 1u);
 #endif
+      }
+    } else {
+      const uint32_t a_hi = a_set + kb * kSlotBytes, a_lo = a_hi + kImgBlk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t o = j * 32;
+        umma(tmem_acc, make_desc(a_hi + o), make_desc(w_hi + o), idesc, (kb | j) ? 1u : accumulate);
+#ifndef PST_NODE_NOSPLIT
+        umma(tmem_acc, make_desc(a_hi + o), make_desc(w_lo + o), idesc, 1u);
+        umma(tmem_acc, make_desc(a_lo + o), make_desc(w_hi + o), idesc, 1u);
+#endif
+      }
     }
     umma_commit_mc(r.empty + slot * 8, (uint16_t)((1u << kCluster) - 1));  // the slot is refilled for the whole cluster
     ++r.n;
@@ -346,6 +372,40 @@ __device__ __forceinline__ void split_store_half(const Epi& e, uint8_t* set, con
   split_store(set, e.row, e.half * 64, x[0]);
   split_store(set, e.row, e.half * 64 + 32, x[1]);
 }
+// The thread's 64 values (K block `half` of its row) as hi / lo fp16 pairs into ITS OWN 64 columns of a TMEM region:
+// an accumulator the thread has just read becomes, in place, the A operand of the next product (no shared memory, no
+// swizzle, no proxy fence; the MMA warp reads hi at columns [64 half, +32), lo at [64 half + 32, +32)).
+__device__ __forceinline__ void split_store_tmem_half(const Epi& e, uint32_t region, const float (&x)[2][32]) {
+  float pk[32];
+  uint32_t* u = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const __half2 h = __floats2half2_rn(x[c >> 4][(c & 15) * 2], x[c >> 4][(c & 15) * 2 + 1]);
+    u[c] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  tmem_st32(region + e.lane_off + e.half * 64, pk);
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float a = x[c >> 4][(c & 15) * 2], b = x[c >> 4][(c & 15) * 2 + 1];
+    const float2 f = __half22float2(__floats2half2_rn(a, b));
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    u[c] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  tmem_st32(region + e.lane_off + e.half * 64 + 32, pk);
+}
+// the inverse: the thread's 64 values back from the hi / lo images it wrote (x = hi + lo: the split keeps 22 bits)
+__device__ __forceinline__ void load_image_tmem_half(const Epi& e, uint32_t region, float (&x)[2][32]) {
+  float hi[32], lo[32];
+  tmem_ld32(region + e.lane_off + e.half * 64, hi);
+  tmem_ld32(region + e.lane_off + e.half * 64 + 32, lo);
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi[c]));
+    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo[c]));
+    x[c >> 4][(c & 15) * 2] = h.x + l.x;
+    x[c >> 4][(c & 15) * 2 + 1] = h.y + l.y;
+  }
+}
 __device__ __forceinline__ void load_row_half(const Epi& e, const float* row_ptr, bool valid, float (&x)[2][32]) {
   const float* src = row_ptr + e.half * 64;
 #pragma unroll
@@ -436,10 +496,17 @@ struct Groups {
   uint32_t bar_done[4];
   uint32_t n_issued = 0, n_waited = 0;
   int tid;
-  __device__ __forceinline__ void issue(uint32_t a_set, uint32_t acc, uint32_t accumulate) {
+#ifdef PST_NODE_PROFILE
+  long long pf[6] = {0, 0, 0, 0, 0, 0}, pf_last = 0;  // chunked_mlp: waits, load + activation, image store, publish + post
+  __device__ __forceinline__ void prof(int i) { const long long t = clock64(); pf[i] += t - pf_last; pf_last = t; }
+#define GPROF(i) G.prof(i)
+#else
+#define GPROF(i) do {} while (0)
+#endif
+  __device__ __forceinline__ void issue(uint32_t a_set, uint32_t acc, uint32_t flags) {  // flags: kFlagAcc | kFlagTmemA
     if (tid == 0) {
       const uint32_t slot = n_issued % kCmdSlots;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cmd + slot * 16), "r"(a_set), "r"(acc), "r"(accumulate),
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cmd + slot * 16), "r"(a_set), "r"(acc), "r"(flags),
                    "r"(bar_done[n_issued & 3])
                    : "memory");
       asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(cmd_bar + slot * 8) : "memory");
@@ -457,10 +524,10 @@ __device__ __forceinline__ void mma_loop(Ring ring, uint32_t cmd_bar, uint32_t c
   for (int i = 0; i < total; ++i) {
     const uint32_t slot = (uint32_t)i % kCmdSlots;
     mbar_wait(cmd_bar + slot * 8, ((uint32_t)i / kCmdSlots) & 1);
-    uint32_t a_set, acc, accumulate, done;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a_set), "=r"(acc), "=r"(accumulate), "=r"(done) : "r"(cmd + slot * 16) : "memory");
+    uint32_t a_set, acc, flags, done;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a_set), "=r"(acc), "=r"(flags), "=r"(done) : "r"(cmd + slot * 16) : "memory");
     tc_after();
-    issue_unit(ring, a_set, acc, accumulate, idesc, done);
+    issue_unit(ring, a_set, acc, flags, idesc, done);
   }
 #ifdef PST_NODE_PROFILE
   if (blockIdx.x == 0) printf("mma warp: waited %lld cycles for weights\n", ring.waited);
@@ -472,25 +539,36 @@ __device__ __forceinline__ void publish() {
   tc_before();
   epi_sync();
 }
+// the same for images written into TMEM (tcgen05.st has been waited for by the storing thread)
+__device__ __forceinline__ void publish_tmem() {
+  tc_before();
+  epi_sync();
+}
 
-// y = act(X . W1[:, c] + b1[c]) . W2[c, :] accumulated over `chunks` 128-wide chunks of the hidden layer.
-// X: image set of the input (already published); U: scratch image set; accH[2]: two hidden accumulators.
-// Software pipeline: the first-layer products run two chunks ahead into alternating accumulators, and the
-// activation of chunk c is computed in registers while the tensor core still reads U for chunk c - 1; only the
-// store into U waits for it.  Issue order F1(0) F1(1) F2(0) F1(2) F2(1) ... == wait order.  Result in acc_out
-// (complete on return).  NOTE the schedule of weight half-units must list the units in this issue order.
+// y (+)= act(X . W1[:, c] + b1[c]) . W2[c, :] accumulated over `chunks` 128-wide chunks of the hidden layer.
+// X: image set of the input in shared memory (already published); accH[2]: two hidden accumulators.  The activated
+// chunk is written IN PLACE over its accumulator as hi / lo fp16 images and the second-layer product takes its A
+// operand from TMEM (round 2; before, one shared-memory image set U held the chunk and the store into it had to wait
+// for the previous chunk's second-layer product).  Issue order F1(0) F1(1) F2(0) F1(2) F2(1) F1(3) ... == wait order;
+// the tensor pipe executes one thread's products in issue order, so F1(c + 2) overwrites accH[c & 1] only after F2(c)
+// has read the image in it.  acc_flags = kFlagAcc: the result is added to what acc_out holds (the residual stream),
+// 0: acc_out is overwritten.  acc_out must not be one of the hidden accumulators.  Result complete on return.
+// NOTE the schedule of weight half-units must list the units in this issue order.
 template <int ACT, int N>  // 1 gelu(tanh), 2 relu
-__device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_addr, uint8_t* U, uint32_t U_addr,
-                                            uint32_t accH0, uint32_t accH1, uint32_t acc_out, int chunks,
-                                            const float (&cv)[N], int b1) {
-  G.issue(X_addr, accH0, 0u);
-  if (chunks > 1) G.issue(X_addr, accH1, 0u);
+__device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_addr, uint32_t x_flags, uint32_t accH0, uint32_t accH1,
+                                            uint32_t acc_out, uint32_t acc_flags, int chunks, const float (&cv)[N], int b1) {
+  G.issue(X_addr, accH0, x_flags);  // x_flags: kFlagTmemA if the input image set is in TMEM, else 0
+  if (chunks > 1) G.issue(X_addr, accH1, x_flags);
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     const int b = b1 + c * 128 + e.half * 64;
-    G.wait_next();  // X . W1[:, c]
+    const uint32_t accH = (c & 1) ? accH1 : accH0;
+    GPROF(0);
+    if (c >= 2) G.wait_next();  // u_{c-2} . W2[c-2, :] (long done: it precedes F1(c) in the pipe)
+    G.wait_next();              // X . W1[:, c]
+    GPROF(1);
     float v[2][32];
-    tmem_ld_half(e, (c & 1) ? accH1 : accH0, v);
+    tmem_ld_half(e, accH, v);
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -498,13 +576,16 @@ __device__ __forceinline__ void chunked_mlp(Groups& G, const Epi& e, uint32_t X_
         const float t = v[q][j] + cv[b + q * 32 + j];
         v[q][j] = ACT == 1 ? gelu_tanh(t) : fmaxf(t, 0.f);
       }
-    if (c > 0) G.wait_next();  // u_{c-1} . W2[c-1, :] has read U
-    split_store_half(e, U, v);
-    publish();
-    G.issue(U_addr, acc_out, c > 0 ? 1u : 0u);
-    if (c + 2 < chunks) G.issue(X_addr, (c & 1) ? accH1 : accH0, 0u);
+    GPROF(2);
+    split_store_tmem_half(e, accH, v);
+    GPROF(3);
+    publish_tmem();
+    G.issue(accH, acc_out, kFlagTmemA | (c > 0 ? kFlagAcc : acc_flags));
+    if (c + 2 < chunks) G.issue(X_addr, accH, x_flags);
+    GPROF(4);
   }
-  G.wait_next();  // last second-layer product
+  for (int c = chunks > 2 ? chunks - 2 : 0; c < chunks; ++c) G.wait_next();  // the last second-layer products
+  GPROF(5);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -540,7 +621,10 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
   uint8_t* U = smem + kOffU;
   const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
   Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
-  const uint32_t t_acc0 = S.tmem_base + 0, t_h1 = S.tmem_base + 128, t_acc1 = S.tmem_base + 256, t_acc2 = S.tmem_base + 384;
+  const uint32_t t_acc0 = S.tmem_base + 0, t_x = S.tmem_base + 128, t_acc1 = S.tmem_base + 256, t_acc2 = S.tmem_base + 384;
+  // t_x: the hi / lo images of the current activation (A operand of every first-layer product, read from TMEM: with
+  // both operands in shared memory a split product moves 192 KB of operands + 64 KB of incoming weights through the
+  // 128 B/clock shared-memory port = 2 000+ cycles for 1 536 cycles of tensor work); it doubles as the row's h1.
   Groups G{S.cmd_bar, S.cmd, {S.bar_done[0], S.bar_done[1], S.bar_done[2], S.bar_done[3]}, 0, 0, tid};
 
   NPROF_DECL;
@@ -572,10 +656,10 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
         for (int j = 0; j < 32; ++j) x[q][j] = x[q][j] / kf;
 #endif
     }
-    split_store_half(e, X, x);
-    publish();
+    split_store_tmem_half(e, t_x, x);
+    publish_tmem();
     NPROF(1);  // partial sums -> images
-    G.issue(X_addr, t_acc0, 0u);
+    G.issue(t_x, t_acc0, kFlagTmemA);
     G.wait_next();
     NPROF(2);  // product 1 (issue + wait)
     // ---- 2. h1 = LN0(h + agg + b3) -> TMEM (fp32) + X images ---------------------------------------------------
@@ -586,18 +670,31 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
       add_residual_bias_half(e, x, hh, p.cv, NodeUpdateParams::kB3);
     }
     layer_norm_row(e, x, p.cv, NodeUpdateParams::kLn0S, NodeUpdateParams::kLn0O);
-    tmem_st_half(e, t_h1, x);
-    split_store_half(e, X, x);
-    publish();
+    split_store_tmem_half(e, t_x, x);
+    publish_tmem();
     NPROF(3);  // LN0
+    // the next tile's partial sums and node state -> L2 while the tensor pipe works on the FFN: every CTA is in the
+    // same phase at the same time, so without this the whole grid waits on HBM at the top of each tile
+    if (ti + 1 < my_tiles) {
+      const int nrow = row + (int)gridDim.x * 128;
+      if (nrow < p.R) {
+        const int e0 = nrow * p.K, t0 = e0 >> p.tile_shift, t1 = (e0 + p.K - 1) >> p.tile_shift;
+        const float* a0 = p.partial + ((size_t)t0 * 4 + (nrow - (t0 << p.tile_shift) / p.K)) * D + e.half * 64;
+        const float* a1 = p.partial + ((size_t)t1 * 4 + (nrow - (t1 << p.tile_shift) / p.K)) * D + e.half * 64;
+        const float* a2 = p.h + (size_t)nrow * D + e.half * 64;
+        prefetch_l2(a0); prefetch_l2(a0 + 32);
+        if (t1 != t0) { prefetch_l2(a1); prefetch_l2(a1 + 32); }
+        prefetch_l2(a2); prefetch_l2(a2 + 32);
+      }
+    }
     // ---- 3. FFN 128 -> 512 -> 128 (gnn_layers.py:385-394), hidden chunked 4 x 128 ---------------------------------
-    chunked_mlp<1>(G, e, X_addr, U, U_addr, t_acc1, t_acc0, t_acc2, 4, p.cv, NodeUpdateParams::kFfnB1);
+    chunked_mlp<1>(G, e, t_x, kFlagTmemA, t_acc1, t_acc0, t_acc2, 0u, 4, p.cv, NodeUpdateParams::kFfnB1);
     NPROF(4);  // FFN (8 products)
     // ---- 4. h2 = LN1(h1 + ffn + b2) -> global h, X images ------------------------------------------------------
     {
       float h1[2][32];
       tmem_ld_half(e, t_acc2, x);
-      tmem_ld_half(e, t_h1, h1);
+      load_image_tmem_half(e, t_x, h1);
       add_residual_bias_half(e, x, h1, p.cv, NodeUpdateParams::kFfnB2);
     }
     layer_norm_row(e, x, p.cv, NodeUpdateParams::kLn1S, NodeUpdateParams::kLn1O);
@@ -625,15 +722,21 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
     }
     NPROF(5);  // LN1 + stores of h
     if (p.n_out > 0) {
-      split_store_half(e, X, x);
-      publish();
+      split_store_tmem_half(e, t_x, x);
+      publish_tmem();
       // ---- 5. the gathered addend tables of the next edge-level kernels: fp16(h2 . Wout_o + b_o) ---------------
-      G.issue(X_addr, t_acc0, 0u);
-#pragma unroll 1
-      for (int o = 0; o < p.n_out; ++o) {
-        if (o + 1 < p.n_out) G.issue(X_addr, ((o + 1) & 1) ? t_acc1 : t_acc0, 0u);
+      // three accumulators are free here (the FFN's): three products are posted up front and run back to back on the
+      // tensor pipe while the earlier ones are converted and stored; the fourth reuses the first accumulator.
+      const uint32_t t_out[4] = {t_acc0, t_acc1, t_acc2, t_acc0};
+#pragma unroll
+      for (int o = 0; o < 3; ++o)
+        if (o < p.n_out) G.issue(t_x, t_out[o], kFlagTmemA);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (o >= p.n_out) break;
         G.wait_next();
-        tmem_ld_half(e, (o & 1) ? t_acc1 : t_acc0, x);
+        NPROF(6);  // tables: waiting for the product
+        tmem_ld_half(e, t_out[o], x);
         add_bias_half(e, x, p.cv, NodeUpdateParams::kOutBias + o * 128);
         if (valid) {
           __half* dst = p.out[o] + (size_t)row * D + e.half * 64;
@@ -650,16 +753,27 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
               st256u(dst + q * 32 + j * 16, pk);
             }
         }
-        tc_before();
-        epi_sync();  // the accumulator just read is overwritten by the group issued at the top of the next pass
+        if (o == 0 && p.n_out > 3) {  // every thread has read the first accumulator: it takes the fourth product
+          tc_before();
+          epi_sync();
+          G.issue(t_x, t_out[3], kFlagTmemA);
+        }
+        NPROF(7);  // tables: epilogue
       }
+      tc_before();
+      epi_sync();
     } else {
       tc_before();
       epi_sync();
     }
-    NPROF(6);  // output tables
+    NPROF(6);
   }
-  NPROF_PRINT("node_update [-, partials, product 1, LN0, FFN, LN1, tables]", 0);
+  NPROF_PRINT("node_update [-, partials, product 1, LN0, FFN, LN1, tables: wait, tables: epilogue]", 0);
+#ifdef PST_NODE_PROFILE
+  if (blockIdx.x == 0 && (tid == 0 || tid == 160))
+    printf("  FFN thread %d [-, waits, load + GELU, image store, publish + post, tail wait]: %lld %lld %lld %lld %lld %lld\n", tid, G.pf[0], G.pf[1],
+           G.pf[2], G.pf[3], G.pf[4], G.pf[5]);
+#endif
   chain_teardown(S, warp);
 }
 
@@ -758,13 +872,9 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
       layer_norm_row(e, x, p.cv, w + RB::kRtLnS, w + RB::kRtLnO);
       split_store_half(e, X, x);
       publish();
-      chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accA, 2, p.cv, w + RB::kRtB1);  // 2 chunks: the output reuses accA
-      {
-        float r[2][32];
-        tmem_ld_half(e, t_accA, x);
-        tmem_ld_half(e, t_res, r);
-        add_residual_bias_half(e, x, r, p.cv, w + RB::kRtB2);
-      }
+      chunked_mlp<2>(G, e, X_addr, 0u, t_accA, t_accB, t_res, kFlagAcc, 2, p.cv, w + RB::kRtB1);  // accumulated onto res in TMEM
+      tmem_ld_half(e, t_res, x);
+      add_bias_half(e, x, p.cv, w + RB::kRtB2);
       tmem_st_half(e, t_res, x);
       // ---- original transition; its result is never read after the last block (modules.py:624-629) ---------------
       if (b < p.num_blocks - 1) {
@@ -772,11 +882,9 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
         layer_norm_row(e, x, p.cv, w + RB::kOtLnS, w + RB::kOtLnO);
         split_store_half(e, X, x);
         publish();
-        chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accA, 2, p.cv, w + RB::kOtB1);
-        float r[2][32];
-        tmem_ld_half(e, t_accA, x);
-        tmem_ld_half(e, t_orig, r);
-        add_residual_bias_half(e, x, r, p.cv, w + RB::kOtB2);
+        chunked_mlp<2>(G, e, X_addr, 0u, t_accA, t_accB, t_orig, kFlagAcc, 2, p.cv, w + RB::kOtB1);
+        tmem_ld_half(e, t_orig, x);
+        add_bias_half(e, x, p.cv, w + RB::kOtB2);
         tmem_st_half(e, t_orig, x);
       }
     }
@@ -907,7 +1015,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_orig_kernel(const __gri
         layer_norm_row(e, x, p.cv, w + OB::kOtLnS, w + OB::kOtLnO);
         split_store_half(e, X, x);
         publish();
-        chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accC, 2, p.cv, w + OB::kOtB1);
+        chunked_mlp<2>(G, e, X_addr, 0u, t_accA, t_accB, t_accC, 0u, 2, p.cv, w + OB::kOtB1);
         float r[2][32];
         tmem_ld_half(e, t_accC, x);
         tmem_ld_half(e, t_orig, r);
@@ -1057,7 +1165,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_token_kernel(const __gr
       layer_norm_row(e, x, p.cv, w + TB::kRtLnS, w + TB::kRtLnO);
       split_store_half(e, X, x);
       publish();
-      chunked_mlp<2>(G, e, X_addr, U, U_addr, t_accA, t_accB, t_accC, 2, p.cv, w + TB::kRtB1);
+      chunked_mlp<2>(G, e, X_addr, 0u, t_accA, t_accB, t_accC, 0u, 2, p.cv, w + TB::kRtB1);
       {
         float r[2][32];
         tmem_ld_half(e, t_accC, x);
