@@ -95,26 +95,34 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MMA issue.  These four are called by ALL 32 lanes of the (converged) MMA warp and elect the issuing lane inside the
+// asm statement.  Round 2 finding: called from `if (tid == X)` code the compiler cannot know that one thread is active
+// and wraps every UTCHMMA in an ELECT / BRA.U.ANY loop with its operands re-materialised (~10 instructions, ~115
+// cycles per MMA measured: a split 128 x 128 x 128 product took 2 750 cycles for 1 536 cycles of tensor work).  With
+// the election inside a statement the whole warp executes, the UTCHMMAs are emitted back to back from uniform registers.
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
       "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
 // A operand from TMEM (K-major only: lane = row, each 32-bit column holds two consecutive K elements), B from shared memory
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
 // arrive on the barrier at the same shared-memory offset in every CTA of the cluster
 __device__ __forceinline__ void umma_commit_mc(uint32_t mbar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(mask)
-               : "memory");
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n" ::"r"(mbar),
+      "h"(mask)
+      : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(mbar)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -519,7 +527,8 @@ struct Groups {
     tc_after();
   }
 };
-// the MMA warp's loop (one thread): `total` groups, in the order the epilogue threads post them
+// the MMA warp's loop (all 32 lanes, converged; the issuing lane is elected inside umma / umma_commit): `total` groups,
+// in the order the epilogue threads post them
 __device__ __forceinline__ void mma_loop(Ring ring, uint32_t cmd_bar, uint32_t cmd, uint32_t idesc, int total) {
   for (int i = 0; i < total; ++i) {
     const uint32_t slot = (uint32_t)i % kCmdSlots;
@@ -530,7 +539,7 @@ __device__ __forceinline__ void mma_loop(Ring ring, uint32_t cmd_bar, uint32_t c
     issue_unit(ring, a_set, acc, flags, idesc, done);
   }
 #ifdef PST_NODE_PROFILE
-  if (blockIdx.x == 0) printf("mma warp: waited %lld cycles for weights\n", ring.waited);
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) printf("mma warp: waited %lld cycles for weights\n", ring.waited);
 #endif
 }
 // images written by the epilogue threads become visible to the tensor core; accumulators read by them may be reused
@@ -612,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
   const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
   if (warp >= kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
-    if (tid == kEpiThreads + 32) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
+    if (warp == kEpiThreads / 32 + 1) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
     __syncwarp();
     chain_teardown(S, warp);
     return;
@@ -656,9 +665,11 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
         for (int j = 0; j < 32; ++j) x[q][j] = x[q][j] / kf;
 #endif
     }
+    NPROF(1);  // partial sums loaded + scaled
     split_store_tmem_half(e, t_x, x);
+    NPROF(7);  // (profile only) image store of the partial sums
     publish_tmem();
-    NPROF(1);  // partial sums -> images
+    NPROF(0);  // (profile only) publish
     G.issue(t_x, t_acc0, kFlagTmemA);
     G.wait_next();
     NPROF(2);  // product 1 (issue + wait)
@@ -808,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
   const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
   if (warp >= kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
-    if (tid == kEpiThreads + 32) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
+    if (warp == kEpiThreads / 32 + 1) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
     __syncwarp();
     chain_teardown(S, warp);
     return;
@@ -971,7 +982,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_orig_kernel(const __gri
   const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA (lock-step weight ring)
   if (warp >= kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
-    if (tid == kEpiThreads + 32) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
+    if (warp == kEpiThreads / 32 + 1) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
     __syncwarp();
     chain_teardown(S, warp);
     return;
@@ -1057,7 +1068,7 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_token_kernel(const __gr
   const int my_tiles = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   if (warp >= kEpiThreads / 32) {
     if (tid == kEpiThreads) producer_loop(S.ring, p.sched, p.n_sched, my_tiles);
-    if (tid == kEpiThreads + 32) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
+    if (warp == kEpiThreads / 32 + 1) mma_loop(S.ring, S.cmd_bar, S.cmd, p.idesc, my_tiles * (p.n_sched / 2));
     __syncwarp();
     chain_teardown(S, warp);
     return;
