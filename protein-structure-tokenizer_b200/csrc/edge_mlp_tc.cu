@@ -163,17 +163,23 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return d;
 }
 
+// MMA issue: umma_f16 / umma_commit are called by ALL 32 lanes of a converged warp and elect the issuing lane inside
+// the asm statement.  Called from `if (lane == 0)` code the compiler cannot know that a single thread is active and
+// wraps every UTCHMMA in an ELECT / BRA.U.ANY loop (~10 instructions per MMA); with the election inside a statement
+// the whole warp executes the UTCHMMAs are emitted back to back (round 2, found on the node-level kernels).
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
-      ".reg .pred p;\n"
+      ".reg .pred p, q;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t mbar_addr) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_addr) : "memory");
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(mbar_addr)
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -235,7 +241,7 @@ struct Unpack<__nv_bfloat16> {
   static __device__ __forceinline__ float2 two(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
 };
 
-// Not inlined on purpose: one thread per tile group issues, and inlining lets the compiler hoist the ~60 loop-invariant
+// Called by the whole first warp of a tile group (converged).  Not inlined on purpose: inlining lets the compiler hoist the ~60 loop-invariant
 // descriptor words of the three GEMMs into registers of ALL threads (the epilogue warps run with 80 registers).
 __device__ __noinline__ void issue_gemm(uint32_t tmem_acc, uint32_t sA_addr, uint32_t sW_addr, uint32_t idesc,
                                         uint32_t mbar_addr, uint32_t accumulate_first) {
@@ -519,8 +525,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
       if (q == 0) {
         mbar_wait(smem_u32(&abar[s]), par);
         mbar_wait(smem_u32(&tbar[s]), MODE == 0 ? par : 0u);
-        if (lane == 0)
-          issue_gemm(tmem_base + (uint32_t)(s * 128), smem_u32(sAall + s * kMatBytes), sW_addr, p.idesc, smem_u32(&gbar[s]), 1u);
+        issue_gemm(tmem_base + (uint32_t)(s * 128), smem_u32(sAall + s * kMatBytes), sW_addr, p.idesc, smem_u32(&gbar[s]), 1u);
         __syncwarp();
       }
       tile = ntile;
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
       tc_fence_before();
       group_sync(g);
       // ---- 2. GEMM 2 ----------------------------------------------------------------------------------
-      if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + kMatBytes, p.idesc, mbar_addr, 0u);
+      if (gt < 32) issue_gemm(tmem_acc, sA_addr, sW_addr + kMatBytes, p.idesc, mbar_addr, 0u);
       mbar_wait(mbar_addr, 0u);
       tc_fence_after();
       if (MODE == 1) {
@@ -562,7 +567,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
         fence_proxy_async();
         tc_fence_before();
         group_sync(g);
-        if (gt == 0) issue_gemm(tmem_acc, sA_addr, sW_addr + 2 * kMatBytes, p.idesc, mbar_addr, 0u);
+        if (gt < 32) issue_gemm(tmem_acc, sA_addr, sW_addr + 2 * kMatBytes, p.idesc, mbar_addr, 0u);
         mbar_wait(mbar_addr, 1u);
         tc_fence_after();
         // pass 1: x = acc + b3 + e.  The tile is re-read (an L2 hit) by TMA into the free A buffer, in the operand
@@ -647,7 +652,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) edge_mlp_tc_kernel(EdgeMlpPara
         fence_proxy_async();
         tc_fence_before();
         group_sync(g);
-        if (gt == 0) {
+        if (gt < 32) {
           tc_fence_after();
           const uint32_t sel_addr = smem_u32(sSel);
 #pragma unroll
@@ -863,7 +868,7 @@ __global__ void __launch_bounds__(kTThreads, 1) edge_msg_t_kernel(MsgTParams p, 
         TPROF(2 + st);  // waiting for stage st (+ issuing the previous stage's products)
         if (st < 2) fence_proxy_async();  // the cp.async copies are generic-proxy writes; the tensor core reads through the async proxy
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t wblk = sW_addr + (st < 2 ? 0u : kMatBytes) + (uint32_t)(st & 1) * kKBlockBytes;
           const uint32_t xblk = ring_addr + (uint32_t)st * kKBlockBytes;
 #pragma unroll
@@ -954,7 +959,7 @@ __global__ void __launch_bounds__(kTThreads, 1) edge_msg_t_kernel(MsgTParams p, 
       group_sync(g);
       TPROF(3);  // group barrier
       // ---- second product: D^T[:, half] = W2^T . act1 (B = the activation image read MN-major, N = 64) ----------------
-      if ((warp & 3) == 0 && lane == 0) {
+      if ((warp & 3) == 0) {
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(slot * 128 + hf * 64);
         const uint32_t w2 = sW_addr + 2 * kMatBytes;
@@ -1239,7 +1244,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_embed_tc_kernel(EmbedParams 
     fence_proxy_async();
     tc_fence_before();
     group_sync(g);
-    if (gt == 0) {
+    if (gt < 32) {
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < 2; ++j) {  // K = 32 = 2 x UMMA_K
