@@ -1324,8 +1324,8 @@ int pst_prepare_node_chain(pst_model* m) {
       const PstLayerW& nx = m->w.layer[l + 1];
       push_unit(w.edge_w1, D, D, 0, 0);
       push_unit(w.edge_w1 + D * D, D, D, 0, 0);
-      push_unit(nx.msg_w1, D, D, 0, 0);
       push_unit(nx.msg_w1 + D * D, D, D, 0, 0);
+      push_unit(nx.msg_w1, D, D, 0, 0);  // last: not computed when the next message MLP gathers fp16(h) itself (edge_msg_t_kernel)
       C.layer_nout[l] = 4;
     }
     C.layer_n[l] = (int)all.size() - C.layer_off[l];
@@ -1401,8 +1401,12 @@ int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const
     const PstLayerW& nx = m->w.layer[layer + 1];
     p.out[0] = reinterpret_cast<__half*>(out_edge_s);
     p.out[1] = reinterpret_cast<__half*>(out_edge_r); put(NodeUpdateParams::kOutBias + 128, w.edge_b1, 128);
-    p.out[2] = reinterpret_cast<__half*>(out_msg_s);
-    p.out[3] = reinterpret_cast<__half*>(out_msg_r);  put(NodeUpdateParams::kOutBias + 384, nx.msg_b1, 128);
+    p.out[2] = reinterpret_cast<__half*>(out_msg_r);  put(NodeUpdateParams::kOutBias + 256, nx.msg_b1, 128);
+    p.out[3] = reinterpret_cast<__half*>(out_msg_s);
+    if (h16) {  // the transposed message kernel takes the sender term from h16: its table (the last one) is not needed
+      p.n_out = 3;
+      p.n_sched -= 2;
+    }
   }
   p.R = R;
   p.num_tiles = (R + 127) / 128;
