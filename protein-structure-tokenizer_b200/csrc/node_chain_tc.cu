@@ -671,13 +671,13 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
     publish_tmem();
     NPROF(0);  // (profile only) publish
     G.issue(t_x, t_acc0, kFlagTmemA);
-    G.wait_next();
-    NPROF(2);  // product 1 (issue + wait)
-    // ---- 2. h1 = LN0(h + agg + b3) -> TMEM (fp32) + X images ---------------------------------------------------
+    // ---- 2. h1 = LN0(h + agg + b3) -> images in t_x ------------------------------------------------------------
     {
       float hh[2][32];
+      load_row_half(e, p.h + (size_t)row * D, valid, hh);  // in flight while the product runs
+      G.wait_next();
+      NPROF(2);  // product 1 (issue + wait)
       tmem_ld_half(e, t_acc0, x);
-      load_row_half(e, p.h + (size_t)row * D, valid, hh);
       add_residual_bias_half(e, x, hh, p.cv, NodeUpdateParams::kB3);
     }
     layer_norm_row(e, x, p.cv, NodeUpdateParams::kLn0S, NodeUpdateParams::kLn0O);
