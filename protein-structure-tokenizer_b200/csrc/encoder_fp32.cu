@@ -208,13 +208,21 @@ __global__ void node_embed_kernel(const float* __restrict__ table, const int32_t
 // tables as well (computed once at model creation by the same tensor-core linear, pst_prepare_layer0_tables).
 __global__ void node_embed_tables_kernel(const float* __restrict__ table, const __half* __restrict__ ps0,
                                          const __half* __restrict__ pr0, const int32_t* __restrict__ row_base,
-                                         float* __restrict__ h, __half* __restrict__ ps, __half* __restrict__ pr, int rows) {
+                                         float* __restrict__ h, __half* __restrict__ ps, __half* __restrict__ pr,
+                                         __half* __restrict__ h16, int rows) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const size_t local = (size_t)(row - row_base[row]);
-  *reinterpret_cast<float4*>(h + (size_t)row * D + lane * 4) = *reinterpret_cast<const float4*>(table + local * D + lane * 4);
-  *reinterpret_cast<uint2*>(ps + (size_t)row * D + lane * 4) = *reinterpret_cast<const uint2*>(ps0 + local * D + lane * 4);
+  const float4 v = *reinterpret_cast<const float4*>(table + local * D + lane * 4);
+  *reinterpret_cast<float4*>(h + (size_t)row * D + lane * 4) = v;
+  if (h16) {  // the transposed message kernel gathers fp16(h) for the sender term: no sender table, no separate conversion pass
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(h16 + (size_t)row * D + lane * 4) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  } else {
+    *reinterpret_cast<uint2*>(ps + (size_t)row * D + lane * 4) = *reinterpret_cast<const uint2*>(ps0 + local * D + lane * 4);
+  }
   *reinterpret_cast<uint2*>(pr + (size_t)row * D + lane * 4) = *reinterpret_cast<const uint2*>(pr0 + local * D + lane * 4);
 }
 
@@ -423,7 +431,8 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     node_embed_tables_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->w.node_table, reinterpret_cast<const __half*>(m->layer0_tables),
                                                          reinterpret_cast<const __half*>(m->layer0_tables) + (size_t)cfg.seq_max_size * D,
                                                          row_base, ws.h, reinterpret_cast<__half*>(ws.ps),
-                                                         reinterpret_cast<__half*>(ws.pr), R);
+                                                         reinterpret_cast<__half*>(ws.pr),
+                                                         (m->use_msg_t && pst_edge_msg_t_ok(m)) ? reinterpret_cast<__half*>(ws.dn) : nullptr, R);
   else
     node_embed_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->w.node_table, row_base, ws.h, R);
   ++L.count;
@@ -467,7 +476,7 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
         if (msg_t) {
           // transposed kernel: the sender term is a product with the gathered rows of fp16(h) (ws.dn is free until the
           // resampler); the node kernel of the previous layer has written it, layer 0 converts the embedding
-          if (l == 0) L.count += pst_launch_to_half(st, ws.h, h16, (size_t)R * D);
+          if (l == 0 && !m->layer0_tables) L.count += pst_launch_to_half(st, ws.h, h16, (size_t)R * D);  // else written with the embedding
           n = pst_launch_edge_msg_t(m, st, l, reinterpret_cast<const uint16_t*>(ws.e), h16, pr, ws.senders_abs, ws.partial, R);
         } else {
           n = pst_launch_edge_mlp_tc(m, st, l, 0, reinterpret_cast<uint16_t*>(ws.e), ps, pr, ws.senders_abs, row_base, ws.partial, R);  // the node kernel sums the partials itself
