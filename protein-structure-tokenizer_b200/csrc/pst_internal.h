@@ -77,7 +77,7 @@ struct pst_model {
   bool use_msg_t;            // message MLPs through the transposed kernel (edge_msg_t_kernel; PST_MSG_T=0 switches it off)
   mutable int launch_count;
   // CUDA-graph cache of the fused hot call (api.cu): a pst_tokenize call whose arguments (pointers and sizes) repeat
-  // is captured once and replayed, which removes the launch gaps between its ~110 dependent kernels
+  // is captured once and replayed, which removes the launch gaps between its dependent kernels
   mutable struct PstGraphCache* graphs;
   // optional per-kernel-group timing (pst_profile_*): CUDA events recorded on the call's stream
   mutable bool prof_on;
