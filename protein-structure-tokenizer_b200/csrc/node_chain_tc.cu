@@ -9,7 +9,7 @@
 //      h   = MaskedLayerNorm0(h + agg)          (:379-382)
 //      h   = MaskedLayerNorm1(h + MLP_{128->512->128}(h))   (:385-399; the 512-wide hidden is chunked 4 x 128
 //                                                 and never leaves the SM)
-//      out_o = fp16(h.Wout_o + b_o)             the four gathered addend tables the next two edge-level
+//      out_o = fp16(h.Wout_o + b_o)             the gathered addend tables (3, or 4 for the old message kernel) the next two edge-level
 //                                                 kernels need: edge MLP of this layer (:402-419) and message
 //                                                 MLP of the next (:344-361), first linear factorised
 //
@@ -22,11 +22,15 @@
 // Numerics: as linear_tc.cu - every fp32 operand is split x = hi + lo (two fp16) and each product is evaluated as
 // hi.hi + hi.lo + lo.hi with fp32 accumulation in TMEM; LayerNorm / GELU / sigmoid / FSQ in fp32 registers.
 //
-// Structure: 1 CTA / SM, 4 epilogue warps (thread = row: the TMEM 32x32b layout) + 1 producer warp.
-// Shared memory: two activation image sets (hi/lo, 2 K-blocks: 64 KB each) + a 3-slot ring of 32 KB weight
-// half-units (hi+lo images of one 64-row K block of a 128-column weight slice) streamed from L2 by
-// cp.async.bulk on full/empty mbarriers; tcgen05.commit releases a slot.  The per-row state that must survive a
-// GEMM (h after LN0, res / orig of the resampler) lives in spare TMEM columns, not in registers.
+// Structure (round 2): 1 CTA / SM in clusters of 2; 8 epilogue warps (thread = row x column half: the TMEM 32x32b
+// layout), a weight-producer warp and an MMA warp.  A 3-slot ring of 32 KB weight half-units (hi + lo images of one
+// 64-row K block of a 128-column weight slice) is streamed from L2 by cp.async.bulk with cluster multicast on full /
+// empty mbarriers; tcgen05.commit releases a slot.  The epilogue threads post every product into a command queue, the
+// MMA warp issues it.  Activations are A operands IN TMEM wherever a region is free: hidden chunks of the MLPs are
+// written in place over their accumulators, node_update_kernel keeps its input / h1 images in a fourth region and has
+// no activation in shared memory; the resampler kernels stage their LayerNorm outputs in one or two shared-memory image
+// sets (X, U: hi / lo, 2 K blocks, 64 KB each) because all four TMEM regions hold state or accumulators there.  The
+// per-row state that must survive a product (res / orig of the resampler) lives in TMEM, not in registers.
 #include <cuda_fp16.h>
 
 #include <vector>
@@ -626,9 +630,6 @@ __global__ void __launch_bounds__(kThreads, 1) node_update_kernel(const __grid_c
     chain_teardown(S, warp);
     return;
   }
-  uint8_t* X = smem + kOffX;
-  uint8_t* U = smem + kOffU;
-  const uint32_t X_addr = smem_u32(X), U_addr = smem_u32(U);
   Epi e{tid, tid & 127, tid >> 7, (uint32_t)((warp & 3) * 32) << 16, S.red};
   const uint32_t t_acc0 = S.tmem_base + 0, t_x = S.tmem_base + 128, t_acc1 = S.tmem_base + 256, t_acc2 = S.tmem_base + 384;
   // t_x: the hi / lo images of the current activation (A operand of every first-layer product, read from TMEM: with

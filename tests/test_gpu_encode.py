@@ -157,6 +157,38 @@ def test_tensor_core_modes_match_oracle(built_lib, precision, codebook, df, mean
     assert agree / total >= min_agree, agree / total
 
 
+@pytest.mark.parametrize("env,codebook,df", [("PST_MSG_T", 4096, 1), ("PST_FUSED_RESAMPLER", 64000, 4)])
+def test_switched_off_kernels_fall_back_to_the_older_gpu_path_with_agreeing_tokens(built_lib, monkeypatch, env, codebook, df):
+    """The two environment switches read at model creation (csrc/api.cu): PST_MSG_T=0 runs the message MLPs through
+    edge_mlp_tc_kernel<., 0> (the node kernel then writes all four addend tables), PST_FUSED_RESAMPLER=0 runs the
+    df > 1 resampler per op.  Both are GPU paths of the same precision mode: latents within the fp16 tolerance of each
+    other, tokens agree."""
+    import torch
+
+    lengths = [64, 101, 256, 50, 190, 77]
+    cfg, params, tok, bbs, graphs = _setup(codebook, df, "fp16", lengths)
+    monkeypatch.setenv(env, "0")
+    _, _, tok_off, _, _ = _setup(codebook, df, "fp16", lengths)
+    monkeypatch.delenv(env)
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)
+    toff = tok.token_offsets(offs)
+    feats = torch.from_numpy(np.concatenate([g["edge_features"].astype(np.float32) for g in graphs])).cuda()
+    send = torch.from_numpy(np.concatenate([g["senders"].astype(np.int32) for g in graphs])).cuda()
+    out = []
+    for t in (tok, tok_off):
+        z = t.encode_graph_device(feats, send, torch.from_numpy(offs).cuda(), torch.from_numpy(toff).cuda(), len(lengths),
+                                  int(offs[-1]), int(toff[-1]))
+        n_launch = t.launches
+        tokens = t.quantize_device(z)
+        torch.cuda.synchronize()
+        out.append((z.cpu().numpy(), tokens.cpu().numpy(), n_launch))
+    (z0, t0, n0), (z1, t1, n1) = out
+    assert n1 > n0 if env == "PST_FUSED_RESAMPLER" else n1 == n0  # the per-op resampler launches ~40 kernels more
+    assert np.isfinite(z1).all()
+    assert np.abs(z0 - z1).max() <= 6e-3
+    assert (t0 == t1).mean() >= 0.99
+
+
 def test_graph_replay_matches_eager_and_follows_new_data(built_lib):
     """pst_tokenize replays a CUDA graph when its argument set repeats (include/pst_abi.h: pst_graph_cache_enable).
     The replayed call must give the tokens of the eager call, and, because only pointers and sizes are baked into
