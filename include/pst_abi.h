@@ -162,7 +162,7 @@ int pst_tokenize(const pst_model* model, void* stream, const float* atoms,
  * the cached graphs).  The launch sequence of pst_tokenize depends only on its arguments (the host never reads device
  * data), so when a call repeats the pointers and sizes of an earlier one on a named stream, the library captures the
  * sequence into a CUDA graph once (on the second occurrence) and replays it afterwards: the dependent kernels of a
- * call (17 in the tensor-core modes at df = 1) otherwise pay a launch gap each.  The cache is keyed by the BUFFERS of a call, up to 64 sets per model (LRU); when the same buffers come back with other sizes (the next ragged chunk of a stream) the instantiated graph is updated in place (cudaGraphExecUpdate);
+ * call (16 in the tensor-core modes at df = 1) otherwise pay a launch gap each.  The cache is keyed by the BUFFERS of a call, up to 64 sets per model (LRU); when the same buffers come back with other sizes (the next ragged chunk of a stream) the instantiated graph is updated in place (cudaGraphExecUpdate);
  * the cache is the only mutable state of a pst_model and is guarded by a mutex.  Calls on the legacy / per-thread
  * default stream, calls made while the caller is itself capturing `stream`, and calls with profiling enabled are
  * enqueued kernel by kernel as before. */

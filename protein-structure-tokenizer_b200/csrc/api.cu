@@ -234,6 +234,7 @@ int pst_model_create(const pst_config* cfg, const float* blob_host, size_t blob_
   if (m->graphs) { const char* g = getenv("PST_CUDA_GRAPH"); m->graphs->enabled = !(g && g[0] == '0'); }
   { const char* t = getenv("PST_MSG_T"); m->use_msg_t = !(t && t[0] == '0'); }
   { const char* t = getenv("PST_FUSED_RESAMPLER"); m->use_fused_resampler = !(t && t[0] == '0'); }
+  { const char* t = getenv("PST_FUSED_FSQ"); m->use_fused_fsq = !(t && t[0] == '0'); }
   m->linear_tc = nullptr;
   m->node_chain = nullptr;
   m->embed_img_dev = nullptr;
@@ -420,11 +421,14 @@ static int tokenize_enqueue(const pst_model* m, cudaStream_t st, const float* at
                                  total_residues, ws.senders, ws.edge_feat, ws.prep, ws.cen4, ws.status, ws.redo, compact);
   }
   if (count < 0) return count;
+  // The quantiser (bound, round, pack) is the epilogue of the fused resampler kernels where they run (tensor-core modes):
+  // the head that forms a token's latent also emits its int32 id.  Other paths quantise in a launch of their own.
+  bool tokens_done = false;
   int n = pst_launch_encode_fp32(m, st, ws.edge_feat, ws.senders, offsets, token_offsets, num_structures,
-                                 total_residues, total_tokens, ws.z, ws, compact);
+                                 total_residues, total_tokens, ws.z, ws, compact, m->use_fused_fsq ? tokens_out : nullptr, &tokens_done);
   if (n < 0) return n;
   count += n;
-  {
+  if (!tokens_done) {
     PstSpan span(m, st, 6);
     count += pst_launch_quantize(m, st, ws.z, total_tokens, tokens_out, nullptr, ws.status);
   }

@@ -415,7 +415,8 @@ int pst_prepare_layer0_tables(pst_model* m) {
 int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edge_feat,
                            const int32_t* senders, const int32_t* offsets,
                            const int32_t* token_offsets, int B, int R, int T, float* z_out,
-                           PstWorkspace& ws, int compact_features) {
+                           PstWorkspace& ws, int compact_features, int32_t* fused_tokens, bool* fused_tokens_done) {
+  if (fused_tokens_done) *fused_tokens_done = false;
   const pst_config& cfg = m->cfg;
   const int K = cfg.num_neighbor;
   const int E = R * K;
@@ -536,8 +537,9 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
   if (tc && cfg.downsampling_ratio == 1) {
     // df = 1: token t attends residue t alone, the three blocks + head are row-local: one fused kernel
     PstSpan span(m, st, 5);
-    int n = pst_launch_resampler_df1(m, st, ws.h, row_base, R, z_out);
+    int n = pst_launch_resampler_df1(m, st, ws.h, row_base, R, z_out, fused_tokens, fused_tokens ? ws.status : nullptr);
     if (n < 0) return n;
+    if (fused_tokens && fused_tokens_done && n > 0) *fused_tokens_done = true;
     return L.count + n;
   }
   if (tc && cfg.downsampling_ratio > 1 && cfg.num_blocks <= 3 && m->use_fused_resampler && T > 0) {
@@ -545,8 +547,10 @@ int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edg
     // buffers the GNN no longer needs (ws.u holds four [R,128] arrays)
     PstSpan span(m, st, 5);
     float* kv[6] = {ws.kx, ws.vx, ws.u, ws.u + (size_t)R * D, ws.u + 2 * (size_t)R * D, ws.u + 3 * (size_t)R * D};
-    int n = pst_launch_resampler_dfn(m, st, ws.h, offsets, token_offsets, B, R, T, kv, ws.q, z_out);
+    int n = pst_launch_resampler_dfn(m, st, ws.h, offsets, token_offsets, B, R, T, kv, ws.q, z_out, fused_tokens,
+                                     fused_tokens ? ws.status : nullptr);
     if (n < 0) return n;
+    if (fused_tokens && fused_tokens_done && n > 0) *fused_tokens_done = true;
     return L.count + n;
   }
   token_embed_kernel<<<(T + 7) / 8, 256, 0, st>>>(m->w.token_table, token_offsets, B, ws.res, T);

@@ -38,6 +38,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "fsq_device.cuh"
 #include "pst_internal.h"
 
 namespace {
@@ -800,6 +801,9 @@ struct ResamplerParams {
   const float* token_table;  // [max_out_len,128] PE of the token index (modules.py:486-500)
   const int32_t* row_base;   // [R] first row of the structure a row belongs to (df = 1: token index == row)
   float* z;                  // [R,8] pre-quantisation latents, unused columns 0
+  int32_t* tokens;           // optional [R]: the FSQ epilogue (bound, round, pack) of the fused tokenize call
+  int32_t* status;           // the call's status word (PST_ERR_NON_FINITE), with `tokens`
+  PstFsqParams fsq;
   int num_blocks;
   const float* down_w;       // [128,8]
   const float* down_b;       // [8]
@@ -942,6 +946,11 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_df1_kernel(const __grid
         float4* zd = reinterpret_cast<float4*>(p.z + (size_t)row * PST_C8);
         zd[0] = make_float4(o[0], o[1], o[2], o[3]);
         zd[1] = make_float4(o[4], o[5], o[6], o[7]);
+        if (p.tokens) {  // quantiser as the epilogue of the chain (model/quantize.py:175-209): int32 token ids
+          bool finite = true;
+          p.tokens[row] = pst_fsq_token(o, p.fsq, finite);
+          if (!finite) atomicMin(p.status, (int)PST_ERR_NON_FINITE);
+        }
       }
       tc_before();
       epi_sync();  // zs (in U) and the TMEM state are rewritten by the next tile
@@ -1050,6 +1059,9 @@ struct ResamplerTokenParams {
   const float* k[3];         // per block [R,128]
   const float* v[3];
   float* z;                  // [T,8]
+  int32_t* tokens;           // optional [T]: the FSQ epilogue of the fused tokenize call
+  int32_t* status;
+  PstFsqParams fsq;
   int num_blocks, df;
   const float* down_w;
   const float* down_b;
@@ -1227,6 +1239,11 @@ __global__ void __launch_bounds__(kThreads, 1) resampler_token_kernel(const __gr
         float4* zd = reinterpret_cast<float4*>(p.z + (size_t)t * PST_C8);
         zd[0] = make_float4(o[0], o[1], o[2], o[3]);
         zd[1] = make_float4(o[4], o[5], o[6], o[7]);
+        if (p.tokens) {  // quantiser as the epilogue of the chain
+          bool finite = true;
+          p.tokens[t] = pst_fsq_token(o, p.fsq, finite);
+          if (!finite) atomicMin(p.status, (int)PST_ERR_NON_FINITE);
+        }
       }
       tc_before();
       epi_sync();  // zs (in U) and the TMEM state are rewritten by the next tile
@@ -1416,12 +1433,14 @@ int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const
 }
 
 // z <- the whole resampler + head for downsampling_ratio == 1 (token t == residue t); h = node features after the GNN
-int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z) {
+int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z,
+                             int32_t* tokens, int32_t* status) {
   if (!m->node_chain || R <= 0 || m->cfg.downsampling_ratio != 1) return 0;
   if (m->cfg.num_blocks > ResamplerParams::kMaxBlocks) return PST_ERR_UNSUPPORTED_CONFIG;
   const PstNodeChain& C = *m->node_chain;
   ResamplerParams p{};
   p.h = h; p.token_table = m->w.token_table; p.row_base = row_base; p.z = z;
+  p.tokens = status ? tokens : nullptr; p.status = status; p.fsq = pst_fsq_params(m);
   p.num_blocks = m->cfg.num_blocks;
   for (int b = 0; b < p.num_blocks; ++b) {
     const PstBlockW& w = m->w.block[b];
@@ -1445,7 +1464,7 @@ int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h
 // z <- the whole resampler + head for downsampling_ratio > 1: token-info lookup, residue track, token track.
 // kv: six [R,128] fp32 buffers (k and v of the three blocks); info: int2 [T].
 int pst_launch_resampler_dfn(const pst_model* m, cudaStream_t st, const float* h, const int32_t* offsets, const int32_t* token_offsets,
-                             int B, int R, int T, float* const* kv, void* info, float* z) {
+                             int B, int R, int T, float* const* kv, void* info, float* z, int32_t* tokens, int32_t* status) {
   if (!m->node_chain || R <= 0 || T <= 0 || m->cfg.downsampling_ratio <= 1) return 0;
   if (m->cfg.num_blocks > 3 || m->cfg.downsampling_ratio > 8) return PST_ERR_UNSUPPORTED_CONFIG;
   const PstNodeChain& C = *m->node_chain;
@@ -1471,6 +1490,7 @@ int pst_launch_resampler_dfn(const pst_model* m, cudaStream_t st, const float* h
   {
     ResamplerTokenParams p{};
     p.token_table = m->w.token_table; p.info = static_cast<const int2*>(info); p.z = z;
+    p.tokens = status ? tokens : nullptr; p.status = status; p.fsq = pst_fsq_params(m);
     p.num_blocks = nb; p.df = m->cfg.downsampling_ratio;
     for (int b = 0; b < nb; ++b) {
       const PstBlockW& w = m->w.block[b];

@@ -74,6 +74,7 @@ struct pst_model {
   float half_l[PST_C8], fsq_offset[PST_C8], fsq_shift[PST_C8];
   int32_t basis[PST_C8], half_width[PST_C8];
   bool use_fused_resampler;  // df > 1: the two fused chain kernels instead of the per-op path (PST_FUSED_RESAMPLER=0 switches them off)
+  bool use_fused_fsq;        // pst_tokenize: the quantiser is the epilogue of the fused resampler kernels (PST_FUSED_FSQ=0: separate launch)
   bool use_msg_t;            // message MLPs through the transposed kernel (edge_msg_t_kernel; PST_MSG_T=0 switches it off)
   mutable int launch_count;
   // CUDA-graph cache of the fused hot call (api.cu): a pst_tokenize call whose arguments (pointers and sizes) repeat
@@ -145,7 +146,8 @@ bool pst_featurize_compact_ok(const pst_model* m);
 int pst_launch_encode_fp32(const pst_model* m, cudaStream_t st, const float* edge_feat,
                            const int32_t* senders, const int32_t* offsets,
                            const int32_t* token_offsets, int B, int R, int T, float* z_out,
-                           PstWorkspace& ws, int compact_features = 0);
+                           PstWorkspace& ws, int compact_features = 0, int32_t* fused_tokens = nullptr,
+                           bool* fused_tokens_done = nullptr);  // fused_tokens: let the resampler's head emit the token ids too
 
 int pst_launch_quantize(const pst_model* m, cudaStream_t st, const float* z, int n,
                         int32_t* tokens, float* bounded, int32_t* status = nullptr);
@@ -185,10 +187,13 @@ int pst_prepare_layer0_tables(pst_model* m);  // encoder_fp32.cu
 int pst_launch_node_update(const pst_model* m, cudaStream_t st, int layer, const float* partial, int partial_tile_shift, float* h, int R,
                            uint16_t* out_edge_s, uint16_t* out_edge_r, uint16_t* out_msg_s, uint16_t* out_msg_r,
                            uint16_t* h16 = nullptr);
-int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z);
+// tokens / status (both or neither): the FSQ epilogue writes the token ids as well (fused tokenize call)
+int pst_launch_resampler_df1(const pst_model* m, cudaStream_t st, const float* h, const int32_t* row_base, int R, float* z,
+                             int32_t* tokens = nullptr, int32_t* status = nullptr);
 // downsampling_ratio > 1: two chain kernels (residue track, token track); kv = six [R,128] fp32 buffers, info = int2 [T]
 int pst_launch_resampler_dfn(const pst_model* m, cudaStream_t st, const float* h, const int32_t* offsets, const int32_t* token_offsets,
-                             int B, int R, int T, float* const* kv, void* info, float* z);
+                             int B, int R, int T, float* const* kv, void* info, float* z, int32_t* tokens = nullptr,
+                             int32_t* status = nullptr);
 
 #define PST_CUDA_OK(expr)                                  \
   do {                                                     \

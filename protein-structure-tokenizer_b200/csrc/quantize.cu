@@ -4,15 +4,12 @@
 //   round        :188       jnp.round = round half to even  (rintf in the default rounding mode)
 //   pack         :209 -> :113-120 -> :105-107   sum_d (q_d + L_d//2) * prod_{d'<d} L_d'  -> uint32
 //   inverse      :122-139   (renorm = False in every released config)
+#include "fsq_device.cuh"
 #include "pst_internal.h"
 
 namespace {
 
-struct FsqParams {
-  float half_l[PST_C8], offset[PST_C8], shift[PST_C8];
-  int basis[PST_C8], half_width[PST_C8], levels[PST_C8];
-  int C;
-};
+using FsqParams = PstFsqParams;
 
 __global__ void fsq_quantize_kernel(const float* __restrict__ z, int n, FsqParams p, int32_t* __restrict__ tokens,
                                     float* __restrict__ bounded, int32_t* __restrict__ status) {
@@ -21,19 +18,8 @@ __global__ void fsq_quantize_kernel(const float* __restrict__ z, int n, FsqParam
   const float4* zp = reinterpret_cast<const float4*>(z + (size_t)t * PST_C8);
   float4 a = zp[0], b = zp[1];
   float v[PST_C8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  int tok = 0;
   bool finite = true;
-#pragma unroll
-  for (int c = 0; c < PST_C8; ++c) {
-    float bd = 0.f;
-    if (c < p.C) {
-      finite = finite && isfinite(v[c]);
-      bd = tanhf(v[c] + p.shift[c]) * p.half_l[c] - p.offset[c];
-      tok += ((int)rintf(bd) + p.half_width[c]) * p.basis[c];
-    }
-    v[c] = bd;
-  }
-  tokens[t] = tok;
+  tokens[t] = pst_fsq_token(v, p, finite);
   // No silent Inf / NaN: the 16-bit operand modes have a finite range (fp16: 65 504); a latent that arrives here
   // non-finite raises the call's device status word instead of becoming an arbitrary token id.
   if (!finite && status) atomicMin(status, (int)PST_ERR_NON_FINITE);
@@ -63,16 +49,7 @@ __global__ void fsq_unpack_kernel(const int32_t* __restrict__ tokens, int n, Fsq
   }
 }
 
-FsqParams make_params(const pst_model* m) {
-  FsqParams p{};
-  p.C = m->cfg.num_levels;
-  for (int c = 0; c < PST_C8; ++c) {
-    p.half_l[c] = m->half_l[c]; p.offset[c] = m->fsq_offset[c]; p.shift[c] = m->fsq_shift[c];
-    p.basis[c] = m->basis[c]; p.half_width[c] = m->half_width[c];
-    p.levels[c] = c < p.C ? m->cfg.levels[c] : 1;
-  }
-  return p;
-}
+FsqParams make_params(const pst_model* m) { return pst_fsq_params(m); }
 
 }  // namespace
 

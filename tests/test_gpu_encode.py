@@ -189,6 +189,27 @@ def test_switched_off_kernels_fall_back_to_the_older_gpu_path_with_agreeing_toke
     assert (t0 == t1).mean() >= 0.99
 
 
+@pytest.mark.parametrize("codebook,df", [(4096, 1), (64000, 4), (1728, 2)])
+def test_fused_fsq_epilogue_is_bit_identical_to_the_quantiser_launch(built_lib, monkeypatch, codebook, df):
+    """pst_tokenize in the tensor-core modes: the head of the fused resampler kernel emits the int32 token ids itself
+    (csrc/fsq_device.cuh is the one definition of bound / round / pack).  PST_FUSED_FSQ=0 keeps the separate
+    fsq_quantize_kernel launch on the same latents: identical ids, one launch more."""
+    lengths = [64, 101, 256, 50, 190, 77, 512]
+    cfg, params, tok, bbs, graphs = _setup(codebook, df, "fp16", lengths, seed=5)
+    monkeypatch.setenv("PST_FUSED_FSQ", "0")
+    _, _, tok_off, _, _ = _setup(codebook, df, "fp16", lengths, seed=5)
+    monkeypatch.delenv("PST_FUSED_FSQ")
+    a = tok.tokenize(bbs)
+    n_a = tok.launches
+    b = tok_off.tokenize(bbs)
+    n_b = tok_off.launches
+    assert n_b == n_a + 1
+    for x, y, n in zip(a, b, lengths):
+        assert x.shape == y.shape == (n // df,)
+        assert np.array_equal(x, y)
+        assert int(x.max()) < codebook
+
+
 def test_graph_replay_matches_eager_and_follows_new_data(built_lib):
     """pst_tokenize replays a CUDA graph when its argument set repeats (include/pst_abi.h: pst_graph_cache_enable).
     The replayed call must give the tokens of the eager call, and, because only pointers and sizes are baked into
