@@ -188,6 +188,15 @@ int pst_parse_pdb(const char* text, size_t text_bytes, int max_residues, float* 
 int pst_parse_pdb_chain(const char* text, size_t text_bytes, char chain_id, int max_residues, float* atom37_positions,
                         uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out);
 
+/* mmCIF (the next ingest format; the reference itself reads PDB text and sample .npy files only).
+ * The `_atom_site` loop goes through the same selection as the PDB records, with BioPython's MMCIFParser conventions
+ * where the formats differ (chain = auth_asym_id, residue number = auth_seq_id, atom name = label_atom_id, altloc /
+ * insertion code '.' / '?' = none, one pdbx_PDB_model_num).  chain_id: NULL or "" = every chain; ids may be longer than
+ * one character.  pst_parse_pdb, pst_parse_pdb_chain, pst_parse_pdb_batch and pst_parse_pdb_files accept mmCIF text as
+ * well: a text whose first token is a `data_` block header is parsed as mmCIF. */
+int pst_parse_mmcif(const char* text, size_t text_bytes, const char* chain_id, int max_residues, float* atom37_positions,
+                    uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out);
+
 /* HOST function: n_files PDB texts parsed side by side on up to n_threads host threads (<= 0: all hardware threads),
  * the feeder in front of pst_tokenize (the reference parses one file at a time in Python,
  * scripts/inference_runner.py:40-74 called from :288-296).  The output arrays are shared: file i's residues are rows

@@ -320,6 +320,239 @@ int parse_text(const char* text, size_t len, std::vector<Residue>& residues, std
   return PST_OK;
 }
 
+// ---- mmCIF ---------------------------------------------------------------------------------------------------
+// The reference itself has no mmCIF reader (its two entry points take PDB text and ProteinStructureSample .npy files);
+// SURVEY section 8f lists one as the next ingest format.  The `_atom_site` loop goes through the same residue / atom
+// selection as the PDB records above, with the BioPython 1.80 MMCIFParser conventions where the formats differ:
+// chain = auth_asym_id (label_asym_id if absent; may be longer than one character), residue number = auth_seq_id
+// (label_seq_id if absent), atom name = label_atom_id, altloc '.' / '?' = none, insertion code '?' / '.' = none, hetero
+// flag from group_PDB ('W' for HOH / WAT, 'H' for other HETATM: the residue name is not part of the id here), model
+// = pdbx_PDB_model_num (a file with more than one distinct value is rejected like a multi-model PDB file).
+struct CifTok {
+  const char* p;
+  size_t n;
+  bool quoted;
+};
+// Next token at or after `pos` (STAR syntax: whitespace-separated values, '...' / "..." quoted values that end at a
+// quote followed by whitespace, ;...; text fields that start in column 1, # comments).  Returns false at the end.
+bool cif_next(const char* t, size_t len, size_t& pos, CifTok& tok) {
+  for (;;) {
+    while (pos < len && (t[pos] == ' ' || t[pos] == '\t' || t[pos] == '\r' || t[pos] == '\n')) ++pos;
+    if (pos >= len) return false;
+    if (t[pos] == '#') {  // comment to the end of the line
+      while (pos < len && t[pos] != '\n') ++pos;
+      continue;
+    }
+    break;
+  }
+  const bool line_start = pos == 0 || t[pos - 1] == '\n';
+  if (t[pos] == ';' && line_start) {  // text field: up to the next line that starts with ';'
+    const size_t a = pos + 1;
+    size_t q = a;
+    for (;;) {
+      const char* nl = static_cast<const char*>(memchr(t + q, '\n', len - q));
+      if (!nl) { q = len; break; }
+      q = static_cast<size_t>(nl - t) + 1;
+      if (q < len && t[q] == ';') break;
+    }
+    tok = {t + a, (q > a ? q - 1 : a) - a, true};
+    pos = q < len ? q + 1 : len;
+    return true;
+  }
+  if (t[pos] == '\'' || t[pos] == '"') {
+    const char qc = t[pos];
+    const size_t a = pos + 1;
+    size_t q = a;
+    while (q < len && t[q] != '\n' && !(t[q] == qc && (q + 1 >= len || t[q + 1] == ' ' || t[q + 1] == '\t' || t[q + 1] == '\r' || t[q + 1] == '\n'))) ++q;
+    tok = {t + a, q - a, true};
+    pos = q < len && t[q] == qc ? q + 1 : q;
+    return true;
+  }
+  const size_t a = pos;
+  while (pos < len && t[pos] != ' ' && t[pos] != '\t' && t[pos] != '\r' && t[pos] != '\n') ++pos;
+  tok = {t + a, pos - a, false};
+  return true;
+}
+inline bool tok_is(const CifTok& k, const char* s) { return k.n == strlen(s) && memcmp(k.p, s, k.n) == 0; }
+inline bool tok_starts(const CifTok& k, const char* s) { const size_t m = strlen(s); return k.n >= m && memcmp(k.p, s, m) == 0; }
+inline bool tok_null(const CifTok& k) { return !k.quoted && k.n == 1 && (k.p[0] == '.' || k.p[0] == '?'); }
+
+bool looks_like_mmcif(const char* t, size_t len) {
+  size_t pos = 0;
+  CifTok k;
+  return cif_next(t, len, pos, k) && !k.quoted && tok_starts(k, "data_");
+}
+
+int parse_mmcif_text(const char* text, size_t len, std::vector<Residue>& residues, std::vector<int>& order, const char* only_chain) {
+  residues.clear();
+  order.clear();
+  size_t pos = 0;
+  CifTok k;
+  // find the `_atom_site.` loop
+  std::vector<std::string> tags;
+  bool have = cif_next(text, len, pos, k);
+  bool found_loop = false;
+  while (have) {
+    if (!k.quoted && tok_is(k, "loop_")) {
+      tags.clear();
+      have = cif_next(text, len, pos, k);
+      while (have && !k.quoted && k.n > 0 && k.p[0] == '_') {
+        tags.emplace_back(k.p, k.n);
+        have = cif_next(text, len, pos, k);
+      }
+      if (!tags.empty() && tags[0].compare(0, 11, "_atom_site.") == 0) { found_loop = true; break; }
+      continue;  // k is the first value of some other loop (or the next keyword)
+    }
+    have = cif_next(text, len, pos, k);
+  }
+  if (!found_loop) return PST_ERR_PDB_MODEL_COUNT;  // no atoms: zero models, as for a PDB file without ATOM records
+  auto col = [&](const char* name) {
+    for (size_t i = 0; i < tags.size(); ++i)
+      if (tags[i].compare(11, std::string::npos, name) == 0) return static_cast<int>(i);
+    return -1;
+  };
+  auto col2 = [&](const char* a, const char* b) { const int c = col(a); return c >= 0 ? c : col(b); };
+  const int c_group = col("group_PDB"), c_atom = col2("label_atom_id", "auth_atom_id"), c_alt = col("label_alt_id"),
+            c_comp = col2("label_comp_id", "auth_comp_id"), c_chain = col2("auth_asym_id", "label_asym_id"),
+            c_seq = col2("auth_seq_id", "label_seq_id"), c_seq_label = col("label_seq_id"), c_ins = col("pdbx_PDB_ins_code"),
+            c_x = col("Cartn_x"), c_y = col("Cartn_y"), c_z = col("Cartn_z"), c_occ = col("occupancy"),
+            c_model = col("pdbx_PDB_model_num");
+  if (c_atom < 0 || c_comp < 0 || c_chain < 0 || c_seq < 0 || c_x < 0 || c_y < 0 || c_z < 0) return PST_ERR_PDB_MALFORMED;
+  const size_t nc = tags.size();
+  residues.reserve(len / 700 + 16);
+  FlatIndex index(len / 700 + 16);
+  std::vector<std::string> chains;  // in order of first appearance
+  std::vector<long> models;
+  std::vector<CifTok> row(nc);
+  unsigned long long last_key = ~0ull;
+  int last_idx = -1, last_chain = -1;
+  static const uint32_t kHoh = pack_cstr("HOH"), kWat = pack_cstr("WAT");
+  while (have) {
+    if (!k.quoted && (k.p[0] == '_' || tok_is(k, "loop_") || tok_starts(k, "data_") || tok_starts(k, "save_"))) break;
+    size_t got = 0;
+    while (have && got < nc) {
+      row[got++] = k;
+      have = cif_next(text, len, pos, k);
+    }
+    if (got < nc) return PST_ERR_PDB_MALFORMED;  // truncated row
+    if (c_model >= 0) {
+      long mnum = 0;
+      const CifTok& m = row[c_model];
+      for (size_t i = 0; i < m.n; ++i) {
+        if (m.p[i] < '0' || m.p[i] > '9') return PST_ERR_PDB_MALFORMED;
+        mnum = mnum * 10 + (m.p[i] - '0');
+      }
+      bool seen = false;
+      for (long v : models) seen = seen || v == mnum;
+      if (!seen) models.push_back(mnum);
+      if (models.size() > 1) return PST_ERR_PDB_MODEL_COUNT;
+    }
+    const bool is_atom = c_group < 0 || !tok_is(row[c_group], "HETATM");
+    const uint32_t resname = pack_field(row[c_comp].p, row[c_comp].n);
+    int chain_idx = -1;
+    {
+      const CifTok& c = row[c_chain];
+      if (last_chain >= 0 && chains[last_chain].size() == c.n && memcmp(chains[last_chain].data(), c.p, c.n) == 0) chain_idx = last_chain;
+      else {
+        for (size_t i = 0; i < chains.size(); ++i)
+          if (chains[i].size() == c.n && memcmp(chains[i].data(), c.p, c.n) == 0) { chain_idx = static_cast<int>(i); break; }
+        if (chain_idx < 0) {
+          if (chains.size() >= 65535) return PST_ERR_PDB_MALFORMED;
+          chain_idx = static_cast<int>(chains.size());
+          chains.emplace_back(c.p, c.n);
+        }
+      }
+      last_chain = chain_idx;
+    }
+    long long resseq = 0;
+    {
+      const CifTok* q = &row[c_seq];
+      if (tok_null(*q) && c_seq_label >= 0) q = &row[c_seq_label];
+      size_t a = 0;
+      bool neg = false;
+      if (a < q->n && (q->p[a] == '-' || q->p[a] == '+')) { neg = q->p[a] == '-'; ++a; }
+      if (a == q->n || q->n - a > 12) return PST_ERR_PDB_MALFORMED;
+      for (; a < q->n; ++a) {
+        if (q->p[a] < '0' || q->p[a] > '9') return PST_ERR_PDB_MALFORMED;
+        resseq = resseq * 10 + (q->p[a] - '0');
+      }
+      if (neg) resseq = -resseq;
+    }
+    const char icode = (c_ins < 0 || tok_null(row[c_ins]) || row[c_ins].n == 0) ? ' ' : row[c_ins].p[0];
+    // residue id packed into 64 bits: chain index 16 | icode 8 | hetero kind 2 | residue number (offset) 38
+    const unsigned long long het = is_atom ? 0ull : ((resname == kHoh || resname == kWat) ? 1ull : 2ull);
+    const unsigned long long key = ((unsigned long long)chain_idx << 48) | ((unsigned long long)(unsigned char)icode << 40) | (het << 38) |
+                                   ((unsigned long long)(resseq + (1LL << 36)) & ((1ull << 38) - 1));
+    int found = key == last_key ? last_idx : index.find(key);
+    Residue* res;
+    if (found < 0) {
+      found = static_cast<int>(residues.size());
+      index.insert(key, found);
+      residues.emplace_back();
+      res = &residues.back();
+      res->resname = resname;
+      res->chain = 0;
+      res->icode = icode;
+      res->resseq = static_cast<int>(resseq);
+      res->chain_rank = chain_idx;
+      memset(res->atoms, 0, sizeof(res->atoms));
+    } else {
+      res = &residues[found];
+    }
+    last_key = key;
+    last_idx = found;
+    const int slot = atom_slot_field(row[c_atom].p, row[c_atom].n);
+    if (slot < 0) continue;
+    const char altloc = (c_alt < 0 || tok_null(row[c_alt]) || row[c_alt].n == 0) ? ' ' : row[c_alt].p[0];
+    Atom& a = res->atoms[slot];
+    float occ = 1.0f;
+    if (altloc != ' ' && (c_occ < 0 || !parse_float(row[c_occ].p, row[c_occ].n, &occ))) occ = 1.0f;
+    if (!a.set || (altloc != ' ' && a.altloc != ' ' && occ > a.occ)) {
+      float x, y, z;
+      if (!parse_float(row[c_x].p, row[c_x].n, &x) || !parse_float(row[c_y].p, row[c_y].n, &y) || !parse_float(row[c_z].p, row[c_z].n, &z))
+        return PST_ERR_PDB_MALFORMED;
+      a.xyz[0] = x; a.xyz[1] = y; a.xyz[2] = z;
+      a.occ = occ;
+      a.altloc = altloc;
+      a.set = true;
+    }
+  }
+  if (residues.empty()) return PST_ERR_PDB_MODEL_COUNT;
+  int want = -1;  // chain filter (the reference's chain_id argument)
+  if (only_chain && only_chain[0]) {
+    for (size_t i = 0; i < chains.size(); ++i)
+      if (chains[i] == only_chain) want = static_cast<int>(i);
+    if (want < 0) return PST_OK;  // no such chain: nothing is emitted
+  }
+  // chains in order of first appearance, residues in order of first appearance inside their chain (stable bucket sort)
+  std::vector<int> start(chains.size() + 1, 0);
+  for (const Residue& r : residues) ++start[r.chain_rank + 1];
+  for (size_t c = 0; c < chains.size(); ++c) start[c + 1] += start[c];
+  std::vector<int> sorted(residues.size());
+  {
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (size_t r = 0; r < residues.size(); ++r) sorted[fill[residues[r].chain_rank]++] = static_cast<int>(r);
+  }
+  for (int r : sorted) {
+    const Residue& res = residues[r];
+    if (want >= 0 && res.chain_rank != want) continue;
+    if (res.icode != ' ') return PST_ERR_PDB_INSERTION_CODE;
+    bool any = false;
+    for (int s = 0; s < 37; ++s) any = any || res.atoms[s].set;
+    if (any) order.push_back(r);
+  }
+  return PST_OK;
+}
+
+// PDB or mmCIF by content: an mmCIF file starts (after comments) with a `data_` block header
+int parse_any(const char* text, size_t len, std::vector<Residue>& residues, std::vector<int>& order, char only_chain = 0) {
+  if (looks_like_mmcif(text, len)) {
+    const char chain[2] = {only_chain, 0};
+    return parse_mmcif_text(text, len, residues, order, only_chain ? chain : nullptr);
+  }
+  return parse_text(text, len, residues, order, only_chain);
+}
+
 // Phase 2: one residue -> row `row` of the caller's arrays
 void emit_residue(const Residue& res, size_t row, float* atom37_positions, uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype) {
   const Tables& T = tables();
@@ -352,7 +585,23 @@ extern "C" int pst_parse_pdb_chain(const char* text, size_t len, char chain_id, 
   *n_residues_out = 0;
   std::vector<Residue> residues;
   std::vector<int> order;
-  const int rc = parse_text(text, len, residues, order, chain_id);
+  const int rc = parse_any(text, len, residues, order, chain_id);
+  if (rc != PST_OK) return rc;
+  const int n_out = static_cast<int>(order.size());
+  *n_residues_out = n_out;
+  if (!(atom37_positions && gt_exists && atom_exists && aatype)) return PST_OK;
+  const int n_emit = n_out < max_residues ? n_out : (max_residues > 0 ? max_residues : 0);
+  for (int i = 0; i < n_emit; ++i) emit_residue(residues[order[i]], static_cast<size_t>(i), atom37_positions, gt_exists, atom_exists, aatype);
+  return n_out > max_residues ? PST_ERR_WORKSPACE_TOO_SMALL : PST_OK;
+}
+
+extern "C" int pst_parse_mmcif(const char* text, size_t len, const char* chain_id, int max_residues, float* atom37_positions,
+                              uint8_t* gt_exists, uint8_t* atom_exists, int32_t* aatype, int32_t* n_residues_out) {
+  if (!text || !n_residues_out) return PST_ERR_BAD_ARGUMENT;
+  *n_residues_out = 0;
+  std::vector<Residue> residues;
+  std::vector<int> order;
+  const int rc = parse_mmcif_text(text, len, residues, order, chain_id);
   if (rc != PST_OK) return rc;
   const int n_out = static_cast<int>(order.size());
   *n_residues_out = n_out;
@@ -413,7 +662,7 @@ int parse_batch(const char* const* texts, const size_t* text_bytes, const char* 
       text = texts[i];
       len = text_bytes[i];
     }
-    status_out[i] = rc == PST_OK ? parse_text(text, len, residues[i], order[i]) : rc;
+    status_out[i] = rc == PST_OK ? parse_any(text, len, residues[i], order[i]) : rc;
     if (status_out[i] != PST_OK) order[i].clear();
   });
   long long total = 0;

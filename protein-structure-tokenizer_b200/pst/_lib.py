@@ -53,6 +53,8 @@ SIGNATURES = {
     "pst_parse_pdb": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "pst_parse_pdb_chain": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_int32)]),
+    "pst_parse_mmcif": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_int32)]),
     "pst_parse_pdb_batch": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pst_parse_pdb_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -298,8 +298,9 @@ class InferenceRunner:
         def save(files, tokens):
             for f, tok in zip(files, tokens):
                 name = os.path.basename(f).split(".pdb")[0]  # scripts/inference_runner.py:316
-                if name.endswith(".npy"):
-                    name = name[: -len(".npy")]
+                for ext in (".npy", ".cif", ".mmcif"):  # sample files and mmCIF files: the stem names the token file too
+                    if name.endswith(ext):
+                        name = name[: -len(ext)]
                 np.save(os.path.join(token_save_path, name + "_tokens"), np.asarray(tok, np.uint32).reshape(1, -1))
 
         kept: List[np.ndarray] = []  # world > 1: this rank's tokens, in shard order, for the gather

@@ -155,6 +155,17 @@ def structure_from_pdb_file(path: str, chain_id: Optional[str] = None) -> Struct
 _scratch = threading.local()
 
 
+def looks_like_mmcif(data: bytes) -> bool:
+    """True when the first token of the text (after blank lines and # comments) is a `data_` block header: the test the
+    C++ parser applies (csrc/pdb_parse.cc `looks_like_mmcif`)."""
+    for line in data[:4096].splitlines():
+        t = line.strip()
+        if not t or t.startswith(b"#"):
+            continue
+        return t.startswith(b"data_")
+    return False
+
+
 def structure_from_pdb_bytes_native(data: bytes, chain_id: Optional[str] = None) -> StructureSample:
     """The same result through the C++ parser of the C ABI (`pst_parse_pdb`, csrc/pdb_parse.cc): ~100x faster than
     the pure-Python loop above, which is kept as an independent restatement for the tests.  Raises ValueError where
@@ -165,9 +176,11 @@ def structure_from_pdb_bytes_native(data: bytes, chain_id: Optional[str] = None)
 
     lib = _lib.load()
     n = C.c_int32(0)
-    if chain_id is not None and len(chain_id) != 1:
+    is_cif = looks_like_mmcif(data)  # mmCIF text (pst_parse_mmcif): chain ids may be longer than one character there
+    if chain_id is not None and len(chain_id) != 1 and not is_cif:
         raise ValueError(f"chain_id must be one character, got {chain_id!r}")
-    chain = C.c_char(chain_id.encode()) if chain_id is not None else C.c_char(b"\0")
+    chain = C.c_char(chain_id.encode()) if (chain_id is not None and not is_cif) else C.c_char(b"\0")
+    cif_chain = chain_id.encode() if (is_cif and chain_id) else None
     # Per-thread scratch arrays, grown on demand and reused from file to file (the runner parses files side by side:
     # fresh multi-hundred-KB arrays per file are mmap'ed and page-faulted every time, which serialises the threads in the
     # kernel), no scan of the text in Python (the GIL is only released inside the C call): capacity guess = one
@@ -180,8 +193,12 @@ def structure_from_pdb_bytes_native(data: bytes, chain_id: Optional[str] = None)
             sc = _scratch.arrays = (np.empty((grow, 37, 3), np.float32), np.empty((grow, 37), np.uint8),
                                     np.empty((grow, 37), np.uint8), np.empty((grow,), np.int32))
         pos, gt, ex, aa = sc
-        rc = lib.pst_parse_pdb_chain(data, len(data), chain, pos.shape[0], pos.ctypes.data, gt.ctypes.data, ex.ctypes.data,
+        if is_cif:
+            rc = lib.pst_parse_mmcif(data, len(data), cif_chain, pos.shape[0], pos.ctypes.data, gt.ctypes.data, ex.ctypes.data,
                                      aa.ctypes.data, C.byref(n))
+        else:
+            rc = lib.pst_parse_pdb_chain(data, len(data), chain, pos.shape[0], pos.ctypes.data, gt.ctypes.data, ex.ctypes.data,
+                                         aa.ctypes.data, C.byref(n))
         if rc == _lib.PST_ERR_WORKSPACE_TOO_SMALL:
             cap = int(n.value)
             continue

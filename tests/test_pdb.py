@@ -257,3 +257,110 @@ def test_chain_filter_matches_the_reference_argument(built_lib):
             parse(bad, "B")
         with pytest.raises(ValueError):
             parse(bad)
+
+
+# ---- mmCIF (csrc/pdb_parse.cc parse_mmcif_text) --------------------------------------------------------------
+_CIF_COLS = ("group_PDB id type_symbol label_atom_id label_alt_id label_comp_id label_asym_id label_entity_id label_seq_id "
+             "pdbx_PDB_ins_code Cartn_x Cartn_y Cartn_z occupancy B_iso_or_equiv auth_seq_id auth_comp_id auth_asym_id "
+             "auth_atom_id pdbx_PDB_model_num").split()
+
+
+def _cif_quote(v):
+    return f'"{v}"' if ("'" in v or " " in v) else v
+
+
+def _pdb_to_mmcif(text, name="T", chain_map=None, model=1):
+    """The ATOM / HETATM records of a PDB text as an mmCIF `_atom_site` loop (the columns wwPDB files carry)."""
+    rows = []
+    for line in text.splitlines():
+        if line[:6] not in ("ATOM  ", "HETATM"):
+            continue
+        chain = line[21]
+        chain = chain_map.get(chain, chain) if chain_map else chain
+        chain = "A" if chain == " " else chain  # CASP models leave the chain column blank; mmCIF needs a value
+        alt = line[16] if line[16] != " " else "."
+        ins = line[26] if line[26] != " " else "?"
+        atom = _cif_quote(line[12:16].strip())
+        rn = line[17:20].strip()
+        rows.append(" ".join([line[:6].strip(), line[6:11].strip(), (line[76:78].strip() or atom[0]), atom, alt, rn, chain, "1",
+                              line[22:26].strip() if line[:4] == "ATOM" else ".", ins, line[30:38].strip(), line[38:46].strip(),
+                              line[46:54].strip(), line[54:60].strip() or "1.00", line[60:66].strip() or "0.00",
+                              line[22:26].strip(), rn, chain, atom, str(model)]))
+    head = [f"data_{name}", "#", f"_entry.id {name}", "#", "_struct.title", ";a title that mentions loop_ and _atom_site.x", "on two lines",
+            ";", "#", "loop_", "_entity.id", "_entity.type", "1 polymer", "2 water", "#", "loop_"] + [f"_atom_site.{c}" for c in _CIF_COLS]
+    return "\n".join(head + rows + ["#", "loop_", "_pdbx_poly_seq_scheme.asym_id", "_pdbx_poly_seq_scheme.seq_id", "A 1", "#"]) + "\n"
+
+
+def _same_dict(s, d):
+    assert s.nb_residues == d["nb_residues"]
+    assert np.array_equal(s.atom37_positions.astype(np.float64), d["atom37_positions"])
+    assert np.array_equal(s.atom37_gt_exists, d["atom37_gt_exists"])
+    assert np.array_equal(s.atom37_atom_exists, d["atom37_atom_exists"])
+    assert np.array_equal(s.aatype, d["aatype"])
+
+
+def test_mmcif_gives_the_arrays_of_the_same_structure_as_pdb(built_lib):
+    """The tricky PDB text (altlocs, HETATM water, UNK, hydrogens, two chains) converted to mmCIF: the C++ parser returns
+    the arrays it returns for the PDB text, and both equal the independent Python restatements."""
+    from pst import synthetic as syn
+
+    for text in (_tricky_text(), _pdb_from_backbone(syn.make_backbones(3, [75])[0], resname="TRP")):
+        cif = _pdb_to_mmcif(text)
+        a = ppdb.structure_from_pdb_bytes_native(text.encode())
+        b = ppdb.structure_from_pdb_bytes_native(cif.encode())
+        _same_samples(a, b)
+        _same_dict(b, pdb_ref.parse_mmcif(cif))
+        _same_dict(b, pdb_ref.parse_pdb(text))
+
+
+def test_mmcif_chain_ids_models_insertion_codes_and_wrapped_rows(built_lib):
+    text = _tricky_text()
+    cif = _pdb_to_mmcif(text, chain_map={"A": "AA", "B": "B2"})
+    full = ppdb.structure_from_pdb_bytes_native(cif.encode())
+    only = ppdb.structure_from_pdb_bytes_native(cif.encode(), chain_id="B2")  # multi-character chain id
+    _same_dict(only, pdb_ref.parse_mmcif(cif, "B2"))
+    _same_samples(only, ppdb.structure_from_pdb_bytes_native(text.encode(), chain_id="B"))
+    assert 0 < only.nb_residues < full.nb_residues
+    assert ppdb.structure_from_pdb_bytes_native(cif.encode(), chain_id="ZZ").nb_residues == 0
+    # a row may continue on the next line, values may be quoted
+    wrapped = cif.replace(" 1.00 ", " 1.00\n  ").replace(" CA ", " 'CA' ")
+    _same_samples(ppdb.structure_from_pdb_bytes_native(wrapped.encode()), full)
+    # two models -> the reference's single-model error; an insertion code -> its insertion-code error
+    two = cif.rstrip("#\n")
+    rows = [l for l in cif.splitlines() if l.startswith(("ATOM", "HETATM"))]
+    second = "\n".join(r.rsplit(" ", 1)[0] + " 2" for r in rows)
+    head, tail = cif.split(rows[-1])
+    with pytest.raises(ValueError, match="single model"):
+        ppdb.structure_from_pdb_bytes_native((head + rows[-1] + "\n" + second + tail).encode())
+    with pytest.raises(ValueError, match="insertion code"):
+        ppdb.structure_from_pdb_bytes_native(cif.replace(" ? ", " A ", 1).encode())
+    with pytest.raises(ValueError, match="single model"):
+        ppdb.structure_from_pdb_bytes_native(b"data_EMPTY\n_entry.id EMPTY\n")
+    assert two  # keep the linter quiet about the helper variable
+
+
+def test_mmcif_files_go_through_the_batch_and_file_entry_points(built_lib, tmp_path):
+    from pst import synthetic as syn
+
+    bbs = syn.make_backbones(31, [60, 90, 64])
+    texts = [_pdb_from_backbone(bb, resname=rn) for bb, rn in zip(bbs, ("GLY", "ALA", "LYS"))]
+    paths = []
+    for i, t in enumerate(texts):
+        f = tmp_path / (f"s{i}.cif" if i != 1 else f"s{i}.pdb")
+        f.write_text(_pdb_to_mmcif(t) if i != 1 else t)
+        paths.append(str(f))
+    out = ppdb.structures_from_pdb_files_native(paths, 2)
+    for o, t in zip(out, texts):
+        _same_samples(o, ppdb.structure_from_pdb_bytes_native(t.encode()))
+
+
+def test_mmcif_of_the_bundled_casp14_files(built_lib):
+    import glob
+
+    files = sorted(glob.glob("/root/reference/casp14_pdbs/*.pdb"))
+    if not files:
+        pytest.skip("reference checkout not present (development container only)")
+    for f in files[:8]:
+        with open(f) as fh:
+            text = fh.read()
+        _same_samples(ppdb.structure_from_pdb_bytes_native(_pdb_to_mmcif(text).encode()), ppdb.structure_from_pdb_bytes_native(text.encode()))
