@@ -13,13 +13,17 @@ def test_tokenize_directory_of_pdbs(built_lib, tmp_path):
     from pst import synthetic as syn
     from pst.config import load_config
     from pst.inference_runner import InferenceRunner
-    from test_pdb import _pdb_from_backbone
+    from test_pdb import _pdb_from_backbone, _pdb_to_mmcif
 
     pdb_dir = tmp_path / "pdbs"
     pdb_dir.mkdir()
     bbs = syn.make_backbones(31, [70, 120, 55])
     for i, bb in enumerate(bbs):
-        (pdb_dir / f"S{i}.pdb").write_text(_pdb_from_backbone(bb))
+        text = _pdb_from_backbone(bb)
+        if i == 1:  # an mmCIF file next to the PDB files: parsed by content, token file named by its stem
+            (pdb_dir / f"S{i}.cif").write_text(_pdb_to_mmcif(text))
+        else:
+            (pdb_dir / f"S{i}.pdb").write_text(text)
     cfg = load_config("vq3d_inference", overrides=["model=gnn/ablation_4k_df_1.yaml", "data=ablation_df_1.yaml"])
     runner = InferenceRunner()
     devices, n = runner.prepare_devices("gpu")
