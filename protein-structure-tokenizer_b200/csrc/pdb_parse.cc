@@ -335,18 +335,38 @@ struct CifTok {
 };
 // Next token at or after `pos` (STAR syntax: whitespace-separated values, '...' / "..." quoted values that end at a
 // quote followed by whitespace, ;...; text fields that start in column 1, # comments).  Returns false at the end.
+struct CifWs {
+  bool ws[256];
+  CifWs() {
+    for (int i = 0; i < 256; ++i) ws[i] = false;
+    ws[(unsigned char)' '] = ws[(unsigned char)'\t'] = ws[(unsigned char)'\r'] = ws[(unsigned char)'\n'] = true;
+  }
+};
+const bool* cif_ws() {
+  static const CifWs t;
+  return t.ws;
+}
 bool cif_next(const char* t, size_t len, size_t& pos, CifTok& tok) {
+  const bool* ws = cif_ws();
   for (;;) {
-    while (pos < len && (t[pos] == ' ' || t[pos] == '\t' || t[pos] == '\r' || t[pos] == '\n')) ++pos;
+    while (pos < len && ws[(unsigned char)t[pos]]) ++pos;
     if (pos >= len) return false;
     if (t[pos] == '#') {  // comment to the end of the line
-      while (pos < len && t[pos] != '\n') ++pos;
+      const char* nl = static_cast<const char*>(memchr(t + pos, '\n', len - pos));
+      pos = nl ? static_cast<size_t>(nl - t) : len;
       continue;
     }
     break;
   }
+  const char c0 = t[pos];
+  if (c0 != ';' && c0 != '\'' && c0 != '"') {  // the common case: a bare value
+    const size_t a = pos;
+    while (pos < len && !ws[(unsigned char)t[pos]]) ++pos;
+    tok = {t + a, pos - a, false};
+    return true;
+  }
   const bool line_start = pos == 0 || t[pos - 1] == '\n';
-  if (t[pos] == ';' && line_start) {  // text field: up to the next line that starts with ';'
+  if (c0 == ';' && line_start) {  // text field: up to the next line that starts with ';'
     const size_t a = pos + 1;
     size_t q = a;
     for (;;) {
@@ -359,17 +379,16 @@ bool cif_next(const char* t, size_t len, size_t& pos, CifTok& tok) {
     pos = q < len ? q + 1 : len;
     return true;
   }
-  if (t[pos] == '\'' || t[pos] == '"') {
-    const char qc = t[pos];
+  if (c0 == '\'' || c0 == '"') {
     const size_t a = pos + 1;
     size_t q = a;
-    while (q < len && t[q] != '\n' && !(t[q] == qc && (q + 1 >= len || t[q + 1] == ' ' || t[q + 1] == '\t' || t[q + 1] == '\r' || t[q + 1] == '\n'))) ++q;
+    while (q < len && t[q] != '\n' && !(t[q] == c0 && (q + 1 >= len || ws[(unsigned char)t[q + 1]]))) ++q;
     tok = {t + a, q - a, true};
-    pos = q < len && t[q] == qc ? q + 1 : q;
+    pos = q < len && t[q] == c0 ? q + 1 : q;
     return true;
   }
-  const size_t a = pos;
-  while (pos < len && t[pos] != ' ' && t[pos] != '\t' && t[pos] != '\r' && t[pos] != '\n') ++pos;
+  const size_t a = pos;  // a ';' that is not at the start of a line is an ordinary character
+  while (pos < len && !ws[(unsigned char)t[pos]]) ++pos;
   tok = {t + a, pos - a, false};
   return true;
 }
