@@ -364,3 +364,25 @@ def test_mmcif_of_the_bundled_casp14_files(built_lib):
         with open(f) as fh:
             text = fh.read()
         _same_samples(ppdb.structure_from_pdb_bytes_native(_pdb_to_mmcif(text).encode()), ppdb.structure_from_pdb_bytes_native(text.encode()))
+
+
+def test_mmcif_detection_by_content_agrees_between_the_wrapper_and_the_library(built_lib):
+    """Leading blank lines and # comments before the `data_` header; a PDB text that merely mentions data_ later."""
+    import ctypes as C
+
+    from pst import _lib
+
+    text = _tricky_text()
+    cif = "\n# produced by a test\n\n" + _pdb_to_mmcif(text)
+    assert ppdb.looks_like_mmcif(cif.encode()) and not ppdb.looks_like_mmcif(text.encode())
+    pdb_with_remark = "REMARK data_block mentioned in a remark\n" + text
+    assert not ppdb.looks_like_mmcif(pdb_with_remark.encode())
+    ref = ppdb.structure_from_pdb_bytes_native(text.encode())
+    _same_samples(ppdb.structure_from_pdb_bytes_native(cif.encode()), ref)
+    _same_samples(ppdb.structure_from_pdb_bytes_native(pdb_with_remark.encode()), ref)
+    # the plain PDB entry point of the C ABI takes the mmCIF text as well (detection inside the library)
+    lib = _lib.load()
+    n = C.c_int32(0)
+    data = cif.encode()
+    assert lib.pst_parse_pdb(data, len(data), 0, None, None, None, None, C.byref(n)) == 0
+    assert n.value == ref.nb_residues
